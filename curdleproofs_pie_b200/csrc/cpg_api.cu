@@ -1,0 +1,542 @@
+// libcpg.so - C ABI (include/cpg.h) over the sm_100a kernels.  One functor (msm.cuh) = one kernel.
+//
+// Built two ways from this one file:
+//   nvcc -gencode arch=compute_100a,code=sm_100a  -> curdleproofs_pie_b200/lib/libcpg.so   (the product)
+//   g++ -x c++ -DCPG_HOST_EMU                     -> tests/_build/libcpg_hostseam.so       (TEST SEAM ONLY:
+//        every "kernel" becomes a host loop over the same per-thread functor with the PTX carry flag
+//        emulated, so the CPU-only test tier can exercise the exact launch logic; the product package
+//        never loads it and refuses to run without a CUDA device)
+#include "../../include/cpg.h"
+#include "msm.cuh"
+
+#include <atomic>
+#include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#ifndef CPG_HOST_EMU
+#include <cuda_runtime.h>
+#endif
+
+using namespace cpg;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+int g_device = -1;
+std::mutex g_init_mu;
+Jac* g_generator = nullptr;  // device copy of the generator (Jacobian)
+
+int fail(const std::string& msg) { g_err = msg; return 1; }
+
+#ifndef CPG_HOST_EMU
+cudaStream_t g_stream = nullptr;       // library default stream
+thread_local cudaStream_t t_stream = nullptr;
+thread_local bool t_stream_set = false;
+cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+cudaStream_t cur() { return t_stream_set ? t_stream : g_stream; }
+
+int ck(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    return fail(std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(x) do { if (int rc_ = ck((x), #x)) return rc_; } while (0)
+
+template <class F, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_each(const F f, uint64_t n) {
+    uint64_t t = blockIdx.x * (uint64_t)BLOCK + threadIdx.x;
+    if (t < n) f(t);
+}
+template <int BLOCK = 128, class F>
+int launch(const F& f, uint64_t n) {
+    if (!n) return 0;
+    uint64_t grid = (n + BLOCK - 1) / BLOCK;
+    if (grid > 0x7fffffffULL) return fail("launch: grid too large");
+    k_each<F, BLOCK><<<(unsigned)grid, BLOCK, 0, cur()>>>(f, n);
+    g_launches++;
+    return ck(cudaGetLastError(), "kernel launch");
+}
+void* scratch_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocAsync(&p, bytes ? bytes : 1, cur()) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void scratch_free(void* p) { if (p) cudaFreeAsync(p, cur()); }
+#else
+// ---- host emulation (test seam) ----
+template <int BLOCK = 128, class F>
+int launch(const F& f, uint64_t n) {
+    g_launches++;
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t t = 0; t < (int64_t)n; t++) f((uint64_t)t);
+    return 0;
+}
+void* scratch_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void scratch_free(void* p) { free(p); }
+#endif
+
+int need_init() {
+    if (g_device < 0) return fail("cpg_init has not been called (no CUDA device selected)");
+    return 0;
+}
+#define NEED_INIT() do { if (int rc_ = need_init()) return rc_; } while (0)
+
+struct Scratch {  // frees on scope exit (stream-ordered)
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) scratch_free(p); }
+    template <class T> T* get(size_t count) {
+        void* p = scratch_alloc(count * sizeof(T));
+        if (p) ptrs.push_back(p);
+        return (T*)p;
+    }
+};
+
+uint32_t windows_for(uint32_t c) { return (256 + c - 1) / c; }
+
+Recode make_recode(uint32_t c) {
+    Recode rc; rc.c = c; rc.W = windows_for(c);
+    for (int i = 0; i < 8; i++) rc.C[i] = 0;
+    for (uint32_t w = 0; w + 1 < rc.W; w++) { uint32_t bit = c - 1 + c * w; rc.C[bit >> 5] |= 1u << (bit & 31); }
+    return rc;
+}
+
+// modmul-count model of the bucket method: n*W mixed adds + 2*NB*W full adds + Horner
+uint32_t pick_window(size_t n) {
+    double best = 1e300; uint32_t bc = 4;
+    for (uint32_t c = 3; c <= 16; c++) {
+        double W = windows_for(c), NB = (double)(1u << (c - 1));
+        double cost = (double)n * W * 10.0 + W * NB * 2.0 * 14.0 + W * (c * 9.0 + 14.0);
+        if (cost < best) { best = cost; bc = c; }
+    }
+    return bc;
+}
+
+const uint8_t GEN48[48] = {0x97, 0xf1, 0xd3, 0xa7, 0x31, 0x97, 0xd7, 0x94, 0x26, 0x95, 0x63, 0x8c, 0x4f, 0xa9, 0xac, 0x0f,
+                           0xc3, 0x68, 0x8c, 0x4f, 0x97, 0x74, 0xb9, 0x05, 0xa1, 0x4e, 0x3a, 0x3f, 0x17, 0x1b, 0xac, 0x58,
+                           0x6c, 0x55, 0xe8, 0x3f, 0xf9, 0x7a, 0x1a, 0xef, 0xfb, 0x3a, 0xf0, 0x0a, 0xdb, 0x22, 0xc6, 0xbb};
+
+struct FixedTable {
+    FixedShape s;
+    Aff* table;      // device
+    size_t bytes;
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* cpg_last_error(void) { return g_err.c_str(); }
+
+#ifndef CPG_HOST_EMU
+const char* cpg_backend(void) { return "cuda-sm_100a"; }
+int cpg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+#else
+const char* cpg_backend(void) { return "host-emulation-test-seam"; }
+int cpg_device_count(void) { return 1; }
+#endif
+
+int cpg_init(int device) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (g_device >= 0) {
+        if (g_device != device) return fail("cpg_init: already initialised on another device (one process per GPU)");
+        return 0;
+    }
+#ifndef CPG_HOST_EMU
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail("cpg_init: no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail("cpg_init: device index out of range");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("cpg_init: kernels are built for sm_100a (B200) only");
+    CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&g_ev0));
+    CK(cudaEventCreate(&g_ev1));
+    // keep freed scratch in the pool instead of returning it to the driver after every call
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = ~0ULL;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+#endif
+    g_device = device;
+    // device-resident generator: decompress its wire encoding once
+    uint8_t* d48 = (uint8_t*)cpg_malloc(48);
+    Aff* daff = (Aff*)cpg_malloc(sizeof(Aff));
+    uint8_t* derr = (uint8_t*)cpg_malloc(1);
+    g_generator = (Jac*)cpg_malloc(sizeof(Jac));
+    if (!d48 || !daff || !derr || !g_generator) { g_device = -1; return fail("cpg_init: allocation failed"); }
+    int rc = cpg_h2d(d48, GEN48, 48);
+    if (!rc) rc = cpg_g1_decompress(d48, 1, 0, daff, derr);
+    if (!rc) rc = cpg_g1_aff_to_jac(daff, 1, g_generator);
+    uint8_t e = 1;
+    if (!rc) rc = cpg_d2h(&e, derr, 1);
+    cpg_free(d48); cpg_free(daff); cpg_free(derr);
+    if (rc || e) { g_device = -1; return fail("cpg_init: generator self-check failed: " + g_err); }
+    return 0;
+}
+
+int cpg_set_stream(void* s) {
+#ifndef CPG_HOST_EMU
+    t_stream = (cudaStream_t)s; t_stream_set = (s != nullptr);
+#else
+    (void)s;
+#endif
+    return 0;
+}
+int cpg_sync(void) {
+    NEED_INIT();
+#ifndef CPG_HOST_EMU
+    CK(cudaStreamSynchronize(cur()));
+#endif
+    return 0;
+}
+void* cpg_malloc(size_t bytes) {
+    if (need_init()) return nullptr;
+#ifndef CPG_HOST_EMU
+    void* p = nullptr;
+    if (ck(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc")) return nullptr;
+    return p;
+#else
+    return malloc(bytes ? bytes : 1);
+#endif
+}
+int cpg_free(void* p) {
+    if (!p) return 0;
+#ifndef CPG_HOST_EMU
+    CK(cudaFree(p));
+#else
+    free(p);
+#endif
+    return 0;
+}
+int cpg_memset(void* p, int v, size_t bytes) {
+    NEED_INIT();
+#ifndef CPG_HOST_EMU
+    CK(cudaMemsetAsync(p, v, bytes, cur()));
+#else
+    memset(p, v, bytes);
+#endif
+    return 0;
+}
+int cpg_h2d(void* d, const void* h, size_t bytes) {
+    NEED_INIT();
+#ifndef CPG_HOST_EMU
+    CK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, cur()));
+#else
+    memcpy(d, h, bytes);
+#endif
+    return 0;
+}
+int cpg_d2h(void* h, const void* d, size_t bytes) {
+    NEED_INIT();
+#ifndef CPG_HOST_EMU
+    CK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, cur()));
+    CK(cudaStreamSynchronize(cur()));
+#else
+    memcpy(h, d, bytes);
+#endif
+    return 0;
+}
+int cpg_d2d(void* dst, const void* src, size_t bytes) {
+    NEED_INIT();
+#ifndef CPG_HOST_EMU
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, cur()));
+#else
+    memmove(dst, src, bytes);
+#endif
+    return 0;
+}
+void* cpg_host_alloc(size_t bytes) {
+#ifndef CPG_HOST_EMU
+    void* p = nullptr;
+    if (ck(cudaMallocHost(&p, bytes ? bytes : 1), "cudaMallocHost")) return nullptr;
+    return p;
+#else
+    return malloc(bytes ? bytes : 1);
+#endif
+}
+int cpg_host_free(void* p) {
+    if (!p) return 0;
+#ifndef CPG_HOST_EMU
+    CK(cudaFreeHost(p));
+#else
+    free(p);
+#endif
+    return 0;
+}
+int cpg_timer_start(void) {
+    NEED_INIT();
+#ifndef CPG_HOST_EMU
+    CK(cudaEventRecord(g_ev0, cur()));
+#endif
+    return 0;
+}
+int cpg_timer_stop(float* ms) {
+    NEED_INIT();
+    *ms = 0.f;
+#ifndef CPG_HOST_EMU
+    CK(cudaEventRecord(g_ev1, cur()));
+    CK(cudaEventSynchronize(g_ev1));
+    CK(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+#endif
+    return 0;
+}
+uint64_t cpg_launch_count(void) { return g_launches.load(); }
+
+/* ---- serialisation ---- */
+int cpg_g1_decompress(const uint8_t* d_in, size_t k, int check, void* d_out, uint8_t* d_err) {
+    NEED_INIT();
+    return launch(Decompress{d_in, check, (Aff*)d_out, d_err}, k);
+}
+int cpg_g1_compress(const void* d_jac, size_t k, uint8_t* d_out) {
+    NEED_INIT();
+    return launch(CompressJac{(const Jac*)d_jac, d_out}, k);
+}
+int cpg_g1_compress_aff(const void* d_aff, size_t k, uint8_t* d_out) {
+    NEED_INIT();
+    return launch(CompressAff{(const Aff*)d_aff, d_out}, k);
+}
+int cpg_g1_aff_to_jac(const void* d_aff, size_t k, void* d_out) {
+    NEED_INIT();
+    return launch(AffToJac{(const Aff*)d_aff, (Jac*)d_out}, k);
+}
+int cpg_g1_jac_to_aff(const void* d_jac, size_t k, void* d_out) {
+    NEED_INIT();
+    return launch(JacToAff{(const Jac*)d_jac, (Aff*)d_out}, k);
+}
+int cpg_g1_generator(void* d_out) {
+    NEED_INIT();
+    return cpg_d2d(d_out, g_generator, sizeof(Jac));
+}
+int cpg_g1_identity(void* d_out) {
+    NEED_INIT();
+    Jac h;
+    for (int i = 0; i < 12; i++) { h.X.l[i] = H_FQ_R[i]; h.Y.l[i] = H_FQ_R[i]; h.Z.l[i] = 0; }
+#ifndef CPG_HOST_EMU
+    // pageable source: the copy is staged before the call returns
+    CK(cudaMemcpyAsync(d_out, &h, sizeof h, cudaMemcpyHostToDevice, cur()));
+    CK(cudaStreamSynchronize(cur()));
+    return 0;
+#else
+    memcpy(d_out, &h, sizeof h);
+    return 0;
+#endif
+}
+
+/* ---- element-wise group law ---- */
+int cpg_g1_add(const void* a, const void* b, size_t k, void* out) {
+    NEED_INIT();
+    return launch(AddPoints{(const Jac*)a, (const Jac*)b, (Jac*)out, 0}, k);
+}
+int cpg_g1_sub(const void* a, const void* b, size_t k, void* out) {
+    NEED_INIT();
+    return launch(AddPoints{(const Jac*)a, (const Jac*)b, (Jac*)out, 1}, k);
+}
+int cpg_g1_neg(const void* a, size_t k, void* out) {
+    NEED_INIT();
+    return launch(NegPoints{(const Jac*)a, (Jac*)out}, k);
+}
+int cpg_g1_eq(const void* a, const void* b, size_t k, uint8_t* out) {
+    NEED_INIT();
+    return launch(EqPoints{(const Jac*)a, (const Jac*)b, out}, k);
+}
+int cpg_g1_is_identity(const void* a, size_t k, uint8_t* out) {
+    NEED_INIT();
+    return launch(IsInfPoints{(const Jac*)a, out}, k);
+}
+int cpg_g1_mul(const void* p, const uint8_t* scalars, size_t k, size_t group, void* out) {
+    NEED_INIT();
+    if (!group) return fail("cpg_g1_mul: group must be >= 1");
+    return launch(MulPoints{(const Jac*)p, (const uint32_t*)scalars, group, (Jac*)out}, k);
+}
+int cpg_g1_fold(const void* L, const void* R, const uint8_t* x, size_t rows, size_t m, void* out) {
+    NEED_INIT();
+    if (!m) return 0;
+    return launch(FoldPoints{(const Jac*)L, (const Jac*)R, (const uint32_t*)x, m, (Jac*)out}, rows * m);
+}
+
+/* ---- batched Pippenger ---- */
+int cpg_g1_msm_batched(const void* d_bases, size_t base_stride, const uint8_t* d_scalars,
+                       size_t B, size_t n, int window, void* d_out) {
+    NEED_INIT();
+    if (!B) return 0;
+    if (n == 0) {  // empty sums are the identity (compute_MSM returns Z1 for empty input)
+        for (size_t b = 0; b < B; b++) if (int rc = cpg_g1_identity((Jac*)d_out + b)) return rc;
+        return 0;
+    }
+    if (n >= 0x7fffffffULL) return fail("cpg_g1_msm_batched: n too large");
+    uint32_t c = window > 0 ? (uint32_t)window : pick_window(n);
+    if (c < 2 || c > 20) return fail("cpg_g1_msm_batched: window must be in [2, 20]");
+    Recode rc = make_recode(c);
+    MsmShape s; s.n = (uint32_t)n; s.c = c; s.W = rc.W; s.NB = 1u << (c - 1); s.base_stride = base_stride;
+    // bound scratch to ~6 GiB per chunk of MSMs
+    size_t per_msm = (size_t)s.W * ((size_t)(s.NB + 1) * 4 + (size_t)n * 4 + (size_t)s.NB * sizeof(Xyzz) + sizeof(Xyzz));
+    size_t chunk = (size_t)6 << 30;
+    chunk = chunk / per_msm; if (chunk < 1) chunk = 1; if (chunk > B) chunk = B;
+    for (size_t b0 = 0; b0 < B; b0 += chunk) {
+        size_t nb = B - b0 < chunk ? B - b0 : chunk;
+        s.B = (uint32_t)nb;
+        uint64_t BW = (uint64_t)nb * s.W;
+        Scratch sc;
+        uint32_t* boff = sc.get<uint32_t>(BW * (s.NB + 1));
+        uint32_t* sorted = sc.get<uint32_t>(BW * n);
+        Xyzz* buckets = sc.get<Xyzz>(BW * s.NB);
+        Xyzz* wsum = sc.get<Xyzz>(BW);
+        if (!boff || !sorted || !buckets || !wsum) return fail("cpg_g1_msm_batched: scratch allocation failed");
+        const uint32_t* ks = (const uint32_t*)d_scalars + (uint64_t)b0 * n * 8;
+        const Aff* bases = (const Aff*)d_bases + (uint64_t)b0 * base_stride;
+        if (int r = launch(SortDigits{s, rc, ks, boff, sorted}, BW)) return r;
+        if (int r = launch(BucketAccumulate{s, bases, boff, sorted, nullptr, buckets}, BW * s.NB)) return r;
+        if (int r = launch(WindowReduce{s, buckets, wsum}, BW)) return r;
+        if (int r = launch(Horner{s, wsum, (Jac*)d_out + b0}, nb)) return r;
+    }
+    return 0;
+}
+
+/* ---- fixed-base tables ---- */
+void* cpg_fixed_table_create(const void* d_bases, size_t nb, int window) {
+    if (need_init()) return nullptr;
+    if (!nb) { fail("cpg_fixed_table_create: empty base vector"); return nullptr; }
+    uint32_t c = window > 0 ? (uint32_t)window : 8;
+    if (c < 2 || c > 16) { fail("cpg_fixed_table_create: window must be in [2, 16]"); return nullptr; }
+    FixedTable* t = new FixedTable;
+    t->s.nb = (uint32_t)nb; t->s.c = c; t->s.W = windows_for(c); t->s.NB = 1u << (c - 1);
+    uint64_t entries = (uint64_t)nb * t->s.W * t->s.NB;
+    t->bytes = entries * sizeof(Aff);
+    t->table = (Aff*)cpg_malloc(t->bytes);
+    Jac* rows = (Jac*)cpg_malloc(entries * sizeof(Jac));
+    int rc = (!t->table || !rows) ? fail("cpg_fixed_table_create: allocation failed") : 0;
+    if (!rc) rc = launch(FixedTableRows{t->s, (const Aff*)d_bases, rows}, (uint64_t)nb * t->s.W);
+    if (!rc) rc = launch(JacToAff{rows, t->table}, entries);
+    if (!rc) rc = cpg_sync();
+    cpg_free(rows);
+    if (rc) { cpg_free(t->table); delete t; return nullptr; }
+    return t;
+}
+int cpg_fixed_table_free(void* table) {
+    if (!table) return 0;
+    FixedTable* t = (FixedTable*)table;
+    cpg_free(t->table);
+    delete t;
+    return 0;
+}
+size_t cpg_fixed_table_bytes(const void* table) { return table ? ((const FixedTable*)table)->bytes : 0; }
+
+int cpg_g1_msm_fixed_batched(const void* table, const uint8_t* d_scalars, size_t B, int accumulate, void* d_out) {
+    NEED_INIT();
+    if (!table) return fail("cpg_g1_msm_fixed_batched: null table");
+    if (!B) return 0;
+    const FixedTable* t = (const FixedTable*)table;
+    Recode rc = make_recode(t->s.c);
+    Scratch sc;
+    Xyzz* partial = sc.get<Xyzz>((uint64_t)B * t->s.W);
+    if (!partial) return fail("cpg_g1_msm_fixed_batched: scratch allocation failed");
+    if (int r = launch(FixedMsmWindow{t->s, rc, (uint32_t)B, t->table, (const uint32_t*)d_scalars, partial}, (uint64_t)B * t->s.W)) return r;
+    return launch(SumWindows{t->s.W, partial, (Jac*)d_out, accumulate}, B);
+}
+
+/* ---- Fr vectors ---- */
+int cpg_fr_add(const uint8_t* a, const uint8_t* b, size_t k, uint8_t* out) {
+    NEED_INIT();
+    return launch(FrBinary{(const uint32_t*)a, (const uint32_t*)b, (uint32_t*)out, 0}, k);
+}
+int cpg_fr_sub(const uint8_t* a, const uint8_t* b, size_t k, uint8_t* out) {
+    NEED_INIT();
+    return launch(FrBinary{(const uint32_t*)a, (const uint32_t*)b, (uint32_t*)out, 1}, k);
+}
+int cpg_fr_mul(const uint8_t* a, const uint8_t* b, size_t k, uint8_t* out) {
+    NEED_INIT();
+    return launch(FrBinary{(const uint32_t*)a, (const uint32_t*)b, (uint32_t*)out, 2}, k);
+}
+int cpg_fr_inverse(const uint8_t* a, size_t k, uint8_t* out) {
+    NEED_INIT();
+    return launch(FrInverse{(const uint32_t*)a, (uint32_t*)out}, k);
+}
+
+/* ---- integer-pipe microbenchmark ---- */
+#ifndef CPG_HOST_EMU
+}  // extern "C"
+namespace {
+// 8 independent accumulator chains per thread so the dependent-issue latency (4 clk) is covered.
+__global__ void __launch_bounds__(256) k_imad_wide(uint64_t iters, uint32_t a0, uint32_t b0, uint64_t* sink) {
+    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+    uint64_t acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = j + threadIdx.x;
+    for (uint64_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= acc[j];
+    if (s == 0x123456789abcdefULL) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_imad_lohi(uint64_t iters, uint32_t a0, uint32_t b0, uint64_t* sink) {
+    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
+    uint32_t lo[8], hi[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { lo[j] = j + threadIdx.x; hi[j] = j; }
+    for (uint64_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[j]) : "r"(a), "r"(b));
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= lo[j] ^ hi[j];
+    if (s == 0x12345678u) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_fq_mul_chain(uint64_t iters, uint64_t* sink) {
+    Fq x = Fq::one(), y = Fq::one();
+    x.l[0] += threadIdx.x; y.l[1] += blockIdx.x;
+    Fq u = y, v = x;
+    for (uint64_t i = 0; i < iters; i++) { x = mul(x, y); u = mul(u, v); }
+    if ((x.l[0] ^ u.l[3]) == 0x12345678u) sink[0] = x.l[1];
+}
+}  // namespace
+extern "C" {
+int cpg_bench_int_pipe(int kind, uint64_t iters, double* per_second, float* ms) {
+    NEED_INIT();
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g_device));
+    int blocks = prop.multiProcessorCount * 8, threads = 256;
+    uint64_t* sink = (uint64_t*)cpg_malloc(8);
+    if (!sink) return 1;
+    for (int rep = 0; rep < 2; rep++) {  // first pass warms up
+        CK(cudaEventRecord(g_ev0, cur()));
+        if (kind == 0) k_imad_wide<<<blocks, threads, 0, cur()>>>(iters, 12345u, 6789u, sink);
+        else if (kind == 1) k_imad_lohi<<<blocks, threads, 0, cur()>>>(iters, 12345u, 6789u, sink);
+        else k_fq_mul_chain<<<blocks, threads, 0, cur()>>>(iters, sink);
+        g_launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(g_ev1, cur()));
+        CK(cudaEventSynchronize(g_ev1));
+        CK(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+    }
+    double ops = (double)blocks * threads * (double)iters * (kind == 2 ? 2.0 : 8.0);
+    *per_second = ops / (*ms * 1e-3);
+    cpg_free(sink);
+    return 0;
+}
+#else
+int cpg_bench_int_pipe(int, uint64_t, double* per_second, float* ms) {
+    *per_second = 0; *ms = 0;
+    return fail("cpg_bench_int_pipe: needs the CUDA build");
+}
+#endif
+
+}  // extern "C"

@@ -1,0 +1,146 @@
+// BLS12-381 base field Fq (12 x u32) and scalar field Fr (8 x u32), Montgomery form.
+// Constants verified numerically in SURVEY.md A.1.
+#pragma once
+#include "bigint.cuh"
+
+namespace cpg {
+
+#if defined(__CUDACC__)
+#define CPG_CONST_DECL __device__ __constant__
+#else
+#define CPG_CONST_DECL static const
+#endif
+
+// Device code reads the __constant__ copies (IMAD takes a constant-bank operand directly);
+// host code (unit tests of the same algorithms) reads the plain arrays.
+#define CPG_FQ_P_INIT {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, \
+                       0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau}
+#define CPG_FQ_R_INIT {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u, \
+                       0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u}
+#define CPG_FQ_R2_INIT {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu, \
+                        0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u}
+#define CPG_FR_P_INIT {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u}
+#define CPG_FR_R_INIT {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau, 0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u}
+#define CPG_FR_R2_INIT {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu, 0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u}
+
+static const uint32_t H_FQ_P[12] = CPG_FQ_P_INIT;
+static const uint32_t H_FQ_R[12] = CPG_FQ_R_INIT;
+static const uint32_t H_FQ_R2[12] = CPG_FQ_R2_INIT;
+static const uint32_t H_FR_P[8] = CPG_FR_P_INIT;
+static const uint32_t H_FR_R[8] = CPG_FR_R_INIT;
+static const uint32_t H_FR_R2[8] = CPG_FR_R2_INIT;
+#if defined(__CUDACC__)
+static __device__ __constant__ uint32_t D_FQ_P[12] = CPG_FQ_P_INIT;
+static __device__ __constant__ uint32_t D_FQ_R[12] = CPG_FQ_R_INIT;
+static __device__ __constant__ uint32_t D_FQ_R2[12] = CPG_FQ_R2_INIT;
+static __device__ __constant__ uint32_t D_FR_P[8] = CPG_FR_P_INIT;
+static __device__ __constant__ uint32_t D_FR_R[8] = CPG_FR_R_INIT;
+static __device__ __constant__ uint32_t D_FR_R2[8] = CPG_FR_R2_INIT;
+#endif
+
+#ifdef __CUDA_ARCH__
+#define CPG_SEL(name) D_##name
+#else
+#define CPG_SEL(name) H_##name
+#endif
+
+struct FqCfg {
+    static constexpr int N = 12;
+    static constexpr uint32_t INV = 0xfffcfffdu;  // -p^-1 mod 2^32
+    static CPG_HD const uint32_t* p() { return CPG_SEL(FQ_P); }
+    static CPG_HD const uint32_t* one() { return CPG_SEL(FQ_R); }
+    static CPG_HD const uint32_t* r2() { return CPG_SEL(FQ_R2); }
+};
+struct FrCfg {
+    static constexpr int N = 8;
+    static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
+    static CPG_HD const uint32_t* p() { return CPG_SEL(FR_P); }
+    static CPG_HD const uint32_t* one() { return CPG_SEL(FR_R); }
+    static CPG_HD const uint32_t* r2() { return CPG_SEL(FR_R2); }
+};
+
+template <class C>
+struct Fp {
+    static constexpr int N = C::N;
+    uint32_t l[N];
+
+    static CPG_HD Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = 0;
+        return r;
+    }
+    static CPG_HD Fp one() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = C::one()[i];
+        return r;
+    }
+    CPG_HD bool is_zero() const { return is_zero_n<N>(l); }
+    CPG_HD bool operator==(const Fp& o) const { return eq_n<N>(l, o.l); }
+    CPG_HD bool operator!=(const Fp& o) const { return !eq_n<N>(l, o.l); }
+};
+
+template <class C> CPG_HD Fp<C> mul(const Fp<C>& a, const Fp<C>& b) { Fp<C> r; mont_mul_n<C::N>(r.l, a.l, b.l, C::p(), C::INV); return r; }
+template <class C> CPG_HD Fp<C> sqr(const Fp<C>& a) { Fp<C> r; mont_mul_n<C::N>(r.l, a.l, a.l, C::p(), C::INV); return r; }
+template <class C> CPG_HD Fp<C> add(const Fp<C>& a, const Fp<C>& b) { Fp<C> r; mod_add_n<C::N>(r.l, a.l, b.l, C::p()); return r; }
+template <class C> CPG_HD Fp<C> sub(const Fp<C>& a, const Fp<C>& b) { Fp<C> r; mod_sub_n<C::N>(r.l, a.l, b.l, C::p()); return r; }
+template <class C> CPG_HD Fp<C> dbl(const Fp<C>& a) { return add(a, a); }
+template <class C> CPG_HD Fp<C> neg(const Fp<C>& a) { return sub(Fp<C>::zero(), a); }
+// plain integer (< p) -> Montgomery form and back
+template <class C> CPG_HD Fp<C> to_mont(const Fp<C>& a) { Fp<C> r2; for (int i = 0; i < C::N; i++) r2.l[i] = C::r2()[i]; return mul(a, r2); }
+template <class C> CPG_HD Fp<C> from_mont(const Fp<C>& a) { Fp<C> o = Fp<C>::zero(); o.l[0] = 1; return mul(a, o); }
+// true iff the plain integer a is < p
+template <class C> CPG_HD bool is_canonical(const Fp<C>& a) { return !geq_n<C::N>(a.l, C::p()); }
+
+// a^e for a public exponent given as little-endian u32 words (left-to-right, 4-bit fixed window).
+// The exponent is uniform across the warp, so table indexing does not diverge.
+template <class C, int EW>
+CPG_HD Fp<C> pow_public(const Fp<C>& a, const uint32_t (&e)[EW]) {
+    Fp<C> tbl[16];
+    tbl[0] = Fp<C>::one();
+    tbl[1] = a;
+    for (int i = 2; i < 16; i++) tbl[i] = mul(tbl[i - 1], a);
+    Fp<C> acc = Fp<C>::one();
+    bool started = false;
+    for (int w = EW * 8 - 1; w >= 0; w--) {
+        uint32_t d = (e[w >> 3] >> ((w & 7) * 4)) & 15u;
+        if (started) {
+            acc = sqr(acc); acc = sqr(acc); acc = sqr(acc); acc = sqr(acc);
+        }
+        if (d) {
+            acc = started ? mul(acc, tbl[d]) : tbl[d];
+            started = true;
+        }
+    }
+    return acc;
+}
+
+typedef Fp<FqCfg> Fq;
+typedef Fp<FrCfg> Fr;
+
+// Fq inversion a^(p-2) and square root candidate a^((p+1)/4) (p = 3 mod 4).
+CPG_HD Fq fq_inv(const Fq& a) {
+    const uint32_t e[12] = {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                            0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+    return pow_public<FqCfg, 12>(a, e);
+}
+CPG_HD Fq fq_sqrt_candidate(const Fq& a) {
+    const uint32_t e[12] = {0xffffeaabu, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u,
+                            0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au};
+    return pow_public<FqCfg, 12>(a, e);
+}
+CPG_HD Fr fr_inv(const Fr& a) {
+    const uint32_t e[8] = {0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+    return pow_public<FrCfg, 8>(a, e);
+}
+
+// (p-1)/2 as a plain integer: y is "lexicographically largest" iff y > (p-1)/2.
+CPG_HD bool fq_is_lex_largest(const Fq& y_plain) {
+    const uint32_t half[12] = {0xffffd555u, 0xdcff7fffu, 0x58a9ffffu, 0x0f55ffffu, 0x7b587b12u, 0xb3986950u,
+                               0x79c2895fu, 0xb23ba5c2u, 0x21a5d66bu, 0x258dd3dbu, 0x1cbff34du, 0x0d0088f5u};
+    // y > half  <=>  !(half >= y)
+    return !geq_n<12>(half, y_plain.l);
+}
+
+}  // namespace cpg

@@ -1,0 +1,268 @@
+// Kernel bodies (one functor = one kernel, one call = one thread) for the batched G1 hot path.
+//
+// Reference sites replaced (all under /root/reference/curdleproofs/curdleproofs/):
+//   compute_MSM                       msm_accumulator.py:6-12   -> batched Pippenger (SortDigits,
+//                                                                  BucketAccumulate, WindowReduce, Horner)
+//   MSMAccumulator.verify's final MSM msm_accumulator.py:60-68  -> same, plus FixedMsm for CRS bases
+//   G_L[i] + x*G_R[i] folds           ipa.py:145-146, same_msm.py:124-126 -> FoldPoints
+//   G'_i = beta^-(i+1) * G_i          grand_prod.py:66-71       -> MulPoints
+//   to/from_compressed_bytes          util.py:27-28,35-36       -> CompressJac / Decompress
+//
+// Batched Pippenger over B independent MSMs of n terms:
+//   window width c, W = ceil(256/c) windows, NB = 2^(c-1) buckets per window (signed digits).
+//   1 SortDigits        thread = (msm, window): counting sort of the n signed digits
+//   2 BucketAccumulate  thread = (msm, window, bucket): XYZZ mixed adds, registers only
+//   3 WindowReduce      thread = (msm, window): running-sum  sum_b (b+1) * S_b
+//   4 Horner            thread = msm: c doublings + 1 add per window
+// Every body is plain per-thread code, so the identical functors run under the CPU test seam.
+#pragma once
+#include "g1.cuh"
+
+namespace cpg {
+
+// ---- signed-digit recoding, local form --------------------------------------------------
+// k' = k + C with C = sum_{w < W-1} 2^(c-1+cw).  Then for w < W-1: d_w = ((k' >> cw) & (2^c-1)) - 2^(c-1)
+// in [-2^(c-1), 2^(c-1)-1], and the top digit d_{W-1} = k' >> c(W-1) in [0, 2^(c-1)] (k < 2^255).
+// No carry chain between windows, so each (term, window) pair is independent.
+struct Recode {
+    uint32_t c, W;
+    uint32_t C[8];
+};
+CPG_HD void recode_add(const Recode& rc, const uint32_t* k, uint32_t* kp) {
+    kp[0] = add_cc(k[0], rc.C[0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) kp[i] = addc_cc(k[i], rc.C[i]);
+    kp[7] = addc(k[7], rc.C[7]);
+}
+CPG_HD int recode_digit(const Recode& rc, const uint32_t* kp, uint32_t w) {
+    uint32_t bit = w * rc.c, limb = bit >> 5, sh = bit & 31;
+    uint32_t v = kp[limb] >> sh;
+    if (sh + rc.c > 32 && limb < 7) v |= kp[limb + 1] << (32 - sh);
+    if (w == rc.W - 1) return (int)v;          // top window: everything that is left, unsigned
+    v &= (1u << rc.c) - 1u;
+    return (int)v - (int)(1u << (rc.c - 1));
+}
+
+struct MsmShape {
+    uint32_t B, n, c, W, NB;      // NB = 2^(c-1)
+    uint64_t base_stride;         // bases of msm m start at m*base_stride (0 = shared by all)
+};
+
+// 1 --- counting sort of the digits of one (msm, window) ----------------------------------
+struct SortDigits {
+    MsmShape s; Recode rc;
+    const uint32_t* scalars;      // [B][n][8] canonical little-endian
+    uint32_t* boff;               // [B*W][NB+1] bucket start offsets (out)
+    uint32_t* sorted;             // [B*W][n] term index | sign<<31, grouped by bucket (out)
+    CPG_HD void operator()(uint64_t t) const {
+        uint32_t m = (uint32_t)(t / s.W), w = (uint32_t)(t % s.W);
+        uint32_t* off = boff + t * (uint64_t)(s.NB + 1);
+        uint32_t* out = sorted + t * (uint64_t)s.n;
+        const uint32_t* ks = scalars + (uint64_t)m * s.n * 8;
+        for (uint32_t b = 0; b <= s.NB; b++) off[b] = 0;
+        uint32_t kp[8];
+        for (uint32_t i = 0; i < s.n; i++) {       // off[a] = number of terms with |digit| = a
+            recode_add(rc, ks + 8 * (uint64_t)i, kp);
+            int d = recode_digit(rc, kp, w);
+            if (d) off[(d < 0 ? -d : d)]++;
+        }
+        uint32_t run = 0;                           // off[a] = END of bucket a-1
+        for (uint32_t b = 1; b <= s.NB; b++) { run += off[b]; off[b] = run; }
+        const uint32_t total = run;
+        for (uint32_t i = s.n; i-- > 0;) {          // fill each bucket from its end (stable)
+            recode_add(rc, ks + 8 * (uint64_t)i, kp);
+            int d = recode_digit(rc, kp, w);
+            if (d) { uint32_t a = (uint32_t)(d < 0 ? -d : d); out[--off[a]] = i | (d < 0 ? 0x80000000u : 0u); }
+        }
+        // off[a] is now the START of bucket a-1: shift down to off[b] = start of bucket b
+        for (uint32_t b = 0; b < s.NB; b++) off[b] = off[b + 1];
+        off[s.NB] = total;
+    }
+};
+
+// 2 --- one bucket: sum of its (signed) bases, mixed XYZZ adds ------------------------------
+struct BucketAccumulate {
+    MsmShape s;
+    const Aff* bases;
+    const uint32_t* boff;
+    const uint32_t* sorted;
+    const uint32_t* order;        // optional permutation of bucket ids (length-balanced warps), or null
+    Xyzz* buckets;                // [B*W][NB] (out)
+    CPG_HD void operator()(uint64_t t) const {
+        uint64_t g = order ? order[t] : t;
+        uint64_t mw = g / s.NB; uint32_t b = (uint32_t)(g % s.NB);
+        uint32_t m = (uint32_t)(mw / s.W);
+        const uint32_t* off = boff + mw * (uint64_t)(s.NB + 1);
+        const uint32_t* lst = sorted + mw * (uint64_t)s.n;
+        const Aff* P = bases + (uint64_t)m * s.base_stride;
+        Xyzz acc = xyzz_inf();
+        uint32_t lo = off[b], hi = off[b + 1];
+        for (uint32_t j = lo; j < hi; j++) {
+            uint32_t e = lst[j];
+            Aff q = P[e & 0x7fffffffu];
+            acc = xyzz_add_mixed(acc, cneg(q, (e >> 31) != 0));
+        }
+        buckets[g] = acc;
+    }
+};
+
+// 3 --- one window: sum_b (b+1) * S_b by running sums ---------------------------------------
+struct WindowReduce {
+    MsmShape s;
+    const Xyzz* buckets;
+    Xyzz* wsum;                   // [B*W] (out)
+    CPG_HD void operator()(uint64_t t) const {
+        const Xyzz* bk = buckets + t * (uint64_t)s.NB;
+        Xyzz run = xyzz_inf(), tot = xyzz_inf();
+        for (uint32_t b = s.NB; b-- > 0;) {
+            run = xyzz_add(run, bk[b]);
+            tot = xyzz_add(tot, run);
+        }
+        wsum[t] = tot;
+    }
+};
+
+// 4 --- one msm: Horner over its windows ----------------------------------------------------
+struct Horner {
+    MsmShape s;
+    const Xyzz* wsum;
+    Jac* out;                     // [B]
+    CPG_HD void operator()(uint64_t m) const {
+        const Xyzz* ws = wsum + m * (uint64_t)s.W;
+        Xyzz acc = ws[s.W - 1];
+        for (uint32_t w = s.W - 1; w-- > 0;) {
+            for (uint32_t j = 0; j < s.c; j++) acc = xyzz_dbl(acc);
+            acc = xyzz_add(acc, ws[w]);
+        }
+        out[m] = xyzz_to_jac(acc);
+    }
+};
+
+// ---- fixed-base tables (CRS generators shared by every proof) ------------------------------
+// T[i][w][d-1] = d * 2^(c w) * G_i as affine, d = 1..NB.  With them an MSM over the CRS needs
+// no doublings and no bucket reduction: n*W mixed adds (SURVEY 8f-2 direction).
+struct FixedShape { uint32_t nb, c, W, NB; };
+
+struct FixedTableRows {            // thread = (base i, window w): the NB multiples, Jacobian scratch
+    FixedShape s;
+    const Aff* bases;
+    Jac* rows;                     // [nb*W][NB]
+    CPG_HD void operator()(uint64_t t) const {
+        uint32_t i = (uint32_t)(t / s.W), w = (uint32_t)(t % s.W);
+        Jac p = to_jac(bases[i]);
+        for (uint32_t j = 0; j < w * s.c; j++) p = jac_dbl(p);
+        Jac acc = p;
+        Jac* row = rows + t * (uint64_t)s.NB;
+        for (uint32_t d = 0; d < s.NB; d++) { row[d] = acc; acc = jac_add(acc, p); }
+    }
+};
+struct JacToAff {                  // thread = one point (one Fq inversion each)
+    const Jac* in; Aff* out;
+    CPG_HD void operator()(uint64_t t) const { out[t] = jac_to_aff(in[t]); }
+};
+struct AffToJac {
+    const Aff* in; Jac* out;
+    CPG_HD void operator()(uint64_t t) const { out[t] = to_jac(in[t]); }
+};
+struct FixedMsmWindow {            // thread = (msm, window): sum_i +-T[i][w][|d|-1]
+    FixedShape s; Recode rc;
+    uint32_t B;
+    const Aff* table;
+    const uint32_t* scalars;       // [B][nb][8]
+    Xyzz* partial;                 // [B*W]
+    CPG_HD void operator()(uint64_t t) const {
+        uint32_t m = (uint32_t)(t / s.W), w = (uint32_t)(t % s.W);
+        const uint32_t* ks = scalars + (uint64_t)m * s.nb * 8;
+        Xyzz acc = xyzz_inf();
+        uint32_t kp[8];
+        for (uint32_t i = 0; i < s.nb; i++) {
+            recode_add(rc, ks + 8 * (uint64_t)i, kp);
+            int d = recode_digit(rc, kp, w);
+            if (!d) continue;
+            uint32_t a = (uint32_t)(d < 0 ? -d : d);
+            Aff q = table[((uint64_t)i * s.W + w) * s.NB + (a - 1)];
+            acc = xyzz_add_mixed(acc, cneg(q, d < 0));
+        }
+        partial[t] = acc;
+    }
+};
+struct SumWindows {                // thread = msm: plain sum of W partials (no doublings)
+    uint32_t W;
+    const Xyzz* partial;
+    Jac* out;
+    int accumulate;                // 1: out[m] += sum, 0: out[m] = sum
+    CPG_HD void operator()(uint64_t m) const {
+        const Xyzz* ps = partial + m * (uint64_t)W;
+        Xyzz acc = ps[0];
+        for (uint32_t w = 1; w < W; w++) acc = xyzz_add(acc, ps[w]);
+        Jac r = xyzz_to_jac(acc);
+        out[m] = accumulate ? jac_add(out[m], r) : r;
+    }
+};
+
+// ---- element-wise kernels (vector scalar-mul, fold, group law, serialisation) ---------------
+struct Decompress {
+    const uint8_t* in; int check; Aff* out; uint8_t* err;
+    CPG_HD void operator()(uint64_t t) const {
+        Aff a;
+        int e = aff_decompress(in + 48 * t, check != 0, &a);
+        out[t] = a;
+        err[t] = (uint8_t)e;
+    }
+};
+struct CompressJac {
+    const Jac* in; uint8_t* out;
+    CPG_HD void operator()(uint64_t t) const { aff_compress(jac_to_aff(in[t]), out + 48 * t); }
+};
+struct CompressAff {
+    const Aff* in; uint8_t* out;
+    CPG_HD void operator()(uint64_t t) const { aff_compress(in[t], out + 48 * t); }
+};
+struct AddPoints {                 // op 0: a+b, 1: a-b
+    const Jac* a; const Jac* b; Jac* out; int op;
+    CPG_HD void operator()(uint64_t t) const { out[t] = jac_add(a[t], op ? neg(b[t]) : b[t]); }
+};
+struct NegPoints {
+    const Jac* a; Jac* out;
+    CPG_HD void operator()(uint64_t t) const { out[t] = neg(a[t]); }
+};
+struct EqPoints {
+    const Jac* a; const Jac* b; uint8_t* out;
+    CPG_HD void operator()(uint64_t t) const { out[t] = jac_eq(a[t], b[t]) ? 1 : 0; }
+};
+struct IsInfPoints {
+    const Jac* a; uint8_t* out;
+    CPG_HD void operator()(uint64_t t) const { out[t] = is_inf(a[t]) ? 1 : 0; }
+};
+struct MulPoints {                 // out[t] = k[t / group] * p[t]   (group = 1: one scalar per point)
+    const Jac* p; const uint32_t* k; uint64_t group; Jac* out;
+    CPG_HD void operator()(uint64_t t) const { out[t] = jac_mul(p[t], k + 8 * (t / group)); }
+};
+struct FoldPoints {                // out[r][i] = L[r][i] + x[r] * R[r][i],  r < rows, i < m
+    const Jac* L; const Jac* R; const uint32_t* x; uint64_t m; Jac* out;
+    CPG_HD void operator()(uint64_t t) const { out[t] = jac_add(L[t], jac_mul(R[t], x + 8 * (t / m))); }
+};
+
+// ---- Fr vector ops on canonical little-endian words (K7) ------------------------------------
+struct FrBinary {                  // op 0 add, 1 sub, 2 mul
+    const uint32_t* a; const uint32_t* b; uint32_t* out; int op;
+    CPG_HD void operator()(uint64_t t) const {
+        Fr x, y, z;
+        for (int i = 0; i < 8; i++) { x.l[i] = a[8 * t + i]; y.l[i] = b[8 * t + i]; }
+        if (op == 0) z = add(x, y);
+        else if (op == 1) z = sub(x, y);
+        else z = from_mont(mul(to_mont(x), to_mont(y)));
+        for (int i = 0; i < 8; i++) out[8 * t + i] = z.l[i];
+    }
+};
+struct FrInverse {                 // 0 -> 0 (cp/util.py:51-54 relies on a value coming back)
+    const uint32_t* a; uint32_t* out;
+    CPG_HD void operator()(uint64_t t) const {
+        Fr x;
+        for (int i = 0; i < 8; i++) x.l[i] = a[8 * t + i];
+        Fr z = x.is_zero() ? x : from_mont(fr_inv(to_mont(x)));
+        for (int i = 0; i < 8; i++) out[8 * t + i] = z.l[i];
+    }
+};
+
+}  // namespace cpg

@@ -1,0 +1,117 @@
+/* cpg.h - C ABI of the B200-native curdleproofs G1 hot path (libcpg.so).
+ *
+ * This is the drop-in boundary for the arithmetic the reference obtains from the external
+ * wheel py_arkworks_bls12381 0.3.5 (Rust/PyO3).  The reference binds it as Python classes
+ *   G1Point  /root/reference/curdleproofs/py_arkworks_bls12381-stubs/__init__.pyi:5-30
+ *   Scalar   /root/reference/curdleproofs/py_arkworks_bls12381-stubs/__init__.pyi:32-54
+ * and calls it one group element at a time.  A maintainer binds THIS header with ctypes/cffi
+ * (INTEGRATION.md shows the stub); every entry point below names the reference interface it
+ * replaces.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - one process per GPU; cpg_init(device) selects it.  All work is enqueued on the library's
+ *     current stream (cpg_set_stream) and is asynchronous unless stated; cpg_sync() waits.
+ *   - "d_" arguments are DEVICE pointers obtained from cpg_malloc.  Host buffers cross only
+ *     through cpg_h2d / cpg_d2h.
+ *   - device formats (little-endian u32 limbs, Fq in Montgomery form R = 2^384):
+ *       affine   point: 96 B  = x | y          (x = y = 0 encodes the identity)
+ *       jacobian point: 144 B = X | Y | Z      (Z = 0 encodes the identity)
+ *       scalar        : 32 B canonical little-endian integer < r (NOT Montgomery), as on the wire
+ *       compressed    : 48 B ZCash/IETF encoding, as on the wire (cp/util.py:27-28)
+ *   - every function returns 0 on success; non-zero is an error whose text cpg_last_error()
+ *     returns.  Encoding errors are reported per element in the err arrays (0 = ok) so that a
+ *     bad lane never aborts a batch; the Python surface turns them into ValueError.
+ *   - there is no CPU fallback: without a CUDA device cpg_init fails and nothing else works.
+ */
+#ifndef CPG_H
+#define CPG_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPG_AFF_BYTES 96
+#define CPG_JAC_BYTES 144
+#define CPG_SCALAR_BYTES 32
+#define CPG_COMPRESSED_BYTES 48
+
+/* ---- runtime ------------------------------------------------------------------------------ */
+int cpg_init(int device);                       /* idempotent */
+int cpg_device_count(void);
+const char* cpg_last_error(void);
+const char* cpg_backend(void);                  /* "cuda-sm_100a" for the product library */
+int cpg_set_stream(void* cuda_stream);          /* cudaStream_t, NULL = library default stream */
+int cpg_sync(void);
+void* cpg_malloc(size_t bytes);                 /* NULL on failure */
+int cpg_free(void* d_ptr);
+int cpg_memset(void* d_ptr, int value, size_t bytes);
+int cpg_h2d(void* d_dst, const void* h_src, size_t bytes);   /* async on the current stream */
+int cpg_d2h(void* h_dst, const void* d_src, size_t bytes);   /* synchronises before returning */
+int cpg_d2d(void* d_dst, const void* d_src, size_t bytes);
+void* cpg_host_alloc(size_t bytes);             /* pinned host memory for the e2e path */
+int cpg_host_free(void* h_ptr);
+/* device timers on the current stream (CUDA events) */
+int cpg_timer_start(void);
+int cpg_timer_stop(float* ms);                  /* synchronises */
+uint64_t cpg_launch_count(void);                /* kernels launched by this library so far */
+
+/* ---- serialisation -------------------------------------------------------------------------
+ * replaces G1Point.from_compressed_bytes (stub :19, check_subgroup=1) and
+ * from_compressed_bytes_unchecked (stub :22; cp/util.py:35-36, cp/msm_accumulator.py:65) */
+int cpg_g1_decompress(const uint8_t* d_in48, size_t k, int check_subgroup, void* d_out_aff, uint8_t* d_err);
+/* replaces G1Point.to_compressed_bytes (stub :30; cp/util.py:27-28) */
+int cpg_g1_compress(const void* d_jac, size_t k, uint8_t* d_out48);
+int cpg_g1_compress_aff(const void* d_aff, size_t k, uint8_t* d_out48);
+int cpg_g1_aff_to_jac(const void* d_aff, size_t k, void* d_out_jac);
+int cpg_g1_jac_to_aff(const void* d_jac, size_t k, void* d_out_aff);
+int cpg_g1_generator(void* d_out_jac);          /* G1Point()            stub :6  */
+int cpg_g1_identity(void* d_out_jac);           /* G1Point.identity()   stub :25 */
+
+/* ---- element-wise group law over k points ---------------------------------------------------
+ * replaces G1Point.__add__/__sub__/__neg__/__eq__ (stub :7-16) */
+int cpg_g1_add(const void* d_a_jac, const void* d_b_jac, size_t k, void* d_out_jac);
+int cpg_g1_sub(const void* d_a_jac, const void* d_b_jac, size_t k, void* d_out_jac);
+int cpg_g1_neg(const void* d_a_jac, size_t k, void* d_out_jac);
+int cpg_g1_eq(const void* d_a_jac, const void* d_b_jac, size_t k, uint8_t* d_out);
+int cpg_g1_is_identity(const void* d_a_jac, size_t k, uint8_t* d_out);
+/* replaces G1Point.__mul__(Scalar) (stub :10); out[i] = scalars[i / group] * p[i]
+ * (group = 1: one scalar per point; group = m: one scalar per row of m points, the
+ * vector scalar-mul  G'_i = beta^-(i+1) G_i  of cp/grand_prod.py:66-71 uses group = 1) */
+int cpg_g1_mul(const void* d_p_jac, const uint8_t* d_scalars, size_t k, size_t group, void* d_out_jac);
+/* IPA / SameMSM generator folding  out[r][i] = L[r][i] + x[r] * R[r][i]
+ * (cp/ipa.py:145-146, cp/same_msm.py:124-126), rows x m points */
+int cpg_g1_fold(const void* d_L_jac, const void* d_R_jac, const uint8_t* d_x, size_t rows, size_t m, void* d_out_jac);
+
+/* ---- multi-scalar multiplication -------------------------------------------------------------
+ * replaces compute_MSM (cp/msm_accumulator.py:6-12) and G1Point.multiexp_unchecked (stub :28):
+ * B independent MSMs of n terms each in one call.  bases of MSM b start at
+ * d_bases_aff + b*base_stride points (base_stride = 0: all MSMs share one base vector);
+ * scalars are [B][n] x 32 B.  window = 0 picks the window width from n. */
+int cpg_g1_msm_batched(const void* d_bases_aff, size_t base_stride, const uint8_t* d_scalars,
+                       size_t B, size_t n, int window, void* d_out_jac);
+/* fixed-base tables for generators shared by every proof (the CRS, cp/crs.py:19-36):
+ * T[i][w][d] = (d+1) 2^(c w) G_i.  Returns NULL on failure. */
+void* cpg_fixed_table_create(const void* d_bases_aff, size_t nb, int window);
+int cpg_fixed_table_free(void* table);
+size_t cpg_fixed_table_bytes(const void* table);
+/* out[b] (+)= sum_i scalars[b][i] * G_i ; accumulate = 1 adds into d_out_jac */
+int cpg_g1_msm_fixed_batched(const void* table, const uint8_t* d_scalars, size_t B, int accumulate, void* d_out_jac);
+
+/* ---- Fr vector ops (Scalar.__add__/__sub__/__mul__/inverse, stub :32-54) on k canonical scalars */
+int cpg_fr_add(const uint8_t* d_a, const uint8_t* d_b, size_t k, uint8_t* d_out);
+int cpg_fr_sub(const uint8_t* d_a, const uint8_t* d_b, size_t k, uint8_t* d_out);
+int cpg_fr_mul(const uint8_t* d_a, const uint8_t* d_b, size_t k, uint8_t* d_out);
+int cpg_fr_inverse(const uint8_t* d_a, size_t k, uint8_t* d_out);   /* inverse(0) = 0, cp/util.py:51-54 */
+
+/* ---- roofline support: saturating integer-pipe microbenchmark ---------------------------------
+ * Runs `iters` dependent-chain steps of 32x32->64 multiply-accumulates on every SM and reports
+ * the achieved MAC/s (kind 0: IMAD.WIDE.U32 chains, kind 1: IMAD.LO+IMAD.HI pairs) and the
+ * Fq Montgomery products/s of this library's own field code (kind 2). */
+int cpg_bench_int_pipe(int kind, uint64_t iters, double* per_second, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPG_H */

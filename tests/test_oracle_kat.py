@@ -1,0 +1,116 @@
+"""The oracle (oracle/) pinned to every known answer the reference's own tests hold for this path
+(SURVEY 8c): curdleproofs/curdleproofs/test_curdleproofs.py:144-213, :236 and
+merlin_transcripts/merlin_transcripts/test_merlin.py:18,29,40."""
+import random
+
+import pytest
+
+from oracle import ark_surface, bls12381_py as bp, merlin_py
+
+GEN_HEX = "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+G99_HEX = "aa10e1055b14a89cc3261699524998732fddc4f30c76c1057eb83732a01416643eb015a932e4080c86f42e485973d240"
+CURVE_ORDER = 52435875175126190479447740508185965837690552500527637822603658699938581184513
+
+
+@pytest.fixture(params=["py", "c"])
+def surface(request):
+    ark_surface.set_backend(request.param)
+    yield ark_surface
+    ark_surface.set_backend("py")
+
+
+def test_g1_kats(surface):
+    G1Point, Scalar = surface.G1Point, surface.Scalar
+    gen, ident = G1Point(), G1Point.identity()
+    assert gen == gen and gen != ident
+    assert (gen + gen) - gen == gen
+    assert -gen + gen == ident
+    assert gen * Scalar(4) == gen + gen + gen + gen
+    cb = gen.to_compressed_bytes()
+    assert G1Point.from_compressed_bytes(cb) == G1Point.from_compressed_bytes_unchecked(cb) == gen
+    assert str(gen) == GEN_HEX
+    assert bytes((gen * Scalar(99)).to_compressed_bytes()).hex() == G99_HEX
+    assert bytes(ident.to_compressed_bytes()) == bytes([0xC0]) + bytes(47)
+    with pytest.raises(TypeError):
+        {gen: 1}
+
+
+def test_scalar_kats(surface):
+    Scalar = surface.Scalar
+    assert bytes(Scalar(4).to_le_bytes()) == bytes.fromhex("04" + "00" * 31)
+    assert bp.R == CURVE_ORDER
+    assert int(Scalar(CURVE_ORDER - 1)) == CURVE_ORDER - 1
+    assert int(Scalar(CURVE_ORDER)) == 0
+    assert int(Scalar(2**256)) == 2**256 % CURVE_ORDER
+    assert int(Scalar(2**257)) == 2**257 % CURVE_ORDER
+    Scalar.from_le_bytes((CURVE_ORDER - 1).to_bytes(32, "little"))
+    with pytest.raises(ValueError):
+        Scalar.from_le_bytes(CURVE_ORDER.to_bytes(32, "little"))
+    assert (Scalar(0).inverse() * Scalar(0)) != Scalar(1)
+
+
+def _not_on_curve():
+    x = 1
+    while pow(x * x * x + 4, (bp.P - 1) // 2, bp.P) == 1:
+        x += 1
+    b = bytearray(x.to_bytes(48, "big"))
+    b[0] |= 0x80
+    return bytes(b)
+
+
+def test_bad_encodings(surface):
+    G1Point = surface.G1Point
+    good = bytearray(bytes.fromhex(GEN_HEX))
+    for bad in (
+        bytes([good[0] & 0x7F]) + bytes(good[1:]),          # compression flag missing
+        bytes([0xC0]) + bytes(46) + b"\x01",                 # infinity with payload
+        bytes([0xE0]) + bytes(47),                           # infinity with sign bit
+        bytes([0x9F]) + b"\xff" * 47,                        # x >= p
+        _not_on_curve(),                                     # x^3 + 4 is a non-residue
+        bytes(47),                                           # wrong length
+    ):
+        with pytest.raises(ValueError):
+            G1Point.from_compressed_bytes_unchecked(bad)
+
+
+def test_c_oracle_matches_python_oracle(cref):
+    rng = random.Random(7)
+    for _ in range(20):
+        k1, k2 = rng.randrange(bp.R), rng.randrange(bp.R)
+        p = bp.mul(bp.GENERATOR, k1)
+        pc = cref.mul(cref.generator(), k1)
+        assert cref.compress(pc) == bp.compress(p)
+        assert cref.compress(cref.add(pc, cref.mul(cref.generator(), k2))) == bp.compress(bp.add(p, bp.mul(bp.GENERATOR, k2)))
+        assert cref.compress(cref.decompress(bp.compress(p), False)) == bp.compress(p)
+    n = 40
+    pts = [bp.mul(bp.GENERATOR, rng.randrange(bp.R)) for _ in range(n)]
+    ks = [rng.randrange(bp.R) for _ in range(n)]
+    want = bp.compress(bp.msm_naive(pts, ks))
+    assert bp.compress(bp.msm_pippenger(pts, ks)) == want
+    cpts = [cref.decompress(bp.compress(p), False) for p in pts]
+    assert cref.compress(cref.msm(cpts, ks)) == want
+    assert cref.compress(cref.msm(cpts, ks, naive=True)) == want
+
+
+def test_strobe_and_merlin_kats():
+    s = merlin_py.Strobe(b"Conformance Test Protocol")
+    s.meta_ad(b"ms", False)
+    s.meta_ad(b"g", True)
+    s.ad(bytes([99]) * 1024, False)
+    s.meta_ad(b"prf", False)
+    prf = s.prf(32, False)
+    assert prf.hex() == "b48e645ca17c667fd5206ba57a6a228d72d8e1903814d3f17f622996d7cfefb0"
+    s.meta_ad(b"key", False)
+    s.key(prf, False)
+    s.meta_ad(b"prf", False)
+    assert s.prf(32, False).hex() == "07e45cce8078cee259e3e375bb85d75610e2d1e1201c5f645045a194edd49ff8"
+    t = merlin_py.Transcript.__new__(merlin_py.Transcript)
+    t.s = merlin_py.Strobe(b"Merlin v1.0")
+    t.append(b"dom-sep", b"test protocol")
+    t.append(b"some label", b"some data")
+    assert t.challenge_bytes(b"challenge", 32).hex() == "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+
+
+def test_c_keccak_matches_python(cref):
+    st = bytearray(range(200))
+    assert bytes(cref.keccak_f1600(st)) == bytes(merlin_py.keccak_f1600(bytearray(range(200))))

@@ -1,0 +1,41 @@
+"""CPU tier: the kernels' per-thread code (host-emulated, see tests/conftest.py::build_seam) driven
+through the same C ABI and launch logic as on the GPU, checked bit-for-bit against the oracle.
+Sizes are small; the GPU tier (tests/test_gpu_parity.py) repeats the cases at full size."""
+import pytest
+
+import parity_cases as pc
+
+
+def test_roundtrip(seam_lib, cref):
+    pc.case_roundtrip(seam_lib, cref, 12)
+
+
+def test_group_law(seam_lib, cref):
+    pc.case_group_law(seam_lib, cref, 12)
+
+
+def test_fold(seam_lib, cref):
+    pc.case_fold(seam_lib, cref, 2, 4)
+
+
+@pytest.mark.parametrize("B,n,window,shared", [(3, 16, 0, False), (2, 33, 5, True), (1, 1, 0, False), (2, 7, 2, False), (1, 40, 8, False)])
+def test_msm(seam_lib, cref, B, n, window, shared):
+    pc.case_msm(seam_lib, cref, B, n, window, shared)
+
+
+def test_msm_edges(seam_lib, cref):
+    pc.case_msm(seam_lib, cref, 4, 12, 4, shared=False, edge=True)
+    pc.case_msm(seam_lib, cref, 3, 12, 3, shared=True, edge=True)
+
+
+def test_msm_empty(seam_lib, cref):
+    out = seam_lib.msm_batched(seam_lib.alloc(96), 0, seam_lib.alloc(32), 2, 0)
+    assert seam_lib.is_identity(out, 2) == [1, 1]
+
+
+def test_fixed_base(seam_lib, cref):
+    pc.case_fixed(seam_lib, cref, 2, 5, 4)
+
+
+def test_fr(seam_lib):
+    pc.case_fr(seam_lib, 16)
