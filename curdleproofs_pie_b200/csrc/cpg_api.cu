@@ -51,12 +51,29 @@ __global__ void __launch_bounds__(BLOCK) k_each(const F f, uint64_t n) {
     uint64_t t = blockIdx.x * (uint64_t)BLOCK + threadIdx.x;
     if (t < n) f(t);
 }
+// ---- optional per-kernel timing (cpg_profile_*): one CUDA event pair per launch on the launching
+// stream, resolved lazily.  Off by default; bench.py turns it on to time the dominant kernel live.
+struct ProfRec { const char* name; cudaEvent_t a, b; uint64_t threads; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::mutex g_prof_mu;
+
 template <int BLOCK = 128, class F>
 int launch(const F& f, uint64_t n) {
     if (!n) return 0;
     uint64_t grid = (n + BLOCK - 1) / BLOCK;
     if (grid > 0x7fffffffULL) return fail("launch: grid too large");
+    ProfRec rec{F::kName, nullptr, nullptr, n};
+    if (g_prof_on) {
+        cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
+        cudaEventRecord(rec.a, cur());
+    }
     k_each<F, BLOCK><<<(unsigned)grid, BLOCK, 0, cur()>>>(f, n);
+    if (g_prof_on) {
+        cudaEventRecord(rec.b, cur());
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(rec);
+    }
     g_launches++;
     return ck(cudaGetLastError(), "kernel launch");
 }
@@ -294,6 +311,57 @@ int cpg_timer_stop(float* ms) {
 }
 uint64_t cpg_launch_count(void) { return g_launches.load(); }
 
+/* ---- per-kernel profile ---- */
+int cpg_profile_enable(int on) {
+#ifndef CPG_HOST_EMU
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = on != 0;
+#else
+    (void)on;
+#endif
+    return 0;
+}
+int cpg_profile_reset(void) {
+#ifndef CPG_HOST_EMU
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+#endif
+    return 0;
+}
+int cpg_profile_report(char* buf, size_t cap) {
+    if (!buf || !cap) return fail("cpg_profile_report: no buffer");
+    buf[0] = 0;
+#ifndef CPG_HOST_EMU
+    NEED_INIT();
+    CK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    struct Agg { const char* name; double ms; uint64_t launches, threads; };
+    std::vector<Agg> agg;
+    for (auto& r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+        size_t i = 0;
+        for (; i < agg.size(); i++) if (!strcmp(agg[i].name, r.name)) break;
+        if (i == agg.size()) agg.push_back(Agg{r.name, 0.0, 0, 0});
+        agg[i].ms += ms; agg[i].launches++; agg[i].threads += r.threads;
+    }
+    std::string out = "{";
+    for (size_t i = 0; i < agg.size(); i++) {
+        char line[256];
+        snprintf(line, sizeof line, "%s\"%s\": {\"ms\": %.6f, \"launches\": %llu, \"threads\": %llu}", i ? ", " : "",
+                 agg[i].name, agg[i].ms, (unsigned long long)agg[i].launches, (unsigned long long)agg[i].threads);
+        out += line;
+    }
+    out += "}";
+    if (out.size() + 1 > cap) return fail("cpg_profile_report: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+#else
+    if (cap >= 3) { buf[0] = '{'; buf[1] = '}'; buf[2] = 0; }
+#endif
+    return 0;
+}
+
 /* ---- serialisation ---- */
 int cpg_g1_decompress(const uint8_t* d_in, size_t k, int check, void* d_out, uint8_t* d_err) {
     NEED_INIT();
@@ -468,36 +536,35 @@ int cpg_fr_inverse(const uint8_t* a, size_t k, uint8_t* out) {
 #ifndef CPG_HOST_EMU
 }  // extern "C"
 namespace {
-// 8 independent accumulator chains per thread so the dependent-issue latency (4 clk) is covered.
+// 8 independent chains per thread.  The multiplicand is the accumulator's own low word, so nothing
+// is loop-invariant (an invariant product gets strength-reduced to adds by ptxas - an earlier
+// version of this probe measured the ALU pipe that way).  SASS: one IMAD.WIDE.U32 per step.
+#define CPG_WIDE_DEP(lo, hi, a) asm volatile("{ .reg .u32 t; mov.u32 t, %0; mad.lo.cc.u32 %0, %2, t, %0; madc.hi.u32 %1, %2, t, %1; }" : "+r"(lo), "+r"(hi) : "r"(a))
 __global__ void __launch_bounds__(256) k_imad_wide(uint64_t iters, uint32_t a0, uint32_t b0, uint64_t* sink) {
-    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
-    uint64_t acc[8];
+    uint32_t a[8], lo[8], hi[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = j + threadIdx.x;
+    for (int j = 0; j < 8; j++) { lo[j] = j + threadIdx.x + b0; hi[j] = j + blockIdx.x; a[j] = a0 * (j + 1) + threadIdx.x; }
     for (uint64_t i = 0; i < iters; i++) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
-    }
-    uint64_t s = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) s ^= acc[j];
-    if (s == 0x123456789abcdefULL) sink[0] = s;
-}
-__global__ void __launch_bounds__(256) k_imad_lohi(uint64_t iters, uint32_t a0, uint32_t b0, uint64_t* sink) {
-    uint32_t a = a0 + threadIdx.x, b = b0 + blockIdx.x;
-    uint32_t lo[8], hi[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) { lo[j] = j + threadIdx.x; hi[j] = j; }
-    for (uint64_t i = 0; i < iters; i++) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(a), "r"(b));
-            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(hi[j]) : "r"(a), "r"(b));
-        }
+        for (int j = 0; j < 8; j++) CPG_WIDE_DEP(lo[j], hi[j], a[j]);
     }
     uint32_t s = 0;
 #pragma unroll
     for (int j = 0; j < 8; j++) s ^= lo[j] ^ hi[j];
+    if (s == 0x12345678u) sink[0] = s;
+}
+// 32-bit IMAD (low half only), data-dependent: the full-rate integer multiply, for context
+__global__ void __launch_bounds__(256) k_imad_lohi(uint64_t iters, uint32_t a0, uint32_t b0, uint64_t* sink) {
+    uint32_t a = a0 + threadIdx.x, x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) x[j] = j + threadIdx.x + b0 + blockIdx.x;
+    for (uint64_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) asm volatile("mad.lo.u32 %0, %1, %0, %0;" : "+r"(x[j]) : "r"(a));
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s ^= x[j];
     if (s == 0x12345678u) sink[0] = s;
 }
 __global__ void __launch_bounds__(256) k_fq_mul_chain(uint64_t iters, uint64_t* sink) {
@@ -540,3 +607,5 @@ int cpg_bench_int_pipe(int, uint64_t, double* per_second, float* ms) {
 #endif
 
 }  // extern "C"
+
+#include "verify.inl"

@@ -1,0 +1,229 @@
+// Host side of the batched prover/verifier: the sequential Fiat-Shamir transcript (stays on the
+// host per the north star) and the HFr bookkeeping that turns challenges into MSM coefficients.
+// Plain C++ (no CUDA).  Follows the reference, restated independently of oracle/:
+//   Keccak-f[1600]      /root/reference/merlin_transcripts/merlin_transcripts/keccak.py:16-66
+//   STROBE-128, R=166   merlin_transcripts/merlin_transcripts/strobe.py:16-107
+//   Merlin framing      merlin_transcripts/merlin_transcripts/merlin_transcript.py:6-24
+//   scalar challenges   curdleproofs/curdleproofs/curdleproofs_transcript.py:15-25
+// KATs: tests/test_host_transcript.py (merlin_transcripts/test_merlin.py:18,29,40 vectors).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+namespace cpgh {
+
+typedef unsigned __int128 u128;
+
+// ---------------------------------------------------------------- Keccak-f[1600] ---
+static inline uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+static const uint64_t KECCAK_RC[24] = {
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
+    0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
+    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
+    0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+
+static inline void keccak_f1600(uint64_t* A) {
+    for (int r = 0; r < 24; r++) {
+        uint64_t C0 = A[0] ^ A[5] ^ A[10] ^ A[15] ^ A[20], C1 = A[1] ^ A[6] ^ A[11] ^ A[16] ^ A[21];
+        uint64_t C2 = A[2] ^ A[7] ^ A[12] ^ A[17] ^ A[22], C3 = A[3] ^ A[8] ^ A[13] ^ A[18] ^ A[23];
+        uint64_t C4 = A[4] ^ A[9] ^ A[14] ^ A[19] ^ A[24];
+        uint64_t D0 = C4 ^ rotl64(C1, 1), D1 = C0 ^ rotl64(C2, 1), D2 = C1 ^ rotl64(C3, 1), D3 = C2 ^ rotl64(C4, 1), D4 = C3 ^ rotl64(C0, 1);
+        uint64_t B[25];
+        // theta + rho + pi:  B[y + 5*((2x+3y)%5)] = rot(A[x+5y] ^ D[x], r[x,y])
+        B[0] = A[0] ^ D0;
+        B[10] = rotl64(A[1] ^ D1, 1);   B[20] = rotl64(A[2] ^ D2, 62);  B[5] = rotl64(A[3] ^ D3, 28);   B[15] = rotl64(A[4] ^ D4, 27);
+        B[16] = rotl64(A[5] ^ D0, 36);  B[1] = rotl64(A[6] ^ D1, 44);   B[11] = rotl64(A[7] ^ D2, 6);   B[21] = rotl64(A[8] ^ D3, 55);  B[6] = rotl64(A[9] ^ D4, 20);
+        B[7] = rotl64(A[10] ^ D0, 3);   B[17] = rotl64(A[11] ^ D1, 10); B[2] = rotl64(A[12] ^ D2, 43);  B[12] = rotl64(A[13] ^ D3, 25); B[22] = rotl64(A[14] ^ D4, 39);
+        B[23] = rotl64(A[15] ^ D0, 41); B[8] = rotl64(A[16] ^ D1, 45);  B[18] = rotl64(A[17] ^ D2, 15); B[3] = rotl64(A[18] ^ D3, 21);  B[13] = rotl64(A[19] ^ D4, 8);
+        B[14] = rotl64(A[20] ^ D0, 18); B[24] = rotl64(A[21] ^ D1, 2);  B[9] = rotl64(A[22] ^ D2, 61);  B[19] = rotl64(A[23] ^ D3, 56);  B[4] = rotl64(A[24] ^ D4, 14);
+        for (int y = 0; y < 25; y += 5) {
+            A[y + 0] = B[y + 0] ^ (~B[y + 1] & B[y + 2]);
+            A[y + 1] = B[y + 1] ^ (~B[y + 2] & B[y + 3]);
+            A[y + 2] = B[y + 2] ^ (~B[y + 3] & B[y + 4]);
+            A[y + 3] = B[y + 3] ^ (~B[y + 4] & B[y + 0]);
+            A[y + 4] = B[y + 4] ^ (~B[y + 0] & B[y + 1]);
+        }
+        A[0] ^= KECCAK_RC[r];
+    }
+}
+
+// --------------------------------------------------------------------- STROBE-128 ---
+struct Strobe128 {
+    static const int RATE = 166;
+    enum { F_I = 1, F_A = 2, F_C = 4, F_T = 8, F_M = 16, F_K = 32 };
+    union { uint64_t w[25]; uint8_t b[200]; } st;   // little-endian host assumed (x86-64 / aarch64)
+    uint8_t pos, pos_begin, flags;
+    uint64_t permutations;
+
+    void init(const uint8_t* label, size_t n) {
+        memset(st.b, 0, 200);
+        const uint8_t hdr[6] = {1, RATE + 2, 1, 0, 1, 96};
+        memcpy(st.b, hdr, 6);
+        memcpy(st.b + 6, "STROBEv1.0.2", 12);
+        keccak_f1600(st.w);
+        pos = pos_begin = flags = 0;
+        permutations = 1;
+        meta_ad(label, n, false);
+    }
+    void run_f() {
+        st.b[pos] ^= pos_begin;
+        st.b[pos + 1] ^= 0x04;
+        st.b[RATE + 1] ^= 0x80;
+        keccak_f1600(st.w);
+        permutations++;
+        pos = pos_begin = 0;
+    }
+    void absorb(const uint8_t* d, size_t n) {
+        while (n) {
+            size_t room = RATE - pos, take = n < room ? n : room;
+            for (size_t i = 0; i < take; i++) st.b[pos + i] ^= d[i];
+            pos += (uint8_t)take; d += take; n -= take;
+            if (pos == RATE) run_f();
+        }
+    }
+    void begin_op(uint8_t fl, bool more) {
+        if (more) return;                         // continuation of the same operation
+        uint8_t old = pos_begin;
+        pos_begin = pos + 1;
+        flags = fl;
+        uint8_t hdr[2] = {old, fl};
+        absorb(hdr, 2);
+        if ((fl & (F_C | F_K)) && pos != 0) run_f();
+    }
+    void meta_ad(const uint8_t* d, size_t n, bool more) { begin_op(F_M | F_A, more); absorb(d, n); }
+    void ad(const uint8_t* d, size_t n, bool more) { begin_op(F_A, more); absorb(d, n); }
+    void prf(uint8_t* out, size_t n, bool more) {
+        begin_op(F_I | F_A | F_C, more);
+        for (size_t i = 0; i < n; i++) {
+            out[i] = st.b[pos];
+            st.b[pos] = 0;
+            pos++;
+            if (pos == RATE) run_f();
+        }
+    }
+};
+
+// ------------------------------------------------------------------------- Fr (host) ---
+// 4 x u64 Montgomery arithmetic mod r; values are kept in Montgomery form inside `HFr` (host Fr).
+struct HFr { uint64_t l[4]; };
+static const uint64_t FR_MOD[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+static const uint64_t FR_INV = 0xfffffffeffffffffULL;   // -r^-1 mod 2^64
+static const HFr FR_R1 = {{0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL, 0x1824b159acc5056fULL}};  // 2^256 mod r
+static const HFr FR_R2 = {{0xc999e990f3f29c6dULL, 0x2b6cedcb87925c23ULL, 0x05d314967254398fULL, 0x0748d9d99f59ff11ULL}};  // 2^512 mod r
+
+static inline bool fr_geq_mod(const uint64_t* a) {
+    for (int i = 3; i >= 0; i--) { if (a[i] > FR_MOD[i]) return true; if (a[i] < FR_MOD[i]) return false; }
+    return true;
+}
+static inline void fr_sub_mod(uint64_t* a) {
+    u128 br = 0;
+    for (int i = 0; i < 4; i++) { u128 d = (u128)a[i] - FR_MOD[i] - (uint64_t)br; a[i] = (uint64_t)d; br = (d >> 64) & 1; }
+}
+static inline HFr fr_add(const HFr& a, const HFr& b) {
+    HFr r; u128 c = 0;
+    for (int i = 0; i < 4; i++) { c += (u128)a.l[i] + b.l[i]; r.l[i] = (uint64_t)c; c >>= 64; }
+    if (fr_geq_mod(r.l)) fr_sub_mod(r.l);      // 2r < 2^256: no carry out
+    return r;
+}
+static inline HFr fr_sub(const HFr& a, const HFr& b) {
+    HFr r; u128 br = 0;
+    for (int i = 0; i < 4; i++) { u128 d = (u128)a.l[i] - b.l[i] - (uint64_t)br; r.l[i] = (uint64_t)d; br = (d >> 64) & 1; }
+    if (br) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)r.l[i] + FR_MOD[i]; r.l[i] = (uint64_t)c; c >>= 64; } }
+    return r;
+}
+static inline HFr fr_mul(const HFr& a, const HFr& b) {
+    uint64_t t[5] = {0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) { c += (u128)a.l[j] * b.l[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[4] = (uint64_t)c; uint64_t t5 = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * FR_INV;
+        c = ((u128)m * FR_MOD[0] + t[0]) >> 64;
+        for (int j = 1; j < 4; j++) { c += (u128)m * FR_MOD[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[3] = (uint64_t)c; t[4] = t5 + (uint64_t)(c >> 64);
+    }
+    HFr r = {{t[0], t[1], t[2], t[3]}};
+    if (t[4] || fr_geq_mod(r.l)) fr_sub_mod(r.l);
+    return r;
+}
+static inline HFr fr_zero() { HFr r = {{0, 0, 0, 0}}; return r; }
+static inline HFr fr_one() { return FR_R1; }
+static inline bool fr_is_zero(const HFr& a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
+static inline bool fr_eq(const HFr& a, const HFr& b) { return a.l[0] == b.l[0] && a.l[1] == b.l[1] && a.l[2] == b.l[2] && a.l[3] == b.l[3]; }
+static inline HFr fr_neg(const HFr& a) { return fr_sub(fr_zero(), a); }
+static inline HFr fr_from_u64(uint64_t v) { HFr r = {{v, 0, 0, 0}}; return fr_mul(r, FR_R2); }
+// canonical 32-byte little-endian -> HFr; false if >= r
+static inline bool fr_from_bytes(HFr* out, const uint8_t* b) {
+    HFr r; memcpy(r.l, b, 32);
+    if (fr_geq_mod(r.l)) return false;
+    *out = fr_mul(r, FR_R2);
+    return true;
+}
+static inline void fr_to_bytes(uint8_t* b, const HFr& a) {
+    HFr one = {{1, 0, 0, 0}};
+    HFr r = fr_mul(a, one);
+    memcpy(b, r.l, 32);
+}
+static inline HFr fr_pow_u64(HFr a, uint64_t e) {
+    HFr r = fr_one();
+    while (e) { if (e & 1) r = fr_mul(r, a); a = fr_mul(a, a); e >>= 1; }
+    return r;
+}
+static inline HFr fr_inv(const HFr& a) {   // a^(r-2); 0 -> 0
+    uint64_t e[4] = {FR_MOD[0] - 2, FR_MOD[1], FR_MOD[2], FR_MOD[3]};
+    HFr r = fr_one();
+    for (int i = 255; i >= 0; i--) {
+        r = fr_mul(r, r);
+        if ((e[i >> 6] >> (i & 63)) & 1) r = fr_mul(r, a);
+    }
+    return r;
+}
+// in-place batch inversion (Montgomery's trick); zeros stay zero
+static inline void fr_batch_inv(HFr* v, size_t n, HFr* scratch) {
+    HFr acc = fr_one();
+    for (size_t i = 0; i < n; i++) { scratch[i] = acc; if (!fr_is_zero(v[i])) acc = fr_mul(acc, v[i]); }
+    acc = fr_inv(acc);
+    for (size_t i = n; i-- > 0;) {
+        if (fr_is_zero(v[i])) continue;
+        HFr t = fr_mul(acc, scratch[i]);
+        acc = fr_mul(acc, v[i]);
+        v[i] = t;
+    }
+}
+
+// -------------------------------------------------------------- Merlin + challenges ---
+struct Transcript {
+    Strobe128 s;
+    void init(const char* label) {
+        s.init((const uint8_t*)"Merlin v1.0", 11);
+        append("dom-sep", (const uint8_t*)label, strlen(label));
+    }
+    void append(const char* label, const uint8_t* msg, size_t n) {
+        uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+        s.meta_ad((const uint8_t*)label, strlen(label), false);
+        s.meta_ad(len, 4, true);
+        s.ad(msg, n, false);
+    }
+    void append_point(const char* label, const uint8_t* p48) { append(label, p48, 48); }
+    void append_fr(const char* label, const HFr& v) { uint8_t b[32]; fr_to_bytes(b, v); append(label, b, 32); }
+    void challenge_bytes(const char* label, uint8_t* out, size_t n) {
+        uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+        s.meta_ad((const uint8_t*)label, strlen(label), false);
+        s.meta_ad(len, 4, true);
+        s.prf(out, n, false);
+    }
+    // rejection-sample a non-zero scalar < r, then bind it back (curdleproofs_transcript.py:15-25)
+    HFr challenge(const char* label) {
+        for (;;) {
+            uint8_t raw[32];
+            challenge_bytes(label, raw, 32);
+            HFr v;
+            if (!fr_from_bytes(&v, raw) || fr_is_zero(v)) continue;
+            append(label, raw, 32);
+            return v;
+        }
+    }
+};
+
+}  // namespace cpgh

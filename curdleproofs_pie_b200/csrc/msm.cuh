@@ -50,6 +50,7 @@ struct MsmShape {
 
 // 1 --- counting sort of the digits of one (msm, window) ----------------------------------
 struct SortDigits {
+    static constexpr const char* kName = "SortDigits";
     MsmShape s; Recode rc;
     const uint32_t* scalars;      // [B][n][8] canonical little-endian
     uint32_t* boff;               // [B*W][NB+1] bucket start offsets (out)
@@ -82,6 +83,7 @@ struct SortDigits {
 
 // 2 --- one bucket: sum of its (signed) bases, mixed XYZZ adds ------------------------------
 struct BucketAccumulate {
+    static constexpr const char* kName = "BucketAccumulate";
     MsmShape s;
     const Aff* bases;
     const uint32_t* boff;
@@ -108,6 +110,7 @@ struct BucketAccumulate {
 
 // 3 --- one window: sum_b (b+1) * S_b by running sums ---------------------------------------
 struct WindowReduce {
+    static constexpr const char* kName = "WindowReduce";
     MsmShape s;
     const Xyzz* buckets;
     Xyzz* wsum;                   // [B*W] (out)
@@ -124,6 +127,7 @@ struct WindowReduce {
 
 // 4 --- one msm: Horner over its windows ----------------------------------------------------
 struct Horner {
+    static constexpr const char* kName = "Horner";
     MsmShape s;
     const Xyzz* wsum;
     Jac* out;                     // [B]
@@ -144,6 +148,7 @@ struct Horner {
 struct FixedShape { uint32_t nb, c, W, NB; };
 
 struct FixedTableRows {            // thread = (base i, window w): the NB multiples, Jacobian scratch
+    static constexpr const char* kName = "FixedTableRows";
     FixedShape s;
     const Aff* bases;
     Jac* rows;                     // [nb*W][NB]
@@ -157,14 +162,17 @@ struct FixedTableRows {            // thread = (base i, window w): the NB multip
     }
 };
 struct JacToAff {                  // thread = one point (one Fq inversion each)
+    static constexpr const char* kName = "JacToAff";
     const Jac* in; Aff* out;
     CPG_HD void operator()(uint64_t t) const { out[t] = jac_to_aff(in[t]); }
 };
 struct AffToJac {
+    static constexpr const char* kName = "AffToJac";
     const Aff* in; Jac* out;
     CPG_HD void operator()(uint64_t t) const { out[t] = to_jac(in[t]); }
 };
 struct FixedMsmWindow {            // thread = (msm, window): sum_i +-T[i][w][|d|-1]
+    static constexpr const char* kName = "FixedMsmWindow";
     FixedShape s; Recode rc;
     uint32_t B;
     const Aff* table;
@@ -187,6 +195,7 @@ struct FixedMsmWindow {            // thread = (msm, window): sum_i +-T[i][w][|d
     }
 };
 struct SumWindows {                // thread = msm: plain sum of W partials (no doublings)
+    static constexpr const char* kName = "SumWindows";
     uint32_t W;
     const Xyzz* partial;
     Jac* out;
@@ -202,6 +211,7 @@ struct SumWindows {                // thread = msm: plain sum of W partials (no 
 
 // ---- element-wise kernels (vector scalar-mul, fold, group law, serialisation) ---------------
 struct Decompress {
+    static constexpr const char* kName = "Decompress";
     const uint8_t* in; int check; Aff* out; uint8_t* err;
     CPG_HD void operator()(uint64_t t) const {
         Aff a;
@@ -211,40 +221,49 @@ struct Decompress {
     }
 };
 struct CompressJac {
+    static constexpr const char* kName = "CompressJac";
     const Jac* in; uint8_t* out;
     CPG_HD void operator()(uint64_t t) const { aff_compress(jac_to_aff(in[t]), out + 48 * t); }
 };
 struct CompressAff {
+    static constexpr const char* kName = "CompressAff";
     const Aff* in; uint8_t* out;
     CPG_HD void operator()(uint64_t t) const { aff_compress(in[t], out + 48 * t); }
 };
 struct AddPoints {                 // op 0: a+b, 1: a-b
+    static constexpr const char* kName = "AddPoints";
     const Jac* a; const Jac* b; Jac* out; int op;
     CPG_HD void operator()(uint64_t t) const { out[t] = jac_add(a[t], op ? neg(b[t]) : b[t]); }
 };
 struct NegPoints {
+    static constexpr const char* kName = "NegPoints";
     const Jac* a; Jac* out;
     CPG_HD void operator()(uint64_t t) const { out[t] = neg(a[t]); }
 };
 struct EqPoints {
+    static constexpr const char* kName = "EqPoints";
     const Jac* a; const Jac* b; uint8_t* out;
     CPG_HD void operator()(uint64_t t) const { out[t] = jac_eq(a[t], b[t]) ? 1 : 0; }
 };
 struct IsInfPoints {
+    static constexpr const char* kName = "IsInfPoints";
     const Jac* a; uint8_t* out;
     CPG_HD void operator()(uint64_t t) const { out[t] = is_inf(a[t]) ? 1 : 0; }
 };
 struct MulPoints {                 // out[t] = k[t / group] * p[t]   (group = 1: one scalar per point)
+    static constexpr const char* kName = "MulPoints";
     const Jac* p; const uint32_t* k; uint64_t group; Jac* out;
     CPG_HD void operator()(uint64_t t) const { out[t] = jac_mul(p[t], k + 8 * (t / group)); }
 };
 struct FoldPoints {                // out[r][i] = L[r][i] + x[r] * R[r][i],  r < rows, i < m
+    static constexpr const char* kName = "FoldPoints";
     const Jac* L; const Jac* R; const uint32_t* x; uint64_t m; Jac* out;
     CPG_HD void operator()(uint64_t t) const { out[t] = jac_add(L[t], jac_mul(R[t], x + 8 * (t / m))); }
 };
 
 // ---- Fr vector ops on canonical little-endian words (K7) ------------------------------------
 struct FrBinary {                  // op 0 add, 1 sub, 2 mul
+    static constexpr const char* kName = "FrBinary";
     const uint32_t* a; const uint32_t* b; uint32_t* out; int op;
     CPG_HD void operator()(uint64_t t) const {
         Fr x, y, z;
@@ -256,6 +275,7 @@ struct FrBinary {                  // op 0 add, 1 sub, 2 mul
     }
 };
 struct FrInverse {                 // 0 -> 0 (cp/util.py:51-54 relies on a value coming back)
+    static constexpr const char* kName = "FrInverse";
     const uint32_t* a; uint32_t* out;
     CPG_HD void operator()(uint64_t t) const {
         Fr x;

@@ -40,6 +40,9 @@ _SIGS = {
     "cpg_timer_start": (_c.c_int, []),
     "cpg_timer_stop": (_c.c_int, [_c.POINTER(_c.c_float)]),
     "cpg_launch_count": (_c.c_uint64, []),
+    "cpg_profile_enable": (_c.c_int, [_c.c_int]),
+    "cpg_profile_reset": (_c.c_int, []),
+    "cpg_profile_report": (_c.c_int, [_c.c_char_p, _c.c_size_t]),
     "cpg_g1_decompress": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "cpg_g1_compress": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "cpg_g1_compress_aff": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p]),
@@ -63,6 +66,13 @@ _SIGS = {
     "cpg_fr_sub": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "cpg_fr_mul": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "cpg_fr_inverse": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "cpg_verifier_create": (_c.c_void_p, [_c.c_char_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_int]),
+    "cpg_verifier_free": (_c.c_int, [_c.c_void_p]),
+    "cpg_verifier_proof_bytes": (_c.c_size_t, [_c.c_void_p]),
+    "cpg_verifier_input_bytes": (_c.c_size_t, [_c.c_void_p]),
+    "cpg_verifier_set_window": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "cpg_verify_batch": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_char_p, _c.c_size_t, _c.c_char_p]),
+    "cpg_verify_replay_device": (_c.c_int, [_c.c_void_p, _c.c_char_p]),
     "cpg_bench_int_pipe": (_c.c_int, [_c.c_int, _c.c_uint64, _c.POINTER(_c.c_double), _c.POINTER(_c.c_float)]),
 }
 EXPORTS = tuple(sorted(_SIGS))
@@ -261,6 +271,17 @@ class CpgLib:
         ms = ctypes.c_float()
         self.check(self.c.cpg_bench_int_pipe(kind, iters, ctypes.byref(per_s), ctypes.byref(ms)), "cpg_bench_int_pipe")
         return per_s.value, ms.value
+
+    def profile(self, on):
+        self.check(self.c.cpg_profile_reset(), "cpg_profile_reset")
+        self.check(self.c.cpg_profile_enable(1 if on else 0), "cpg_profile_enable")
+
+    def profile_report(self):
+        import json
+
+        buf = ctypes.create_string_buffer(1 << 16)
+        self.check(self.c.cpg_profile_report(buf, len(buf)), "cpg_profile_report")
+        return json.loads(buf.value.decode() or "{}")
 
     def timer_start(self):
         self.check(self.c.cpg_timer_start(), "cpg_timer_start")

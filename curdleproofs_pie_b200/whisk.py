@@ -1,0 +1,102 @@
+"""Batched Whisk-facing API: the reference's bytes-in / bool-out entry points, B proofs per call.
+
+Mirrors /root/reference/curdleproofs/curdleproofs/whisk_interface.py:
+    IsValidWhiskShuffleProof(crs, pre_trackers, post_trackers, proof_bytes) -> bool        (:74-87)
+becomes
+    IsValidWhiskShuffleProofBatch(crs, [pre_trackers], [post_trackers], [proof_bytes]) -> [bool]
+with the same acceptance rule per proof (any decoding problem or failed check -> False).
+All group arithmetic runs on the GPU through cpg_verify_batch (include/cpg.h); there is no CPU path.
+"""
+import ctypes
+
+from . import runtime as _rt
+
+
+class BatchVerifier:
+    """Holds the device-resident CRS (fixed-base tables) for one (ell, n_blinders)."""
+
+    def __init__(self, crs_bytes, ell, n_blinders=4, fixed_window=8, host_threads=0, lib=None):
+        self.lib = lib or _rt.get_lib()
+        self.ell = int(ell)
+        self.n_blinders = int(n_blinders)
+        crs_bytes = bytes(crs_bytes)
+        if len(crs_bytes) != 48 * (self.ell + self.n_blinders + 5):
+            raise ValueError("crs_bytes must be CurdleproofsCrs.to_bytes() for (ell, n_blinders)")
+        self.handle = self.lib.c.cpg_verifier_create(crs_bytes, self.ell, self.n_blinders, fixed_window, host_threads)
+        if not self.handle:
+            raise _rt.CpgError("cpg_verifier_create failed: " + self.lib.last_error())
+        self.proof_len = int(self.lib.c.cpg_verifier_proof_bytes(self.handle))
+        self.input_len = int(self.lib.c.cpg_verifier_input_bytes(self.handle))
+
+    def set_window(self, c):
+        self.lib.check(self.lib.c.cpg_verifier_set_window(self.handle, int(c)), "cpg_verifier_set_window")
+
+    def verify_raw(self, inputs, proofs, B):
+        """inputs: B*input_len bytes, proofs: B*proof_len bytes -> bytes of B verdicts."""
+        out = ctypes.create_string_buffer(max(1, B))
+        self.lib.check(self.lib.c.cpg_verify_batch(self.handle, inputs, proofs, B, out), "cpg_verify_batch")
+        return out.raw[:B]
+
+    def verify(self, inputs, proofs):
+        """inputs[i] = vec_R|vec_S|vec_T|vec_U (48-byte points), proofs[i] = M|proof wire bytes.
+        Wrong-length entries are rejected (the reference's BufReader would raise -> False)."""
+        B = len(inputs)
+        if len(proofs) != B:
+            raise ValueError("inputs and proofs must have the same length")
+        ok_len = [len(inputs[i]) == self.input_len and len(proofs[i]) >= self.proof_len for i in range(B)]
+        idx = [i for i in range(B) if ok_len[i]]
+        verdicts = [False] * B
+        if idx:
+            raw = self.verify_raw(b"".join(bytes(inputs[i]) for i in idx), b"".join(bytes(proofs[i])[:self.proof_len] for i in idx), len(idx))
+            for j, i in enumerate(idx):
+                verdicts[i] = bool(raw[j])
+        return verdicts
+
+    def close(self):
+        if self.handle:
+            self.lib.c.cpg_verifier_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def trackers_to_input(pre_trackers, post_trackers):
+    """[(r_G, k_r_G)...] pre/post -> vec_R|vec_S|vec_T|vec_U bytes (whisk_interface.py:96-100).
+    Trackers may be WhiskTracker-like objects (.r_G/.k_r_G) or (r_G, k_r_G) tuples."""
+    def halves(ts):
+        a, b = [], []
+        for t in ts:
+            r, k = (t.r_G, t.k_r_G) if hasattr(t, "r_G") else t
+            a.append(bytes(r)); b.append(bytes(k))
+        return b"".join(a), b"".join(b)
+
+    R, S = halves(pre_trackers)
+    T, U = halves(post_trackers)
+    return R + S + T + U
+
+
+_CACHE = {}
+
+
+def IsValidWhiskShuffleProofBatch(crs, pre_shuffle_trackers, post_shuffle_trackers, whisk_shuffle_proofs):
+    """crs: object with to_bytes()/vec_G/vec_H (the reference's CurdleproofsCrs) or (crs_bytes, ell)."""
+    if isinstance(crs, tuple):
+        crs_bytes, ell = crs
+        nbl = 4
+    else:
+        crs_bytes, ell, nbl = crs.to_bytes(), len(crs.vec_G), len(crs.vec_H)
+    key = (bytes(crs_bytes), ell, nbl)
+    ver = _CACHE.get(key)
+    if ver is None:
+        ver = _CACHE[key] = BatchVerifier(crs_bytes, ell, nbl)
+    inputs = []
+    for pre, post in zip(pre_shuffle_trackers, post_shuffle_trackers):
+        try:
+            inputs.append(trackers_to_input(pre, post))
+        except Exception:
+            inputs.append(b"")
+    return ver.verify(inputs, list(whisk_shuffle_proofs))

@@ -56,6 +56,11 @@ int cpg_host_free(void* h_ptr);
 int cpg_timer_start(void);
 int cpg_timer_stop(float* ms);                  /* synchronises */
 uint64_t cpg_launch_count(void);                /* kernels launched by this library so far */
+/* per-kernel device time: when enabled every launch is bracketed by a CUDA event pair on its
+ * stream; report() synchronises and writes JSON {"Kernel": {"ms":..,"launches":..,"threads":..}} */
+int cpg_profile_enable(int on);
+int cpg_profile_reset(void);
+int cpg_profile_report(char* buf, size_t cap);
 
 /* ---- serialisation -------------------------------------------------------------------------
  * replaces G1Point.from_compressed_bytes (stub :19, check_subgroup=1) and
@@ -105,10 +110,29 @@ int cpg_fr_sub(const uint8_t* d_a, const uint8_t* d_b, size_t k, uint8_t* d_out)
 int cpg_fr_mul(const uint8_t* d_a, const uint8_t* d_b, size_t k, uint8_t* d_out);
 int cpg_fr_inverse(const uint8_t* d_a, size_t k, uint8_t* d_out);   /* inverse(0) = 0, cp/util.py:51-54 */
 
+/* ---- batched shuffle-proof verification -------------------------------------------------------
+ * Replaces, for B proofs at once, IsValidWhiskShuffleProof (cp/whisk_interface.py:74-108) ->
+ * CurdleProofsProof.verify (cp/curdleproofs.py:162-248) and everything below it.  The transcript
+ * and the Fr coefficient algebra run on `host_threads` host threads (0 = all cores); every group
+ * operation runs on the GPU (decompress, D / A', one MSM per proof).
+ *   crs_bytes : (ell + n_blinders + 5) * 48 B = CurdleproofsCrs.to_bytes (cp/crs.py:93-102)
+ *   inputs    : [B][4*ell*48]  vec_R | vec_S | vec_T | vec_U  (tracker halves, whisk_interface.py:96-100)
+ *   proofs    : [B][cpg_verifier_proof_bytes]  M | proof      (WhiskShuffleProof.to_bytes, :57-61)
+ *   verdicts  : [B], 1 = the reference would return True */
+void* cpg_verifier_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window, int host_threads);
+int cpg_verifier_free(void* verifier);
+size_t cpg_verifier_proof_bytes(const void* verifier);
+size_t cpg_verifier_input_bytes(const void* verifier);
+int cpg_verifier_set_window(void* verifier, int var_window);
+int cpg_verify_batch(void* verifier, const uint8_t* inputs, const uint8_t* proofs, size_t B, uint8_t* verdicts);
+/* re-run the device side (decompress, D/A', MSM, test) of the last batch on its resident inputs */
+int cpg_verify_replay_device(void* verifier, uint8_t* verdicts_or_null);
+
 /* ---- roofline support: saturating integer-pipe microbenchmark ---------------------------------
  * Runs `iters` dependent-chain steps of 32x32->64 multiply-accumulates on every SM and reports
- * the achieved MAC/s (kind 0: IMAD.WIDE.U32 chains, kind 1: IMAD.LO+IMAD.HI pairs) and the
- * Fq Montgomery products/s of this library's own field code (kind 2). */
+ * the achieved rate: kind 0 = 32x32->64 MAC/s of data-dependent IMAD.WIDE.U32 chains (THE roofline
+ * denominator: 32 lanes/clk/SM on B200), kind 1 = 32-bit IMAD/s (full-rate, context only),
+ * kind 2 = Fq Montgomery products/s of this library's own field code. */
 int cpg_bench_int_pipe(int kind, uint64_t iters, double* per_second, float* ms);
 
 #ifdef __cplusplus

