@@ -167,6 +167,8 @@ def run_ours_verify(args, rank, world, dist):
     c = args.window or pick_window(NV)
     ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), ell, host_threads=args.host_threads)
     ver.set_window(c)
+    ver.set_transcript(args.transcript == "device")
+    ver.set_streams(args.streams)
     inputs, proofs, expected = make_verify_batch(case, B)
     out = ctypes.create_string_buffer(B)
 
@@ -176,13 +178,9 @@ def run_ours_verify(args, rank, world, dist):
             dist.barrier()
 
     def max_over_ranks(ms):
-        if dist is None:
-            return ms
-        import torch
+        from curdleproofs_pie_b200 import sharding
 
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(ms, dist, device="cuda")
 
     def step_e2e():
         lib.check(lib.c.cpg_verify_batch(ver.handle, inputs, proofs, B, out), "cpg_verify_batch")
@@ -255,10 +253,11 @@ def run_ours_verify(args, rank, world, dist):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fq, 255-bit Fr)", "data": "synthetic",
         "config": {"workload": "batch verification of Whisk-size (n=128, ell=124) curdleproofs, B=%d proofs per GPU per step; "
                                "reference-generated golden proof replicated, lane-unique weights, 1/64 lanes corrupted, verdicts checked" % B,
-                   "B_per_gpu": B, "n": n, "var_terms": NV, "fixed_terms": NF, "window": c,
+                   "B_per_gpu": B, "n": n, "var_terms": NV, "fixed_terms": NF, "window": c, "transcript": args.transcript, "streams": args.streams,
                    "l2": "inputs_larger_than_l2 (%.0f MB wire + scalars per step)" % (B * (NV * 80 + NF * 32) / 1e6), "sharding": "per-proof, no collective"},
         "e2e": {"value": total * args.steps / (ms_e2e * 1e-3), "unit": "verifications/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": B * (NV * 48 + 64 + NV * 32 + NF * 32), "d2h_bytes_per_step": B * (96 + NV + 2),
+                "h2d_bytes_per_step": B * (NV * 48 + 7 * 32 + (0 if args.transcript == "device" else 64 + NV * 32 + NF * 32 + 1)),
+                "d2h_bytes_per_step": B * (1 + (0 if args.transcript == "device" else 96 + NV + 1)),
                 "host_threads": args.host_threads or (os.cpu_count() or 1)},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
@@ -382,13 +381,9 @@ def run_ours(args, rank, world, dist):
             dist.barrier()
 
     def max_over_ranks(ms):
-        if dist is None:
-            return ms
-        import torch
+        from curdleproofs_pie_b200 import sharding
 
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(ms, dist, device="cuda")
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -547,6 +542,8 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="proofs (or MSMs) per GPU per step")
     ap.add_argument("--n", type=int, default=128)
     ap.add_argument("--window", type=int, default=0, help="bucket window width (0 = from the work model)")
+    ap.add_argument("--transcript", default="device", choices=["device", "host"], help="where the Fiat-Shamir transcript + coefficient algebra run")
+    ap.add_argument("--streams", type=int, default=1, help="sub-batches in flight on separate CUDA streams")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads for the transcript (0 = all cores)")
     ap.add_argument("--cpu-sample", type=int, default=400, help="MSMs in the bounded CPU sample (msm workload)")
     ap.add_argument("--cpu-sample-verify", type=int, default=24, help="verifications in the bounded CPU sample")

@@ -46,8 +46,8 @@ int ck(cudaError_t e, const char* what) {
 }
 #define CK(x) do { if (int rc_ = ck((x), #x)) return rc_; } while (0)
 
-template <class F, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_each(const F f, uint64_t n) {
+template <class F, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_each(const F f, uint64_t n) {
     uint64_t t = blockIdx.x * (uint64_t)BLOCK + threadIdx.x;
     if (t < n) f(t);
 }
@@ -58,7 +58,7 @@ bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 std::mutex g_prof_mu;
 
-template <int BLOCK = 128, class F>
+template <int BLOCK = 128, int MINB = 1, class F>
 int launch(const F& f, uint64_t n) {
     if (!n) return 0;
     uint64_t grid = (n + BLOCK - 1) / BLOCK;
@@ -68,7 +68,7 @@ int launch(const F& f, uint64_t n) {
         cudaEventCreate(&rec.a); cudaEventCreate(&rec.b);
         cudaEventRecord(rec.a, cur());
     }
-    k_each<F, BLOCK><<<(unsigned)grid, BLOCK, 0, cur()>>>(f, n);
+    k_each<F, BLOCK, MINB><<<(unsigned)grid, BLOCK, 0, cur()>>>(f, n);
     if (g_prof_on) {
         cudaEventRecord(rec.b, cur());
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -85,7 +85,7 @@ void* scratch_alloc(size_t bytes) {
 void scratch_free(void* p) { if (p) cudaFreeAsync(p, cur()); }
 #else
 // ---- host emulation (test seam) ----
-template <int BLOCK = 128, class F>
+template <int BLOCK = 128, int MINB = 1, class F>
 int launch(const F& f, uint64_t n) {
     g_launches++;
 #pragma omp parallel for schedule(dynamic, 8)
@@ -449,7 +449,7 @@ int cpg_g1_msm_batched(const void* d_bases, size_t base_stride, const uint8_t* d
     Recode rc = make_recode(c);
     MsmShape s; s.n = (uint32_t)n; s.c = c; s.W = rc.W; s.NB = 1u << (c - 1); s.base_stride = base_stride;
     // bound scratch to ~6 GiB per chunk of MSMs
-    size_t per_msm = (size_t)s.W * ((size_t)(s.NB + 1) * 4 + (size_t)n * 4 + (size_t)s.NB * sizeof(Xyzz) + sizeof(Xyzz));
+    size_t per_msm = (size_t)s.W * ((size_t)(s.NB + 1) * 4 + (size_t)n * 6 + (size_t)s.NB * (sizeof(Xyzz) + 2) + sizeof(Xyzz));
     size_t chunk = (size_t)6 << 30;
     chunk = chunk / per_msm; if (chunk < 1) chunk = 1; if (chunk > B) chunk = B;
     for (size_t b0 = 0; b0 < B; b0 += chunk) {
@@ -459,13 +459,20 @@ int cpg_g1_msm_batched(const void* d_bases, size_t base_stride, const uint8_t* d
         Scratch sc;
         uint32_t* boff = sc.get<uint32_t>(BW * (s.NB + 1));
         uint32_t* sorted = sc.get<uint32_t>(BW * n);
+        const bool balanced = s.NB <= 256;
+        uint16_t* rank = balanced ? sc.get<uint16_t>(BW * s.NB) : nullptr;
+        if (balanced && !rank) return fail("cpg_g1_msm_batched: scratch allocation failed");
         Xyzz* buckets = sc.get<Xyzz>(BW * s.NB);
         Xyzz* wsum = sc.get<Xyzz>(BW);
         if (!boff || !sorted || !buckets || !wsum) return fail("cpg_g1_msm_batched: scratch allocation failed");
         const uint32_t* ks = (const uint32_t*)d_scalars + (uint64_t)b0 * n * 8;
         const Aff* bases = (const Aff*)d_bases + (uint64_t)b0 * base_stride;
-        if (int r = launch(SortDigits{s, rc, ks, boff, sorted}, BW)) return r;
-        if (int r = launch(BucketAccumulate{s, bases, boff, sorted, nullptr, buckets}, BW * s.NB)) return r;
+        int16_t* dig = sc.get<int16_t>((uint64_t)nb * n * s.W);
+        if (!dig) return fail("cpg_g1_msm_batched: scratch allocation failed");
+        if (int r = launch(RecodeDigits{s, rc, ks, dig}, (uint64_t)nb * n)) return r;
+        if (int r = launch(SortDigits{s, dig, boff, sorted, rank}, BW)) return r;
+        uint64_t nthreads = balanced ? (((uint64_t)nb + 31) / 32) * 32 * s.W * s.NB : BW * s.NB;
+        if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, rank, BW, buckets}, nthreads)) return r;
         if (int r = launch(WindowReduce{s, buckets, wsum}, BW)) return r;
         if (int r = launch(Horner{s, wsum, (Jac*)d_out + b0}, nb)) return r;
     }

@@ -1,6 +1,7 @@
-// Host side of the batched prover/verifier: the sequential Fiat-Shamir transcript (stays on the
-// host per the north star) and the HFr bookkeeping that turns challenges into MSM coefficients.
-// Plain C++ (no CUDA).  Follows the reference, restated independently of oracle/:
+// The sequential Fiat-Shamir transcript and the Fr bookkeeping that turns challenges into MSM
+// coefficients.  Plain C++ in CPG_HD functions: the batched verifier runs this code either on host
+// threads (the north star's default placement) or, one proof per thread, as a GPU kernel
+//  - the same source either way.  Follows the reference, restated independently of oracle/:
 //   Keccak-f[1600]      /root/reference/merlin_transcripts/merlin_transcripts/keccak.py:16-66
 //   STROBE-128, R=166   merlin_transcripts/merlin_transcripts/strobe.py:16-107
 //   Merlin framing      merlin_transcripts/merlin_transcripts/merlin_transcript.py:6-24
@@ -11,19 +12,37 @@
 #include <stdint.h>
 #include <string.h>
 
+#ifndef CPG_HD
+#define CPG_HD inline
+#endif
+#if defined(__CUDACC__)
+#define CPGH_CONST static __device__ __constant__
+#else
+#define CPGH_CONST static const
+#endif
+#ifdef __CUDA_ARCH__
+#define CPGH_SEL(name) D_##name
+#else
+#define CPGH_SEL(name) H_##name
+#endif
+
 namespace cpgh {
 
 typedef unsigned __int128 u128;
 
 // ---------------------------------------------------------------- Keccak-f[1600] ---
-static inline uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
-static const uint64_t KECCAK_RC[24] = {
-    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL,
-    0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL,
-    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL,
-    0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
+CPG_HD uint64_t rotl64(uint64_t x, int n) { return (x << n) | (x >> (64 - n)); }
+#define CPGH_KECCAK_RC_INIT { \
+    0x0000000000000001ULL, 0x0000000000008082ULL, 0x800000000000808aULL, 0x8000000080008000ULL, 0x000000000000808bULL, 0x0000000080000001ULL, \
+    0x8000000080008081ULL, 0x8000000000008009ULL, 0x000000000000008aULL, 0x0000000000000088ULL, 0x0000000080008009ULL, 0x000000008000000aULL, \
+    0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL, 0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, \
+    0x000000000000800aULL, 0x800000008000000aULL, 0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL}
+static const uint64_t H_KECCAK_RC[24] = CPGH_KECCAK_RC_INIT;
+#if defined(__CUDACC__)
+static __device__ __constant__ uint64_t D_KECCAK_RC[24] = CPGH_KECCAK_RC_INIT;
+#endif
 
-static inline void keccak_f1600(uint64_t* A) {
+CPG_HD void keccak_f1600(uint64_t* A) {
     for (int r = 0; r < 24; r++) {
         uint64_t C0 = A[0] ^ A[5] ^ A[10] ^ A[15] ^ A[20], C1 = A[1] ^ A[6] ^ A[11] ^ A[16] ^ A[21];
         uint64_t C2 = A[2] ^ A[7] ^ A[12] ^ A[17] ^ A[22], C3 = A[3] ^ A[8] ^ A[13] ^ A[18] ^ A[23];
@@ -44,7 +63,7 @@ static inline void keccak_f1600(uint64_t* A) {
             A[y + 3] = B[y + 3] ^ (~B[y + 4] & B[y + 0]);
             A[y + 4] = B[y + 4] ^ (~B[y + 0] & B[y + 1]);
         }
-        A[0] ^= KECCAK_RC[r];
+        A[0] ^= CPGH_SEL(KECCAK_RC)[r];
     }
 }
 
@@ -56,17 +75,18 @@ struct Strobe128 {
     uint8_t pos, pos_begin, flags;
     uint64_t permutations;
 
-    void init(const uint8_t* label, size_t n) {
+    CPG_HD void init(const uint8_t* label, size_t n) {
         memset(st.b, 0, 200);
         const uint8_t hdr[6] = {1, RATE + 2, 1, 0, 1, 96};
         memcpy(st.b, hdr, 6);
-        memcpy(st.b + 6, "STROBEv1.0.2", 12);
+        const uint8_t ver[12] = {'S', 'T', 'R', 'O', 'B', 'E', 'v', '1', '.', '0', '.', '2'};
+        memcpy(st.b + 6, ver, 12);
         keccak_f1600(st.w);
         pos = pos_begin = flags = 0;
         permutations = 1;
         meta_ad(label, n, false);
     }
-    void run_f() {
+    CPG_HD void run_f() {
         st.b[pos] ^= pos_begin;
         st.b[pos + 1] ^= 0x04;
         st.b[RATE + 1] ^= 0x80;
@@ -74,7 +94,7 @@ struct Strobe128 {
         permutations++;
         pos = pos_begin = 0;
     }
-    void absorb(const uint8_t* d, size_t n) {
+    CPG_HD void absorb(const uint8_t* d, size_t n) {
         while (n) {
             size_t room = RATE - pos, take = n < room ? n : room;
             for (size_t i = 0; i < take; i++) st.b[pos + i] ^= d[i];
@@ -82,7 +102,7 @@ struct Strobe128 {
             if (pos == RATE) run_f();
         }
     }
-    void begin_op(uint8_t fl, bool more) {
+    CPG_HD void begin_op(uint8_t fl, bool more) {
         if (more) return;                         // continuation of the same operation
         uint8_t old = pos_begin;
         pos_begin = pos + 1;
@@ -91,9 +111,9 @@ struct Strobe128 {
         absorb(hdr, 2);
         if ((fl & (F_C | F_K)) && pos != 0) run_f();
     }
-    void meta_ad(const uint8_t* d, size_t n, bool more) { begin_op(F_M | F_A, more); absorb(d, n); }
-    void ad(const uint8_t* d, size_t n, bool more) { begin_op(F_A, more); absorb(d, n); }
-    void prf(uint8_t* out, size_t n, bool more) {
+    CPG_HD void meta_ad(const uint8_t* d, size_t n, bool more) { begin_op(F_M | F_A, more); absorb(d, n); }
+    CPG_HD void ad(const uint8_t* d, size_t n, bool more) { begin_op(F_A, more); absorb(d, n); }
+    CPG_HD void prf(uint8_t* out, size_t n, bool more) {
         begin_op(F_I | F_A | F_C, more);
         for (size_t i = 0; i < n; i++) {
             out[i] = st.b[pos];
@@ -107,32 +127,43 @@ struct Strobe128 {
 // ------------------------------------------------------------------------- Fr (host) ---
 // 4 x u64 Montgomery arithmetic mod r; values are kept in Montgomery form inside `HFr` (host Fr).
 struct HFr { uint64_t l[4]; };
-static const uint64_t FR_MOD[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
-static const uint64_t FR_INV = 0xfffffffeffffffffULL;   // -r^-1 mod 2^64
-static const HFr FR_R1 = {{0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL, 0x1824b159acc5056fULL}};  // 2^256 mod r
-static const HFr FR_R2 = {{0xc999e990f3f29c6dULL, 0x2b6cedcb87925c23ULL, 0x05d314967254398fULL, 0x0748d9d99f59ff11ULL}};  // 2^512 mod r
+#define CPGH_FR_MOD_INIT {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL}
+#define CPGH_FR_R1_INIT {0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL, 0x1824b159acc5056fULL}  /* 2^256 mod r */
+#define CPGH_FR_R2_INIT {0xc999e990f3f29c6dULL, 0x2b6cedcb87925c23ULL, 0x05d314967254398fULL, 0x0748d9d99f59ff11ULL}  /* 2^512 mod r */
+static const uint64_t H_FR_MOD[4] = CPGH_FR_MOD_INIT;
+static const uint64_t H_FR_R1[4] = CPGH_FR_R1_INIT;
+static const uint64_t H_FR_R2[4] = CPGH_FR_R2_INIT;
+#if defined(__CUDACC__)
+static __device__ __constant__ uint64_t D_FR_MOD[4] = CPGH_FR_MOD_INIT;
+static __device__ __constant__ uint64_t D_FR_R1[4] = CPGH_FR_R1_INIT;
+static __device__ __constant__ uint64_t D_FR_R2[4] = CPGH_FR_R2_INIT;
+#endif
+#define FR_MOD CPGH_SEL(FR_MOD)
+static const uint64_t FR_INV = 0xfffffffeffffffffULL;   // -r^-1 mod 2^64 (scalar constant: usable on both sides)
+CPG_HD HFr fr_r1() { HFr r; for (int i = 0; i < 4; i++) r.l[i] = CPGH_SEL(FR_R1)[i]; return r; }
+CPG_HD HFr fr_r2() { HFr r; for (int i = 0; i < 4; i++) r.l[i] = CPGH_SEL(FR_R2)[i]; return r; }
 
-static inline bool fr_geq_mod(const uint64_t* a) {
+CPG_HD bool fr_geq_mod(const uint64_t* a) {
     for (int i = 3; i >= 0; i--) { if (a[i] > FR_MOD[i]) return true; if (a[i] < FR_MOD[i]) return false; }
     return true;
 }
-static inline void fr_sub_mod(uint64_t* a) {
+CPG_HD void fr_sub_mod(uint64_t* a) {
     u128 br = 0;
     for (int i = 0; i < 4; i++) { u128 d = (u128)a[i] - FR_MOD[i] - (uint64_t)br; a[i] = (uint64_t)d; br = (d >> 64) & 1; }
 }
-static inline HFr fr_add(const HFr& a, const HFr& b) {
+CPG_HD HFr fr_add(const HFr& a, const HFr& b) {
     HFr r; u128 c = 0;
     for (int i = 0; i < 4; i++) { c += (u128)a.l[i] + b.l[i]; r.l[i] = (uint64_t)c; c >>= 64; }
     if (fr_geq_mod(r.l)) fr_sub_mod(r.l);      // 2r < 2^256: no carry out
     return r;
 }
-static inline HFr fr_sub(const HFr& a, const HFr& b) {
+CPG_HD HFr fr_sub(const HFr& a, const HFr& b) {
     HFr r; u128 br = 0;
     for (int i = 0; i < 4; i++) { u128 d = (u128)a.l[i] - b.l[i] - (uint64_t)br; r.l[i] = (uint64_t)d; br = (d >> 64) & 1; }
     if (br) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)r.l[i] + FR_MOD[i]; r.l[i] = (uint64_t)c; c >>= 64; } }
     return r;
 }
-static inline HFr fr_mul(const HFr& a, const HFr& b) {
+CPG_HD HFr fr_mul(const HFr& a, const HFr& b) {
     uint64_t t[5] = {0, 0, 0, 0, 0};
     for (int i = 0; i < 4; i++) {
         u128 c = 0;
@@ -147,30 +178,30 @@ static inline HFr fr_mul(const HFr& a, const HFr& b) {
     if (t[4] || fr_geq_mod(r.l)) fr_sub_mod(r.l);
     return r;
 }
-static inline HFr fr_zero() { HFr r = {{0, 0, 0, 0}}; return r; }
-static inline HFr fr_one() { return FR_R1; }
-static inline bool fr_is_zero(const HFr& a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
-static inline bool fr_eq(const HFr& a, const HFr& b) { return a.l[0] == b.l[0] && a.l[1] == b.l[1] && a.l[2] == b.l[2] && a.l[3] == b.l[3]; }
-static inline HFr fr_neg(const HFr& a) { return fr_sub(fr_zero(), a); }
-static inline HFr fr_from_u64(uint64_t v) { HFr r = {{v, 0, 0, 0}}; return fr_mul(r, FR_R2); }
+CPG_HD HFr fr_zero() { HFr r = {{0, 0, 0, 0}}; return r; }
+CPG_HD HFr fr_one() { return fr_r1(); }
+CPG_HD bool fr_is_zero(const HFr& a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
+CPG_HD bool fr_eq(const HFr& a, const HFr& b) { return a.l[0] == b.l[0] && a.l[1] == b.l[1] && a.l[2] == b.l[2] && a.l[3] == b.l[3]; }
+CPG_HD HFr fr_neg(const HFr& a) { return fr_sub(fr_zero(), a); }
+CPG_HD HFr fr_from_u64(uint64_t v) { HFr r = {{v, 0, 0, 0}}; return fr_mul(r, fr_r2()); }
 // canonical 32-byte little-endian -> HFr; false if >= r
-static inline bool fr_from_bytes(HFr* out, const uint8_t* b) {
+CPG_HD bool fr_from_bytes(HFr* out, const uint8_t* b) {
     HFr r; memcpy(r.l, b, 32);
     if (fr_geq_mod(r.l)) return false;
-    *out = fr_mul(r, FR_R2);
+    *out = fr_mul(r, fr_r2());
     return true;
 }
-static inline void fr_to_bytes(uint8_t* b, const HFr& a) {
+CPG_HD void fr_to_bytes(uint8_t* b, const HFr& a) {
     HFr one = {{1, 0, 0, 0}};
     HFr r = fr_mul(a, one);
     memcpy(b, r.l, 32);
 }
-static inline HFr fr_pow_u64(HFr a, uint64_t e) {
+CPG_HD HFr fr_pow_u64(HFr a, uint64_t e) {
     HFr r = fr_one();
     while (e) { if (e & 1) r = fr_mul(r, a); a = fr_mul(a, a); e >>= 1; }
     return r;
 }
-static inline HFr fr_inv(const HFr& a) {   // a^(r-2); 0 -> 0
+CPG_HD HFr fr_inv(const HFr& a) {   // a^(r-2); 0 -> 0
     uint64_t e[4] = {FR_MOD[0] - 2, FR_MOD[1], FR_MOD[2], FR_MOD[3]};
     HFr r = fr_one();
     for (int i = 255; i >= 0; i--) {
@@ -180,7 +211,7 @@ static inline HFr fr_inv(const HFr& a) {   // a^(r-2); 0 -> 0
     return r;
 }
 // in-place batch inversion (Montgomery's trick); zeros stay zero
-static inline void fr_batch_inv(HFr* v, size_t n, HFr* scratch) {
+CPG_HD void fr_batch_inv(HFr* v, size_t n, HFr* scratch) {
     HFr acc = fr_one();
     for (size_t i = 0; i < n; i++) { scratch[i] = acc; if (!fr_is_zero(v[i])) acc = fr_mul(acc, v[i]); }
     acc = fr_inv(acc);
@@ -193,28 +224,31 @@ static inline void fr_batch_inv(HFr* v, size_t n, HFr* scratch) {
 }
 
 // -------------------------------------------------------------- Merlin + challenges ---
+// Labels are string literals; their length is taken at compile time (no strlen in device code).
 struct Transcript {
     Strobe128 s;
-    void init(const char* label) {
-        s.init((const uint8_t*)"Merlin v1.0", 11);
-        append("dom-sep", (const uint8_t*)label, strlen(label));
+    template <size_t N> CPG_HD void init(const char (&label)[N]) {
+        const uint8_t merlin[11] = {'M', 'e', 'r', 'l', 'i', 'n', ' ', 'v', '1', '.', '0'};
+        s.init(merlin, 11);
+        const char ds[8] = "dom-sep";
+        append(ds, (const uint8_t*)label, N - 1);
     }
-    void append(const char* label, const uint8_t* msg, size_t n) {
+    template <size_t N> CPG_HD void append(const char (&label)[N], const uint8_t* msg, size_t n) {
         uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
-        s.meta_ad((const uint8_t*)label, strlen(label), false);
+        s.meta_ad((const uint8_t*)label, N - 1, false);
         s.meta_ad(len, 4, true);
         s.ad(msg, n, false);
     }
-    void append_point(const char* label, const uint8_t* p48) { append(label, p48, 48); }
-    void append_fr(const char* label, const HFr& v) { uint8_t b[32]; fr_to_bytes(b, v); append(label, b, 32); }
-    void challenge_bytes(const char* label, uint8_t* out, size_t n) {
+    template <size_t N> CPG_HD void append_point(const char (&label)[N], const uint8_t* p48) { append(label, p48, 48); }
+    template <size_t N> CPG_HD void append_fr(const char (&label)[N], const HFr& v) { uint8_t b[32]; fr_to_bytes(b, v); append(label, b, 32); }
+    template <size_t N> CPG_HD void challenge_bytes(const char (&label)[N], uint8_t* out, size_t n) {
         uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
-        s.meta_ad((const uint8_t*)label, strlen(label), false);
+        s.meta_ad((const uint8_t*)label, N - 1, false);
         s.meta_ad(len, 4, true);
         s.prf(out, n, false);
     }
     // rejection-sample a non-zero scalar < r, then bind it back (curdleproofs_transcript.py:15-25)
-    HFr challenge(const char* label) {
+    template <size_t N> CPG_HD HFr challenge(const char (&label)[N]) {
         for (;;) {
             uint8_t raw[32];
             challenge_bytes(label, raw, 32);

@@ -10,6 +10,7 @@
 //
 // Batched Pippenger over B independent MSMs of n terms:
 //   window width c, W = ceil(256/c) windows, NB = 2^(c-1) buckets per window (signed digits).
+//   0 RecodeDigits      thread = (msm, term): the W signed digits of one scalar
 //   1 SortDigits        thread = (msm, window): counting sort of the n signed digits
 //   2 BucketAccumulate  thread = (msm, window, bucket): XYZZ mixed adds, registers only
 //   3 WindowReduce      thread = (msm, window): running-sum  sum_b (b+1) * S_b
@@ -48,63 +49,116 @@ struct MsmShape {
     uint64_t base_stride;         // bases of msm m start at m*base_stride (0 = shared by all)
 };
 
+// 0 --- signed digits of one scalar, all windows ---------------------------------------------
+// dig[msm][term][w]: the W digits of a term are contiguous (one thread writes them in a row) and a
+// warp of SortDigits threads (consecutive windows of one MSM) reads consecutive int16s: coalesced both ways.
+struct RecodeDigits {
+    static constexpr const char* kName = "RecodeDigits";
+    MsmShape s; Recode rc;
+    const uint32_t* scalars;      // [B][n][8] canonical little-endian
+    int16_t* dig;                 // [B][n][W] (out)
+    CPG_HD void operator()(uint64_t t) const {      // t = msm*n + term
+        uint32_t kp[8];
+        recode_add(rc, scalars + 8 * t, kp);
+        int16_t* out = dig + t * (uint64_t)s.W;
+        for (uint32_t w = 0; w < s.W; w++) out[w] = (int16_t)recode_digit(rc, kp, w);
+    }
+};
+
 // 1 --- counting sort of the digits of one (msm, window) ----------------------------------
 struct SortDigits {
     static constexpr const char* kName = "SortDigits";
-    MsmShape s; Recode rc;
-    const uint32_t* scalars;      // [B][n][8] canonical little-endian
+    MsmShape s;
+    const int16_t* dig;           // [B][n][W] from RecodeDigits
     uint32_t* boff;               // [B*W][NB+1] bucket start offsets (out)
     uint32_t* sorted;             // [B*W][n] term index | sign<<31, grouped by bucket (out)
+    uint16_t* rank;               // [B*W][NB] buckets of this window ordered by list length, longest first (out; may be null)
     CPG_HD void operator()(uint64_t t) const {
         uint32_t m = (uint32_t)(t / s.W), w = (uint32_t)(t % s.W);
         uint32_t* off = boff + t * (uint64_t)(s.NB + 1);
         uint32_t* out = sorted + t * (uint64_t)s.n;
-        const uint32_t* ks = scalars + (uint64_t)m * s.n * 8;
+        const int16_t* dg = dig + (uint64_t)m * s.n * s.W + w;
         for (uint32_t b = 0; b <= s.NB; b++) off[b] = 0;
-        uint32_t kp[8];
         for (uint32_t i = 0; i < s.n; i++) {       // off[a] = number of terms with |digit| = a
-            recode_add(rc, ks + 8 * (uint64_t)i, kp);
-            int d = recode_digit(rc, kp, w);
+            int d = dg[(uint64_t)i * s.W];
             if (d) off[(d < 0 ? -d : d)]++;
         }
         uint32_t run = 0;                           // off[a] = END of bucket a-1
         for (uint32_t b = 1; b <= s.NB; b++) { run += off[b]; off[b] = run; }
         const uint32_t total = run;
         for (uint32_t i = s.n; i-- > 0;) {          // fill each bucket from its end (stable)
-            recode_add(rc, ks + 8 * (uint64_t)i, kp);
-            int d = recode_digit(rc, kp, w);
+            int d = dg[(uint64_t)i * s.W];
             if (d) { uint32_t a = (uint32_t)(d < 0 ? -d : d); out[--off[a]] = i | (d < 0 ? 0x80000000u : 0u); }
         }
         // off[a] is now the START of bucket a-1: shift down to off[b] = start of bucket b
         for (uint32_t b = 0; b < s.NB; b++) off[b] = off[b + 1];
         off[s.NB] = total;
+        // Rank the buckets by length (insertion sort, NB <= 256).  BucketAccumulate gives one warp the
+        // same window and the same rank of 32 different MSMs, whose lengths are tightly concentrated,
+        // so its lanes run near-equal trip counts: no global sort, no atomics.
+        if (rank) {
+            uint16_t* rk = rank + t * (uint64_t)s.NB;
+            for (uint32_t b = 0; b < s.NB; b++) {
+                uint32_t len = off[b + 1] - off[b];
+                uint32_t j = b;
+                while (j > 0) {
+                    uint32_t pb = rk[j - 1];
+                    if (off[pb + 1] - off[pb] >= len) break;
+                    rk[j] = (uint16_t)pb;
+                    j--;
+                }
+                rk[j] = (uint16_t)b;
+            }
+        }
     }
 };
 
 // 2 --- one bucket: sum of its (signed) bases, mixed XYZZ adds ------------------------------
+// Thread -> bucket mapping.  Without `rank`: t = (msm*W + w)*NB + b.  With `rank` (balanced): a warp
+// takes ONE window w and ONE rank r of 32 consecutive MSMs (lane = msm): the rank-r buckets of the same
+// window of different MSMs have nearly the same length, so the lanes run equal trip counts.  (Mixing
+// windows inside a warp is what must be avoided: the top window holds only 255 - c(W-1) bits, i.e. a
+// few very long buckets, and one such lane would stall its 31 neighbours.)
 struct BucketAccumulate {
     static constexpr const char* kName = "BucketAccumulate";
     MsmShape s;
     const Aff* bases;
     const uint32_t* boff;
     const uint32_t* sorted;
-    const uint32_t* order;        // optional permutation of bucket ids (length-balanced warps), or null
+    const uint16_t* rank;         // from SortDigits, or null
+    uint64_t BW;                  // B*W
     Xyzz* buckets;                // [B*W][NB] (out)
     CPG_HD void operator()(uint64_t t) const {
-        uint64_t g = order ? order[t] : t;
-        uint64_t mw = g / s.NB; uint32_t b = (uint32_t)(g % s.NB);
+        uint64_t mw; uint32_t b;
+        if (rank) {
+            uint32_t lane = (uint32_t)(t % 32), r = (uint32_t)((t / 32) % s.NB);
+            uint64_t q = t / (32ull * s.NB);
+            uint32_t w = (uint32_t)(q % s.W);
+            uint64_t msm = (q / s.W) * 32 + lane;
+            if (msm >= s.B) return;
+            mw = msm * s.W + w;
+            b = rank[mw * s.NB + r];
+        } else {
+            mw = t / s.NB; b = (uint32_t)(t % s.NB);
+        }
         uint32_t m = (uint32_t)(mw / s.W);
         const uint32_t* off = boff + mw * (uint64_t)(s.NB + 1);
         const uint32_t* lst = sorted + mw * (uint64_t)s.n;
         const Aff* P = bases + (uint64_t)m * s.base_stride;
         Xyzz acc = xyzz_inf();
         uint32_t lo = off[b], hi = off[b + 1];
-        for (uint32_t j = lo; j < hi; j++) {
-            uint32_t e = lst[j];
+        if (lo < hi) {
+            uint32_t e = lst[lo];
             Aff q = P[e & 0x7fffffffu];
-            acc = xyzz_add_mixed(acc, cneg(q, (e >> 31) != 0));
+            for (uint32_t j = lo; j < hi; j++) {
+                // fetch the next base before the ~10 Fq products of this add (hides the gather latency)
+                uint32_t e2 = (j + 1 < hi) ? lst[j + 1] : e;
+                Aff q2 = P[e2 & 0x7fffffffu];
+                acc = xyzz_add_mixed(acc, cneg(q, (e >> 31) != 0));
+                e = e2; q = q2;
+            }
         }
-        buckets[g] = acc;
+        buckets[mw * s.NB + b] = acc;
     }
 };
 

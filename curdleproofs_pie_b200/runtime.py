@@ -71,6 +71,8 @@ _SIGS = {
     "cpg_verifier_proof_bytes": (_c.c_size_t, [_c.c_void_p]),
     "cpg_verifier_input_bytes": (_c.c_size_t, [_c.c_void_p]),
     "cpg_verifier_set_window": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "cpg_verifier_set_transcript": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "cpg_verifier_set_streams": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "cpg_verify_batch": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_char_p, _c.c_size_t, _c.c_char_p]),
     "cpg_verify_replay_device": (_c.c_int, [_c.c_void_p, _c.c_char_p]),
     "cpg_bench_int_pipe": (_c.c_int, [_c.c_int, _c.c_uint64, _c.POINTER(_c.c_double), _c.POINTER(_c.c_float)]),

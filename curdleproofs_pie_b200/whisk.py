@@ -15,7 +15,7 @@ from . import runtime as _rt
 class BatchVerifier:
     """Holds the device-resident CRS (fixed-base tables) for one (ell, n_blinders)."""
 
-    def __init__(self, crs_bytes, ell, n_blinders=4, fixed_window=8, host_threads=0, lib=None):
+    def __init__(self, crs_bytes, ell, n_blinders=4, fixed_window=0, host_threads=0, lib=None):
         self.lib = lib or _rt.get_lib()
         self.ell = int(ell)
         self.n_blinders = int(n_blinders)
@@ -30,6 +30,13 @@ class BatchVerifier:
 
     def set_window(self, c):
         self.lib.check(self.lib.c.cpg_verifier_set_window(self.handle, int(c)), "cpg_verifier_set_window")
+
+    def set_transcript(self, on_device):
+        """True: transcript + coefficients per proof on the GPU (default); False: on host threads."""
+        self.lib.check(self.lib.c.cpg_verifier_set_transcript(self.handle, 1 if on_device else 0), "cpg_verifier_set_transcript")
+
+    def set_streams(self, n):
+        self.lib.check(self.lib.c.cpg_verifier_set_streams(self.handle, int(n)), "cpg_verifier_set_streams")
 
     def verify_raw(self, inputs, proofs, B):
         """inputs: B*input_len bytes, proofs: B*proof_len bytes -> bytes of B verdicts."""

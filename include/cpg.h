@@ -112,9 +112,10 @@ int cpg_fr_inverse(const uint8_t* d_a, size_t k, uint8_t* d_out);   /* inverse(0
 
 /* ---- batched shuffle-proof verification -------------------------------------------------------
  * Replaces, for B proofs at once, IsValidWhiskShuffleProof (cp/whisk_interface.py:74-108) ->
- * CurdleProofsProof.verify (cp/curdleproofs.py:162-248) and everything below it.  The transcript
- * and the Fr coefficient algebra run on `host_threads` host threads (0 = all cores); every group
- * operation runs on the GPU (decompress, D / A', one MSM per proof).
+ * CurdleProofsProof.verify (cp/curdleproofs.py:162-248) and everything below it.  Every group
+ * operation runs on the GPU (decompress, D / A', one MSM per proof); the transcript and the Fr
+ * coefficient algebra run per proof either on the GPU or on `host_threads` host threads
+ * (cpg_verifier_set_transcript; 0 threads = all cores).
  *   crs_bytes : (ell + n_blinders + 5) * 48 B = CurdleproofsCrs.to_bytes (cp/crs.py:93-102)
  *   inputs    : [B][4*ell*48]  vec_R | vec_S | vec_T | vec_U  (tracker halves, whisk_interface.py:96-100)
  *   proofs    : [B][cpg_verifier_proof_bytes]  M | proof      (WhiskShuffleProof.to_bytes, :57-61)
@@ -124,6 +125,11 @@ int cpg_verifier_free(void* verifier);
 size_t cpg_verifier_proof_bytes(const void* verifier);
 size_t cpg_verifier_input_bytes(const void* verifier);
 int cpg_verifier_set_window(void* verifier, int var_window);
+/* where the Fiat-Shamir transcript + coefficient algebra run: 1 = one proof per GPU thread (default;
+ * only wire bytes cross PCIe), 0 = on `host_threads` host threads (the reference's placement) */
+int cpg_verifier_set_transcript(void* verifier, int on_device);
+/* sub-batches in flight on separate CUDA streams (1..8, default 1; device transcript only) */
+int cpg_verifier_set_streams(void* verifier, int nstreams);
 int cpg_verify_batch(void* verifier, const uint8_t* inputs, const uint8_t* proofs, size_t B, uint8_t* verdicts);
 /* re-run the device side (decompress, D/A', MSM, test) of the last batch on its resident inputs */
 int cpg_verify_replay_device(void* verifier, uint8_t* verdicts_or_null);

@@ -1,0 +1,65 @@
+"""The N>1 path on CPU: world_size-2 gloo processes exercise the per-proof sharding, the
+max-over-ranks timing reduction and the verdict gather that bench.py / a multi-GPU caller use."""
+import os
+import socket
+import sys
+
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, total, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from curdleproofs_pie_b200 import sharding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = sharding.shard_range(total, rank, world)
+    local = bytes((i * 7 + 3) % 2 for i in range(lo, hi))           # this rank's "verdicts"
+    full = sharding.gather_verdicts(local, total, dist)
+    slowest = sharding.max_over_ranks(10.0 + rank, dist)
+    dist.barrier()
+    q.put((rank, lo, hi, full, slowest))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [10, 7, 1])
+def test_two_rank_sharding_and_gather(total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = bytes((i * 7 + 3) % 2 for i in range(total))
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == total        # contiguous cover
+    for rank, lo, hi, full, slowest in res:
+        assert full == want
+        assert slowest == 11.0
+
+
+def test_shard_range_properties():
+    from curdleproofs_pie_b200.sharding import shard_range
+
+    for total in (0, 1, 5, 64, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(total, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == total
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1

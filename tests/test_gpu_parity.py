@@ -117,7 +117,8 @@ import verify_cases as vc  # noqa: E402
 @pytest.mark.parametrize("name,copies,window", [("shuffle_N8_seed1234.json", 1, 0), ("shuffle_N64_seed2024.json", 3, 0),
                                                  ("shuffle_N128_seed4096.json", 40, 0), ("shuffle_N128_seed4096.json", 2, 5)])
 def test_verify_batch(gpu_lib, name, copies, window):
-    vc.check_batch(gpu_lib, name, copies=copies, window=window)
+    vc.check_batch(gpu_lib, name, copies=copies, window=window, transcript_on_device=True)
+    vc.check_batch(gpu_lib, name, copies=min(copies, 2), window=window, transcript_on_device=False)
 
 
 def test_verify_replay_matches(gpu_lib):

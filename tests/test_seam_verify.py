@@ -5,9 +5,14 @@ import ctypes
 import verify_cases as vc
 
 
-def test_verify_batch_N8(seam_lib):
-    vc.check_batch(seam_lib, "shuffle_N8_seed1234.json")
+import pytest
 
 
-def test_verify_batch_N16_two_copies(seam_lib):
-    vc.check_batch(seam_lib, "shuffle_N16_seed77.json", copies=2, window=4)
+@pytest.mark.parametrize("on_device", [True, False])
+def test_verify_batch_N8(seam_lib, on_device):
+    vc.check_batch(seam_lib, "shuffle_N8_seed1234.json", transcript_on_device=on_device, fixed_window=4)
+
+
+@pytest.mark.parametrize("on_device", [True, False])
+def test_verify_batch_N16_two_copies(seam_lib, on_device):
+    vc.check_batch(seam_lib, "shuffle_N16_seed77.json", copies=2, window=4, transcript_on_device=on_device, fixed_window=5)

@@ -38,10 +38,11 @@ def variants(case):
     return out
 
 
-def check_batch(lib, name, copies=1, window=0):
+def check_batch(lib, name, copies=1, window=0, transcript_on_device=True, fixed_window=0):
     case = sc.load_case(name)
     ell = case["N"] - 4
-    ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), ell, lib=lib)
+    ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), ell, fixed_window=fixed_window, lib=lib)
+    ver.set_transcript(transcript_on_device)
     if window:
         ver.set_window(window)
     vs = variants(case) * copies
