@@ -130,6 +130,119 @@ CPG_HD void mont_mul_n(uint32_t* r, const uint32_t* a, const uint32_t* b, const 
     for (int j = 0; j < N; j++) r[j] = borrow ? t[j] : s[j];
 }
 
+// ---- dedicated squaring ------------------------------------------------------------------------
+// a^2 = sum_i a_i * f^(i) * 2^(32 i)  with the row vector  f^(i) = [0,...,0, a_i, 2a_{i+1}, 2a_{i+2}, ...]
+// (i leading zeros): the 66 off-diagonal products are taken once and doubled through the operand
+// d = 2a, the 12 diagonal ones once - 78 instead of 144 product MACs; the 144 reduction MACs stay.
+// Needs p < 2^(32N-3): d = 2a is then exact in N limbs and the look-ahead partial sums
+// (row i already holds 2 a_i a_j for all j > i) stay below 2^(32N).  True for Fq (381 bits in 384), not for Fr.  Row i of the interleaved (CIOS, even/odd) scheme of
+// mont_mul_n then uses f^(i) as its multiplicand vector and a_i as its multiplier; entries below i are
+// compile-time zeros whose MACs degenerate to the carry/shift adds.
+template <int N, int I>
+CPG_HD void sqr_row_vec(uint32_t* f, const uint32_t* a, const uint32_t* d) {
+#pragma unroll
+    for (int j = 0; j < N; j++) f[j] = j < I ? 0u : (j == I ? a[j] : (j == I + 1 ? (d[j] & 0xfffffffeu) : d[j]));
+}
+// x += (f[R] + f[R+2] 2^64 + ...) * b over even entries R >= I only; carry out left in CF.
+// Returns false (and leaves CF untouched) when the row has no even entry >= I.
+template <int N, int I>
+CPG_HD bool cmad_even_from(uint32_t* acc, const uint32_t* f, uint32_t b) {
+    constexpr int R0 = (I + 1) & ~1;      // first even index >= I
+    if (R0 >= N) return false;
+    acc[R0] = mad_lo_cc(f[R0], b, acc[R0]);
+    acc[R0 + 1] = madc_hi_cc(f[R0], b, acc[R0 + 1]);
+#pragma unroll
+    for (int j = R0 + 2; j < N; j += 2) {
+        acc[j] = madc_lo_cc(f[j], b, acc[j]);
+        acc[j + 1] = madc_hi_cc(f[j], b, acc[j + 1]);
+    }
+    return true;
+}
+// y[j] = y[j+2] + (odd entries f[j+1], j+1 >= I) * b, carry-in from CF, in place (cf. madc_shift2)
+template <int N, int I>
+CPG_HD void madc_shift2_from(uint32_t* y, const uint32_t* f, uint32_t b) {
+#pragma unroll
+    for (int j = 0; j < N - 2; j += 2) {
+        if (j + 1 >= I) {
+            y[j] = madc_lo_cc(f[j + 1], b, y[j + 2]);
+            y[j + 1] = madc_hi_cc(f[j + 1], b, y[j + 3]);
+        } else {
+            y[j] = addc_cc(y[j + 2], 0);
+            y[j + 1] = addc_cc(y[j + 3], 0);
+        }
+    }
+    if (N - 1 >= I) {
+        y[N - 2] = madc_lo_cc(f[N - 1], b, 0);
+        y[N - 1] = madc_hi(f[N - 1], b, 0);
+    } else {
+        y[N - 2] = addc(0, 0);
+        y[N - 1] = 0;
+    }
+}
+template <int N, int I>
+CPG_HD void mont_sqr_step(uint32_t* x, uint32_t* y, const uint32_t* a, const uint32_t* d, const uint32_t* p, uint32_t inv) {
+    uint32_t f[N];
+    sqr_row_vec<N, I>(f, a, d);
+    const uint32_t bi = a[I];
+    x[0] = add_cc(x[0], y[1]);
+    madc_shift2_from<N, I>(y, f, bi);
+    if (cmad_even_from<N, I>(x, f, bi)) y[N - 1] = addc(y[N - 1], 0);
+    uint32_t m = mul_lo(x[0], inv);
+    cmad_even<N>(x, p, m);
+    y[N - 1] = addc(y[N - 1], 0);
+    cmad_even<N>(y, p + 1, m);
+}
+template <int N, int I>
+struct SqrSteps {
+    static CPG_HD void run(uint32_t* e, uint32_t* o, const uint32_t* a, const uint32_t* d, const uint32_t* p, uint32_t inv) {
+        // odd I: the accumulator aligned at 1 is `o` (see mont_mul_n), even I: `e`
+        if (I & 1) mont_sqr_step<N, I>(o, e, a, d, p, inv);
+        else mont_sqr_step<N, I>(e, o, a, d, p, inv);
+        SqrSteps<N, I + 1>::run(e, o, a, d, p, inv);
+    }
+};
+template <int N>
+struct SqrSteps<N, N> {
+    static CPG_HD void run(uint32_t*, uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t) {}
+};
+// r = a * a / 2^(32N) mod p, a < p < 2^(32N-3), result < p.  r may alias a.
+template <int N>
+CPG_HD void mont_sqr_n(uint32_t* r, const uint32_t* a, const uint32_t* p, uint32_t inv) {
+    uint32_t d[N];
+    d[0] = a[0] << 1;
+#pragma unroll
+    for (int j = 1; j < N; j++) d[j] = (a[j] << 1) | (a[j - 1] >> 31);
+    uint32_t e[N], o[N];
+    {   // row 0: vector [a_0, 2a_1 (bit 0 clear), d_2, ...] times a_0
+        uint32_t f[N];
+        sqr_row_vec<N, 0>(f, a, d);
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+            e[j] = mul_lo(f[j], a[0]);
+            e[j + 1] = mul_hi(f[j], a[0]);
+            o[j] = mul_lo(f[j + 1], a[0]);
+            o[j + 1] = mul_hi(f[j + 1], a[0]);
+        }
+        uint32_t m = mul_lo(e[0], inv);
+        cmad_even<N>(e, p, m);
+        o[N - 1] = addc(o[N - 1], 0);
+        cmad_even<N>(o, p + 1, m);
+    }
+    SqrSteps<N, 1>::run(e, o, a, d, p, inv);
+    uint32_t t[N];
+    t[0] = add_cc(o[1], e[0]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) t[j] = addc_cc(o[j + 1], e[j]);
+    t[N - 1] = addc(e[N - 1], 0);
+    uint32_t s[N];
+    s[0] = sub_cc(t[0], p[0]);
+#pragma unroll
+    for (int j = 1; j < N; j++) s[j] = subc_cc(t[j], p[j]);
+    uint32_t borrow = subc(0, 0);
+#pragma unroll
+    for (int j = 0; j < N; j++) r[j] = borrow ? t[j] : s[j];
+}
+
 // r = a + b mod p
 template <int N>
 CPG_HD void mod_add_n(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p) {

@@ -51,6 +51,28 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_each(const F f, uint64_t n) {
     uint64_t t = blockIdx.x * (uint64_t)BLOCK + threadIdx.x;
     if (t < n) f(t);
 }
+// SortDigits with its per-thread histogram (NB+1 words) and rank (NB halfwords) arrays in shared
+// memory: element k of thread t sits at [k*BLOCK + t], so a thread always stays in its own bank.
+constexpr int SORT_BLOCK = 128;
+__global__ void __launch_bounds__(SORT_BLOCK) k_sort_digits_smem(SortDigits f, uint64_t n_threads) {
+    extern __shared__ uint32_t sort_smem[];
+    const MsmShape& s = f.s;
+    uint32_t* off_base = sort_smem + threadIdx.x;
+    uint16_t* rk_base = (uint16_t*)(sort_smem + (size_t)(s.NB + 1) * SORT_BLOCK) + threadIdx.x;
+    uint64_t t = blockIdx.x * (uint64_t)SORT_BLOCK + threadIdx.x;
+    if (t >= n_threads) return;
+    uint32_t m = (uint32_t)(t / s.W), w = (uint32_t)(t % s.W);
+    StridedView<uint32_t> off{off_base, SORT_BLOCK};
+    StridedView<uint16_t> rk{rk_base, SORT_BLOCK};
+    sort_digits_body(s, f.dig + (uint64_t)m * s.n * s.W + w, f.sorted + t * (uint64_t)s.n, off, rk, f.rank != nullptr);
+    uint32_t* goff = f.boff + t * (uint64_t)(s.NB + 1);
+    for (uint32_t b = 0; b <= s.NB; b++) goff[b] = off[b];
+    if (f.rank) {
+        uint16_t* grk = f.rank + t * (uint64_t)s.NB;
+        for (uint32_t b = 0; b < s.NB; b++) grk[b] = rk[b];
+    }
+}
+
 // ---- optional per-kernel timing (cpg_profile_*): one CUDA event pair per launch on the launching
 // stream, resolved lazily.  Off by default; bench.py turns it on to time the dominant kernel live.
 struct ProfRec { const char* name; cudaEvent_t a, b; uint64_t threads; };
@@ -77,6 +99,24 @@ int launch(const F& f, uint64_t n) {
     g_launches++;
     return ck(cudaGetLastError(), "kernel launch");
 }
+int launch_sort_digits(const SortDigits& f, uint64_t n) {
+    const MsmShape& s = f.s;
+    size_t smem = (size_t)(s.NB + 1) * SORT_BLOCK * 4 + (size_t)s.NB * SORT_BLOCK * 2;
+    if (smem > 200 * 1024) return launch(f, n);                 // very wide windows: per-thread global arrays
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        if (int rc = ck(cudaFuncSetAttribute(k_sort_digits_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute")) return rc;
+        configured = smem;
+    }
+    if (!n) return 0;
+    uint64_t grid = (n + SORT_BLOCK - 1) / SORT_BLOCK;
+    ProfRec rec{SortDigits::kName, nullptr, nullptr, n};
+    if (g_prof_on) { cudaEventCreate(&rec.a); cudaEventCreate(&rec.b); cudaEventRecord(rec.a, cur()); }
+    k_sort_digits_smem<<<(unsigned)grid, SORT_BLOCK, smem, cur()>>>(f, n);
+    if (g_prof_on) { cudaEventRecord(rec.b, cur()); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back(rec); }
+    g_launches++;
+    return ck(cudaGetLastError(), "kernel launch");
+}
 void* scratch_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocAsync(&p, bytes ? bytes : 1, cur()) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -92,6 +132,7 @@ int launch(const F& f, uint64_t n) {
     for (int64_t t = 0; t < (int64_t)n; t++) f((uint64_t)t);
     return 0;
 }
+int launch_sort_digits(const SortDigits& f, uint64_t n) { return launch(f, n); }
 void* scratch_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void scratch_free(void* p) { free(p); }
 #endif
@@ -470,7 +511,7 @@ int cpg_g1_msm_batched(const void* d_bases, size_t base_stride, const uint8_t* d
         int16_t* dig = sc.get<int16_t>((uint64_t)nb * n * s.W);
         if (!dig) return fail("cpg_g1_msm_batched: scratch allocation failed");
         if (int r = launch(RecodeDigits{s, rc, ks, dig}, (uint64_t)nb * n)) return r;
-        if (int r = launch(SortDigits{s, dig, boff, sorted, rank}, BW)) return r;
+        if (int r = launch_sort_digits(SortDigits{s, dig, boff, sorted, rank}, BW)) return r;
         uint64_t nthreads = balanced ? (((uint64_t)nb + 31) / 32) * 32 * s.W * s.NB : BW * s.NB;
         if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, rank, BW, buckets}, nthreads)) return r;
         if (int r = launch(WindowReduce{s, buckets, wsum}, BW)) return r;

@@ -47,6 +47,7 @@ static __device__ __constant__ uint32_t D_FR_R2[8] = CPG_FR_R2_INIT;
 struct FqCfg {
     static constexpr int N = 12;
     static constexpr uint32_t INV = 0xfffcfffdu;  // -p^-1 mod 2^32
+    static constexpr bool FAST_SQR = true;        // p < 2^381: three spare bits, mont_sqr_n's partial sums fit
     static CPG_HD const uint32_t* p() { return CPG_SEL(FQ_P); }
     static CPG_HD const uint32_t* one() { return CPG_SEL(FQ_R); }
     static CPG_HD const uint32_t* r2() { return CPG_SEL(FQ_R2); }
@@ -54,6 +55,7 @@ struct FqCfg {
 struct FrCfg {
     static constexpr int N = 8;
     static constexpr uint32_t INV = 0xffffffffu;  // -r^-1 mod 2^32
+    static constexpr bool FAST_SQR = false;       // r > 2^254: the doubled operand overflows mont_sqr_n's window
     static CPG_HD const uint32_t* p() { return CPG_SEL(FR_P); }
     static CPG_HD const uint32_t* one() { return CPG_SEL(FR_R); }
     static CPG_HD const uint32_t* r2() { return CPG_SEL(FR_R2); }
@@ -82,7 +84,12 @@ struct Fp {
 };
 
 template <class C> CPG_HD Fp<C> mul(const Fp<C>& a, const Fp<C>& b) { Fp<C> r; mont_mul_n<C::N>(r.l, a.l, b.l, C::p(), C::INV); return r; }
-template <class C> CPG_HD Fp<C> sqr(const Fp<C>& a) { Fp<C> r; mont_mul_n<C::N>(r.l, a.l, a.l, C::p(), C::INV); return r; }
+template <class C> CPG_HD Fp<C> sqr(const Fp<C>& a) {
+    Fp<C> r;
+    if (C::FAST_SQR) mont_sqr_n<C::N>(r.l, a.l, C::p(), C::INV);
+    else mont_mul_n<C::N>(r.l, a.l, a.l, C::p(), C::INV);
+    return r;
+}
 template <class C> CPG_HD Fp<C> add(const Fp<C>& a, const Fp<C>& b) { Fp<C> r; mod_add_n<C::N>(r.l, a.l, b.l, C::p()); return r; }
 template <class C> CPG_HD Fp<C> sub(const Fp<C>& a, const Fp<C>& b) { Fp<C> r; mod_sub_n<C::N>(r.l, a.l, b.l, C::p()); return r; }
 template <class C> CPG_HD Fp<C> dbl(const Fp<C>& a) { return add(a, a); }

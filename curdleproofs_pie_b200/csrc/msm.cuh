@@ -66,6 +66,47 @@ struct RecodeDigits {
 };
 
 // 1 --- counting sort of the digits of one (msm, window) ----------------------------------
+// The per-thread histogram / rank arrays are reached through small views so the same body runs on
+// thread-private global arrays (generic launcher, host test seam) or on bank-conflict-free strided
+// slices of shared memory (k_sort_digits_smem in cpg_api.cu: element k of thread t at [k*BLOCK + t]).
+template <class T> struct LinView { T* p; CPG_HD T& operator[](uint32_t i) const { return p[i]; } };
+template <class T> struct StridedView { T* p; uint32_t stride; CPG_HD T& operator[](uint32_t i) const { return p[(size_t)i * stride]; } };
+
+template <class Off, class Rank>
+CPG_HD void sort_digits_body(const MsmShape& s, const int16_t* dg, uint32_t* out, Off off, Rank rk, bool want_rank) {
+    for (uint32_t b = 0; b <= s.NB; b++) off[b] = 0;
+    for (uint32_t i = 0; i < s.n; i++) {           // off[a] = number of terms with |digit| = a
+        int d = dg[(uint64_t)i * s.W];
+        if (d) off[(uint32_t)(d < 0 ? -d : d)]++;
+    }
+    uint32_t run = 0;                               // off[a] = END of bucket a-1
+    for (uint32_t b = 1; b <= s.NB; b++) { run += off[b]; off[b] = run; }
+    const uint32_t total = run;
+    for (uint32_t i = s.n; i-- > 0;) {              // fill each bucket from its end (stable)
+        int d = dg[(uint64_t)i * s.W];
+        if (d) { uint32_t a = (uint32_t)(d < 0 ? -d : d); uint32_t pos = off[a] - 1; off[a] = pos; out[pos] = i | (d < 0 ? 0x80000000u : 0u); }
+    }
+    // off[a] is now the START of bucket a-1: shift down to off[b] = start of bucket b
+    for (uint32_t b = 0; b < s.NB; b++) off[b] = off[b + 1];
+    off[s.NB] = total;
+    // Rank the buckets by length (insertion sort, NB <= 256).  BucketAccumulate gives one warp the
+    // same window and the same rank of 32 different MSMs, whose lengths are tightly concentrated,
+    // so its lanes run near-equal trip counts: no global sort, no atomics.
+    if (want_rank) {
+        for (uint32_t b = 0; b < s.NB; b++) {
+            uint32_t len = off[b + 1] - off[b];
+            uint32_t j = b;
+            while (j > 0) {
+                uint32_t pb = rk[j - 1];
+                if (off[pb + 1] - off[pb] >= len) break;
+                rk[j] = (uint16_t)pb;
+                j--;
+            }
+            rk[j] = (uint16_t)b;
+        }
+    }
+}
+
 struct SortDigits {
     static constexpr const char* kName = "SortDigits";
     MsmShape s;
@@ -75,41 +116,9 @@ struct SortDigits {
     uint16_t* rank;               // [B*W][NB] buckets of this window ordered by list length, longest first (out; may be null)
     CPG_HD void operator()(uint64_t t) const {
         uint32_t m = (uint32_t)(t / s.W), w = (uint32_t)(t % s.W);
-        uint32_t* off = boff + t * (uint64_t)(s.NB + 1);
-        uint32_t* out = sorted + t * (uint64_t)s.n;
-        const int16_t* dg = dig + (uint64_t)m * s.n * s.W + w;
-        for (uint32_t b = 0; b <= s.NB; b++) off[b] = 0;
-        for (uint32_t i = 0; i < s.n; i++) {       // off[a] = number of terms with |digit| = a
-            int d = dg[(uint64_t)i * s.W];
-            if (d) off[(d < 0 ? -d : d)]++;
-        }
-        uint32_t run = 0;                           // off[a] = END of bucket a-1
-        for (uint32_t b = 1; b <= s.NB; b++) { run += off[b]; off[b] = run; }
-        const uint32_t total = run;
-        for (uint32_t i = s.n; i-- > 0;) {          // fill each bucket from its end (stable)
-            int d = dg[(uint64_t)i * s.W];
-            if (d) { uint32_t a = (uint32_t)(d < 0 ? -d : d); out[--off[a]] = i | (d < 0 ? 0x80000000u : 0u); }
-        }
-        // off[a] is now the START of bucket a-1: shift down to off[b] = start of bucket b
-        for (uint32_t b = 0; b < s.NB; b++) off[b] = off[b + 1];
-        off[s.NB] = total;
-        // Rank the buckets by length (insertion sort, NB <= 256).  BucketAccumulate gives one warp the
-        // same window and the same rank of 32 different MSMs, whose lengths are tightly concentrated,
-        // so its lanes run near-equal trip counts: no global sort, no atomics.
-        if (rank) {
-            uint16_t* rk = rank + t * (uint64_t)s.NB;
-            for (uint32_t b = 0; b < s.NB; b++) {
-                uint32_t len = off[b + 1] - off[b];
-                uint32_t j = b;
-                while (j > 0) {
-                    uint32_t pb = rk[j - 1];
-                    if (off[pb + 1] - off[pb] >= len) break;
-                    rk[j] = (uint16_t)pb;
-                    j--;
-                }
-                rk[j] = (uint16_t)b;
-            }
-        }
+        LinView<uint32_t> off{boff + t * (uint64_t)(s.NB + 1)};
+        LinView<uint16_t> rk{rank ? rank + t * (uint64_t)s.NB : nullptr};
+        sort_digits_body(s, dig + (uint64_t)m * s.n * s.W + w, sorted + t * (uint64_t)s.n, off, rk, rank != nullptr);
     }
 };
 

@@ -8,6 +8,8 @@ using namespace cpg;
 
 extern "C" {
 void hs_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fq x, y; memcpy(x.l, a, 48); memcpy(y.l, b, 48); Fq z = mul(x, y); memcpy(r, z.l, 48); }
+void hs_fq_sqr(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.l, a, 48); Fq z = sqr(x); memcpy(r, z.l, 48); }
+void hs_fr_sqr(const uint32_t* a, uint32_t* r) { Fr x; memcpy(x.l, a, 32); Fr z = sqr(x); memcpy(r, z.l, 32); }
 void hs_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fq x, y; memcpy(x.l, a, 48); memcpy(y.l, b, 48); Fq z = add(x, y); memcpy(r, z.l, 48); }
 void hs_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fq x, y; memcpy(x.l, a, 48); memcpy(y.l, b, 48); Fq z = sub(x, y); memcpy(r, z.l, 48); }
 void hs_fq_inv(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.l, a, 48); Fq z = fq_inv(x); memcpy(r, z.l, 48); }
