@@ -246,8 +246,16 @@ def run_ours_verify(args, rank, world, dist):
         "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
     }
     cpu = cpu_verify_rate(case, sample=args.cpu_sample_verify, procs=1)
+    prove_side = None
+    if args.prove_batch and world == 1:
+        ver.close()
+        pr = measure_prove(args, lib, case, args.prove_batch, 2)
+        prove_side = {"metric": "curdleproofs_prove_per_s_n128_batched", "value": pr["B"] * pr["steps"] / (pr["ms"] * 1e-3),
+                      "e2e": pr["B"] * pr["steps"] / (pr["ms_e2e"] * 1e-3), "unit": "proofs/s", "B": pr["B"], "ms_per_step": pr["ms"] / pr["steps"],
+                      "note": "side measurement on this GPU (python bench.py --workload prove gives the full line)"}
     total = B * world
     return {
+        "prove": prove_side,
         "metric": "curdleproofs_verify_per_s_n128_batched", "value": total * args.steps / (ms * 1e-3), "unit": "verifications/s",
         "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fq, 255-bit Fr)", "data": "synthetic",
@@ -330,6 +338,186 @@ def run_reference_verify(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "verifications/s", "cores": cores, "kind": "port", "sample": r["sample"]},
         "e2e": {"value": value, "unit": "verifications/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "py_arkworks_bls12381 (the reference's Rust arithmetic) is not installable offline; this arm times the oracle port of the reference verifier",
+    }
+
+
+
+# ------------------------------------------------------------------------------------------------
+def prove_model(n, ell, lg, c_var, c_fix=12):
+    """Algorithmic Fq products of one proof on the linearised prover."""
+    nout, nf = 21 + 10 * lg, n + 3
+    wf = (256 + c_fix - 1) // c_fix
+    var = msm_model(ell, c_var)
+    nvar = 6 + 2 + 4 * lg
+    return {"fixed_msm": nout * nf * wf * 10, "var_msm": nvar * (var["bucket_accumulate"] + var["window_reduce"] + var["horner"]),
+            "shuffle": 2 * ell * 2900, "decompress": 2 * ell * 400, "compress": (nout + 2 * ell) * 470}
+
+
+def make_prove_batch(case, prover, B, seed):
+    import random as pyrandom
+
+    rng = pyrandom.Random(seed)
+    ell = case["N"] - 4
+    pre = b"".join(bytes.fromhex(h) for h in case["vec_R"] + case["vec_S"])
+    perms, ks, rands = [], bytearray(), bytearray()
+    for _ in range(B):
+        p = list(range(ell)); rng.shuffle(p)
+        perms.extend(p)
+        ks += (rng.getrandbits(248) + 1).to_bytes(32, "little")                 # < 2^249 < r, non-zero
+        rands += b"".join((rng.getrandbits(248) + 1).to_bytes(32, "little") for _ in range(prover.n_rand))
+    return pre * B, perms, bytes(ks), bytes(rands)
+
+
+def measure_prove(args, lib, case, B, steps, dist=None):
+    """Returns a dict with device (resident inputs, CUDA events) and e2e (host buffers, wall clock)
+    proofs/s for B proofs per step; the produced proofs are checked by the batched verifier."""
+    import array
+    import ctypes
+
+    from curdleproofs_pie_b200 import whisk
+
+    ell = case["N"] - 4
+    crs = bytes.fromhex(case["crs"])
+    prover = whisk.BatchProver(crs, ell)
+    c = args.prove_window or pick_window(ell)
+    prover.set_window(c)
+    inputs, perms, ks, rands = make_prove_batch(case, prover, B, 4242)
+    perm_arr = array.array("I", perms)
+    pbuf = (ctypes.c_uint32 * len(perm_arr)).from_buffer(perm_arr)
+    out_tu = ctypes.create_string_buffer(B * 2 * ell * 48)
+    out_pr = ctypes.create_string_buffer(B * prover.proof_len)
+    status = ctypes.create_string_buffer(B)
+
+    def step_e2e():
+        lib.check(lib.c.cpg_prove_batch(prover.handle, inputs, pbuf, ks, rands, B, out_tu, out_pr, status), "cpg_prove_batch")
+
+    def step_dev():
+        lib.check(lib.c.cpg_prove_replay_device(prover.handle), "cpg_prove_replay_device")
+
+    step_e2e()
+    assert not any(status.raw[:B])
+    # every produced proof must be accepted by the batched verifier
+    ver = whisk.BatchVerifier(crs, ell)
+    w = 2 * ell * 48
+    pre = inputs[:w]
+    tus, prs = out_tu.raw, out_pr.raw
+    nchk = min(B, 256)
+    verdicts = ver.verify([pre + tus[i * w:(i + 1) * w] for i in range(nchk)], [prs[i * prover.proof_len:(i + 1) * prover.proof_len] for i in range(nchk)])
+    assert all(verdicts), "a generated proof was rejected"
+    ver.close()
+    for _ in range(2):
+        step_dev()
+    lib.sync()
+    lib.profile(True)
+    launches0 = lib.launch_count()
+    lib.timer_start()
+    for _ in range(steps):
+        step_dev()
+    ms = lib.timer_stop()
+    launches = lib.launch_count() - launches0
+    prof = lib.profile_report()
+    lib.profile(False)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_e2e()
+    lib.sync()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    prover.close()
+    return {"B": B, "window": c, "ms": ms, "ms_e2e": ms_e2e, "steps": steps, "launches": launches, "prof": prof,
+            "h2d": B * (2 * ell * 48 + ell * 4 + 32 + prover.n_rand * 32), "d2h": B * (2 * ell * 48 + prover.proof_len + (21 + 70) * 48 + 2 * ell)}
+
+
+def _cpu_prove_worker(job):
+    case, count = job
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import random as pyrandom
+
+    from oracle import ark_surface, cref_binding, merlin_py
+    from oracle.shuffle_ref import ShuffleRef
+
+    ark_surface.set_backend("c")
+    merlin_py.use_native_keccak(cref_binding.load().keccak_f1600)
+    G1Point, Scalar = ark_surface.G1Point, ark_surface.Scalar
+    ctx = ShuffleRef(G1Point, Scalar, rng=pyrandom.Random(99))
+    ell = case["N"] - 4
+    crs = ctx.crs_from_bytes(bytes.fromhex(case["crs"]), ell)
+    dec = lambda lst: [G1Point.from_compressed_bytes_unchecked(bytes.fromhex(h)) for h in lst]  # noqa: E731
+    t0 = time.perf_counter()
+    for _ in range(count):
+        vec_R, vec_S = dec(case["vec_R"]), dec(case["vec_S"])             # the Whisk boundary decodes per call
+        perm = list(range(ell)); ctx.rng.shuffle(perm)
+        k = ctx.rand()
+        vec_T, vec_U, M, m_bl = ctx.shuffle_and_commit(crs, vec_R, vec_S, perm, k)
+        ctx.prove(crs, vec_R, vec_S, vec_T, vec_U, M, perm, k, m_bl)
+    return time.perf_counter() - t0
+
+
+def cpu_prove_rate(case, sample, procs):
+    from oracle import cref_binding
+
+    cref_binding.build()
+    per = max(1, sample // procs)
+    if procs == 1:
+        secs = _cpu_prove_worker((case, per))
+    else:
+        import multiprocessing as mp
+
+        with mp.get_context("fork").Pool(procs) as pool:
+            t0 = time.perf_counter()
+            pool.map(_cpu_prove_worker, [(case, per)] * procs)
+            secs = time.perf_counter() - t0
+    done = per * procs
+    return {"value": done / secs, "unit": "proofs/s", "cores": procs, "kind": "port",
+            "sample": "%d n=128 proofs (oracle/shuffle_ref.py incl. the reference's self-check MSMs, C arithmetic)" % done, "seconds": secs}
+
+
+def run_ours_prove(args, rank, world, dist):
+    from curdleproofs_pie_b200 import runtime as rt
+    from curdleproofs_pie_b200 import sharding
+
+    lib = rt.get_lib()
+    assert lib.backend == "cuda-sm_100a"
+    case = load_golden()
+    B = args.batch if args.batch != 8192 else 4096          # BASELINE config 3: 4096 proofs per batch
+    sampler = ClockSampler(lib.device) if rank == 0 else None
+    if dist is not None:
+        dist.barrier()
+    r = measure_prove(args, lib, case, B, args.steps)
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = sharding.max_over_ranks(r["ms"], dist, device="cuda")
+    ms_e2e = sharding.max_over_ranks(r["ms_e2e"], dist, device="cuda")
+    if rank != 0:
+        return None
+    peak_mac, _ = lib.bench_int_pipe(0, 20000)
+    model = prove_model(128, 124, 7, r["window"])
+    total_modmul = B * sum(model.values())
+    prof = r["prof"]
+    fm = prof.get("FixedMsmWindow", {"ms": 0.0, "launches": 1})
+    fm_ms_step = fm["ms"] / args.steps
+    fm_macs = B * model["fixed_msm"] * MAC_PER_MODMUL
+    total_kernel_ms = sum(v["ms"] for v in prof.values())
+    cpu = cpu_prove_rate(case, sample=args.cpu_sample_prove, procs=1)
+    total = B * world
+    return {
+        "metric": "curdleproofs_prove_per_s_n128_batched", "value": total * args.steps / (ms * 1e-3), "unit": "proofs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": 3, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 limbs (381-bit Fq, 255-bit Fr)", "data": "synthetic",
+        "config": {"workload": "batch generation of Whisk-size (n=128, ell=124) curdleproofs, B=%d proofs per GPU per step in lock-step; "
+                               "pre-shuffle trackers from the reference-generated fixture, per-lane permutation / k / blinders; 256 of the proofs re-checked by the batched verifier" % B,
+                   "B_per_gpu": B, "n": 128, "window_var": r["window"], "window_fixed": 12, "sharding": "per-proof, no collective",
+                   "l2": "inputs_larger_than_l2 (%.0f MB per step)" % (r["h2d"] / 1e6)},
+        "e2e": {"value": total * args.steps / (ms_e2e * 1e-3), "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+        "gpu_launches": r["launches"], "clocks": clocks,
+        "roofline": {"bound": "int_pipe", "kernel": "FixedMsmWindow", "achieved": fm_macs / (fm_ms_step * 1e-3) / 1e9 if fm_ms_step else 0.0,
+                     "peak": peak_mac / 1e9, "unit": "GMAC/s", "frac": (fm_macs / (fm_ms_step * 1e-3) / peak_mac) if fm_ms_step and peak_mac else None,
+                     "traffic": None, "kernel_share_of_step": fm["ms"] / total_kernel_ms if total_kernel_ms else None,
+                     "whole_step_frac_of_peak": total_modmul * MAC_PER_MODMUL / (ms / args.steps * 1e-3) / peak_mac if peak_mac else None,
+                     "peak_source": "data-dependent IMAD.WIDE.U32 chains measured in this run",
+                     "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}},
+        "cpu_baseline": cpu,
     }
 
 
@@ -538,7 +726,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="verify", choices=["verify", "msm"])
+    ap.add_argument("--workload", default="verify", choices=["verify", "prove", "msm"])
+    ap.add_argument("--prove-window", type=int, default=0, help="bucket window of the prover's variable-base MSMs (0 = model)")
+    ap.add_argument("--prove-batch", type=int, default=1024, help="proofs in the prove side-measurement of the default (verify) run; 0 = skip")
+    ap.add_argument("--cpu-sample-prove", type=int, default=4, help="proofs in the bounded CPU sample")
     ap.add_argument("--batch", type=int, default=8192, help="proofs (or MSMs) per GPU per step")
     ap.add_argument("--n", type=int, default=128)
     ap.add_argument("--window", type=int, default=0, help="bucket window width (0 = from the work model)")
@@ -569,7 +760,7 @@ def main():
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
     os.environ["CPG_DEVICE"] = str(local)
-    line = (run_ours_verify if args.workload == "verify" else run_ours)(args, rank, world, dist)
+    line = {"verify": run_ours_verify, "prove": run_ours_prove, "msm": run_ours}[args.workload](args, rank, world, dist)
     if line is not None:
         print(json.dumps(line), flush=True)
     if dist is not None:

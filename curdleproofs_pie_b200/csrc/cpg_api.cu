@@ -657,3 +657,4 @@ int cpg_bench_int_pipe(int, uint64_t, double* per_second, float* ms) {
 }  // extern "C"
 
 #include "verify.inl"
+#include "prove.inl"

@@ -75,6 +75,13 @@ _SIGS = {
     "cpg_verifier_set_streams": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "cpg_verify_batch": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_char_p, _c.c_size_t, _c.c_char_p]),
     "cpg_verify_replay_device": (_c.c_int, [_c.c_void_p, _c.c_char_p]),
+    "cpg_prover_create": (_c.c_void_p, [_c.c_char_p, _c.c_size_t, _c.c_size_t, _c.c_int]),
+    "cpg_prover_free": (_c.c_int, [_c.c_void_p]),
+    "cpg_prover_proof_bytes": (_c.c_size_t, [_c.c_void_p]),
+    "cpg_prover_rand_scalars": (_c.c_size_t, [_c.c_void_p]),
+    "cpg_prover_set_window": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "cpg_prove_replay_device": (_c.c_int, [_c.c_void_p]),
+    "cpg_prove_batch": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_char_p, _c.c_char_p, _c.c_size_t, _c.c_char_p, _c.c_char_p, _c.c_char_p]),
     "cpg_bench_int_pipe": (_c.c_int, [_c.c_int, _c.c_uint64, _c.POINTER(_c.c_double), _c.POINTER(_c.c_float)]),
 }
 EXPORTS = tuple(sorted(_SIGS))

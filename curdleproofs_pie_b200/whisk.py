@@ -107,3 +107,93 @@ def IsValidWhiskShuffleProofBatch(crs, pre_shuffle_trackers, post_shuffle_tracke
         except Exception:
             inputs.append(b"")
     return ver.verify(inputs, list(whisk_shuffle_proofs))
+
+
+class BatchProver:
+    """Device-resident CRS tables + lock-step proof generation (cpg_prove_batch)."""
+
+    def __init__(self, crs_bytes, ell, n_blinders=4, fixed_window=0, lib=None):
+        self.lib = lib or _rt.get_lib()
+        self.ell = int(ell)
+        self.n = self.ell + int(n_blinders)
+        crs_bytes = bytes(crs_bytes)
+        if len(crs_bytes) != 48 * (self.n + 5):
+            raise ValueError("crs_bytes must be CurdleproofsCrs.to_bytes() for (ell, n_blinders)")
+        self.handle = self.lib.c.cpg_prover_create(crs_bytes, self.ell, int(n_blinders), fixed_window)
+        if not self.handle:
+            raise _rt.CpgError("cpg_prover_create failed: " + self.lib.last_error())
+        self.proof_len = int(self.lib.c.cpg_prover_proof_bytes(self.handle))
+        self.n_rand = int(self.lib.c.cpg_prover_rand_scalars(self.handle))
+
+    def set_window(self, c):
+        self.lib.check(self.lib.c.cpg_prover_set_window(self.handle, int(c)), "cpg_prover_set_window")
+
+    def draw_randomness(self, rng):
+        """Blinders for ONE proof in the reference's draw order, from a `random`-like
+        object; call it right after drawing the permutation and k as the reference does."""
+        order = _rt.R_ORDER
+        return b"".join(rng.randint(1, order - 1).to_bytes(32, "little") for _ in range(self.n_rand))
+
+    def prove_raw(self, inputs, perms, ks, rand, B):
+        import array
+
+        perm_arr = array.array("I", perms)
+        assert perm_arr.itemsize == 4 and len(perm_arr) == B * self.ell
+        out_tu = ctypes.create_string_buffer(B * 2 * self.ell * 48)
+        out_pr = ctypes.create_string_buffer(B * self.proof_len)
+        status = ctypes.create_string_buffer(max(1, B))
+        pbuf = (ctypes.c_uint32 * len(perm_arr)).from_buffer(perm_arr)
+        self.lib.check(self.lib.c.cpg_prove_batch(self.handle, inputs, pbuf, ks, rand, B, out_tu, out_pr, status), "cpg_prove_batch")
+        return out_tu.raw, out_pr.raw, status.raw[:B]
+
+    def prove(self, pre_inputs, perms, ks, rands):
+        """pre_inputs[i] = vec_R|vec_S bytes, perms[i] = list of ell ints, ks[i] = int, rands[i] = bytes
+        from draw_randomness.  Returns [(vec_T|vec_U bytes, M|proof bytes)]; raises on a malformed input."""
+        B = len(pre_inputs)
+        flat_perm = [int(x) for p in perms for x in p]
+        tu, pr, st = self.prove_raw(b"".join(pre_inputs), flat_perm, b"".join(int(k).to_bytes(32, "little") for k in ks), b"".join(rands), B)
+        if any(st):
+            raise ValueError("serialised data seems to be invalid (lanes %s)" % [i for i, s in enumerate(st) if s])
+        w = 2 * self.ell * 48
+        return [(tu[i * w:(i + 1) * w], pr[i * self.proof_len:(i + 1) * self.proof_len]) for i in range(B)]
+
+    def close(self):
+        if self.handle:
+            self.lib.c.cpg_prover_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def GenerateWhiskShuffleProofBatch(crs, pre_shuffle_trackers_per_proof, rng=None):
+    """Batched GenerateWhiskShuffleProof (whisk_interface.py:111-140): for each proof draws the
+    permutation, k and the blinders from `rng` (default: the `random` module) exactly as the
+    reference does, then proves all of them on the GPU.  Returns [(post_trackers, proof_bytes)]."""
+    import random as _random
+
+    rng = rng or _random
+    if isinstance(crs, tuple):
+        crs_bytes, ell = crs
+        nbl = 4
+    else:
+        crs_bytes, ell, nbl = crs.to_bytes(), len(crs.vec_G), len(crs.vec_H)
+    prover = BatchProver(crs_bytes, ell, nbl)
+    inputs, perms, ks, rands = [], [], [], []
+    for trackers in pre_shuffle_trackers_per_proof:
+        perm = list(range(ell))
+        rng.shuffle(perm)
+        k = rng.randint(1, _rt.R_ORDER - 1)
+        halves = trackers_to_input(trackers, [])
+        inputs.append(halves)
+        perms.append(perm); ks.append(k); rands.append(prover.draw_randomness(rng))
+    out = []
+    for tu, proof in prover.prove(inputs, perms, ks, rands):
+        T, U = tu[:48 * ell], tu[48 * ell:]
+        post = [(T[48 * i:48 * i + 48], U[48 * i:48 * i + 48]) for i in range(ell)]
+        out.append((post, proof))
+    prover.close()
+    return out

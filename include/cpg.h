@@ -134,6 +134,29 @@ int cpg_verify_batch(void* verifier, const uint8_t* inputs, const uint8_t* proof
 /* re-run the device side (decompress, D/A', MSM, test) of the last batch on its resident inputs */
 int cpg_verify_replay_device(void* verifier, uint8_t* verdicts_or_null);
 
+/* ---- batched shuffle-proof generation ----------------------------------------------------------
+ * Replaces, for B proofs in lock-step, GenerateWhiskShuffleProof (cp/whisk_interface.py:111-140) ->
+ * shuffle_permute_and_commit_input (cp/curdleproofs.py:301-321) + CurdleProofsProof.new (:50-160) and
+ * every sub-proof's .new below it.  Transcript, Fr algebra and all group operations run on the GPU;
+ * randomness is an input so that a caller drawing it in the reference's order gets the
+ * reference's proof bytes.
+ *   inputs    : [B][2*ell*48]  vec_R | vec_S (pre-shuffle tracker halves)
+ *   perms     : [B][ell] u32   post[j] = k * pre[perm[j]]
+ *   ks        : [B][32]        shuffle scalar k (canonical LE)
+ *   rand      : [B][cpg_prover_rand_scalars][32]
+ *               m_bl(4) a_bl(2) c_bl(4) ipa_r(n) ipa_z(n-2) r_t r_u r_a r_b r_k msm_r(n), canonical LE
+ *   out_tu    : [B][2*ell*48]  vec_T | vec_U (post-shuffle tracker halves)
+ *   out_proofs: [B][cpg_prover_proof_bytes]  M | proof  (WhiskShuffleProof.to_bytes, :57-61)
+ *   status    : [B] 0 ok, 1 malformed input point encoding */
+void* cpg_prover_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window);
+int cpg_prover_free(void* prover);
+size_t cpg_prover_proof_bytes(const void* prover);
+size_t cpg_prover_rand_scalars(const void* prover);
+int cpg_prover_set_window(void* prover, int var_window);
+int cpg_prove_replay_device(void* prover);   /* device side of the last batch again, inputs resident */
+int cpg_prove_batch(void* prover, const uint8_t* inputs, const uint32_t* perms, const uint8_t* ks, const uint8_t* rand,
+                    size_t B, uint8_t* out_tu, uint8_t* out_proofs, uint8_t* status);
+
 /* ---- roofline support: saturating integer-pipe microbenchmark ---------------------------------
  * Runs `iters` dependent-chain steps of 32x32->64 multiply-accumulates on every SM and reports
  * the achieved rate: kind 0 = 32x32->64 MAC/s of data-dependent IMAD.WIDE.U32 chains (THE roofline

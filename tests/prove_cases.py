@@ -1,0 +1,67 @@
+"""Batched prover (cpg_prove_batch) against the golden fixtures produced by the UNMODIFIED reference:
+with the blinders drawn from Python's `random` in the reference's order under the fixture's seed, the
+post-shuffle trackers, M and the proof wire bytes must equal the reference's bit for bit."""
+import random
+
+import shuffle_cases as sc
+from curdleproofs_pie_b200 import runtime as rt
+from curdleproofs_pie_b200 import whisk
+
+
+def replay_rng(case, prover):
+    """Re-create the reference test's RNG stream (oracle/gen_golden.py::one_case) up to the prover's draws."""
+    N = case["N"]
+    ell = N - 4
+    random.seed(case["seed"])
+    for _ in range(ell + 4 + 3):                    # CurdleproofsCrs.new: ell + n_bl + 3 random points
+        random.randint(1, rt.R_ORDER - 1)
+    perm = list(range(ell))
+    random.shuffle(perm)
+    k = random.randint(1, rt.R_ORDER - 1)
+    for _ in range(2 * ell):                        # vec_R, vec_S
+        random.randint(1, rt.R_ORDER - 1)
+    rand = prover.draw_randomness(random)           # m_bl, then CurdleProofsProof.new's 3n + 9 draws
+    assert perm == case["perm"] and k == case["k"]
+    return perm, k, rand
+
+
+def check_prove(lib, name, copies=1, fixed_window=0, window=0):
+    case = sc.load_case(name)
+    ell = case["N"] - 4
+    prover = whisk.BatchProver(bytes.fromhex(case["crs"]), ell, fixed_window=fixed_window, lib=lib)
+    if window:
+        prover.set_window(window)
+    perm, k, rand = replay_rng(case, prover)
+    pre = b"".join(bytes.fromhex(h) for h in case["vec_R"] + case["vec_S"])
+    res = prover.prove([pre] * copies, [perm] * copies, [k] * copies, [rand] * copies)
+    want_tu = b"".join(bytes.fromhex(h) for h in case["vec_T"] + case["vec_U"])
+    want_proof = bytes.fromhex(case["M"]) + bytes.fromhex(case["proof"])
+    for tu, proof in res:
+        assert tu == want_tu, "post-shuffle trackers differ from the reference's"
+        assert proof[:48] == want_proof[:48], "M differs"
+        assert proof == want_proof, "proof bytes differ from the reference's (first diff at %d)" % next(i for i in range(len(proof)) if proof[i] != want_proof[i])
+    prover.close()
+    return res
+
+
+def check_prove_then_verify(lib, name, B=3, fixed_window=0):
+    """Fresh randomness per lane (different permutations and k): every proof must verify, and must stop
+    verifying when paired with another lane's trackers."""
+    case = sc.load_case(name)
+    ell = case["N"] - 4
+    crs = bytes.fromhex(case["crs"])
+    prover = whisk.BatchProver(crs, ell, fixed_window=fixed_window, lib=lib)
+    rng = random.Random(2718)
+    pre = b"".join(bytes.fromhex(h) for h in case["vec_R"] + case["vec_S"])
+    perms, ks, rands = [], [], []
+    for _ in range(B):
+        p = list(range(ell)); rng.shuffle(p)
+        perms.append(p); ks.append(rng.randint(1, rt.R_ORDER - 1)); rands.append(prover.draw_randomness(rng))
+    res = prover.prove([pre] * B, perms, ks, rands)
+    prover.close()
+    ver = whisk.BatchVerifier(crs, ell, fixed_window=fixed_window, lib=lib)
+    inputs = [pre + tu for tu, _ in res]
+    proofs = [pr for _, pr in res]
+    assert ver.verify(inputs, proofs) == [True] * B
+    assert ver.verify(inputs, proofs[1:] + proofs[:1]) == [False] * B
+    ver.close()

@@ -135,3 +135,17 @@ def test_verify_replay_matches(gpu_lib):
     assert [bool(x) for x in out.raw] == [g and True for g in got] or True   # replay has no host-side rejects
     honest = [i for i, v in enumerate(vs) if v[0] == "honest"]
     assert all(out.raw[i] == 1 for i in honest)
+
+
+# ---- batched prover (cpg_prove_batch): proof bytes equal the reference's under the fixture's seed ----
+import prove_cases as prc  # noqa: E402
+
+
+@pytest.mark.parametrize("name,copies", [("shuffle_N8_seed1234.json", 1), ("shuffle_N16_seed77.json", 2), ("shuffle_N64_seed2024.json", 2),
+                                          ("shuffle_N128_seed4096.json", 3)])
+def test_prove_batch_bytes_equal_reference(gpu_lib, name, copies):
+    prc.check_prove(gpu_lib, name, copies=copies)
+
+
+def test_prove_then_verify_full_size(gpu_lib):
+    prc.check_prove_then_verify(gpu_lib, "shuffle_N128_seed4096.json", B=96)

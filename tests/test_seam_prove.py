@@ -1,0 +1,15 @@
+"""CPU tier for the batched prover: per-round step kernels and MSMs on the host-emulated kernels,
+proof bytes against the reference's golden fixtures."""
+import prove_cases as pc
+
+
+def test_prove_bytes_N8(seam_lib):
+    pc.check_prove(seam_lib, "shuffle_N8_seed1234.json", fixed_window=4)
+
+
+def test_prove_bytes_N16_two_lanes(seam_lib):
+    pc.check_prove(seam_lib, "shuffle_N16_seed77.json", copies=2, fixed_window=5, window=3)
+
+
+def test_prove_then_verify_N8(seam_lib):
+    pc.check_prove_then_verify(seam_lib, "shuffle_N8_seed1234.json", B=3, fixed_window=4)
