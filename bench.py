@@ -728,7 +728,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="verify", choices=["verify", "prove", "msm"])
     ap.add_argument("--prove-window", type=int, default=0, help="bucket window of the prover's variable-base MSMs (0 = model)")
-    ap.add_argument("--prove-batch", type=int, default=1024, help="proofs in the prove side-measurement of the default (verify) run; 0 = skip")
+    ap.add_argument("--prove-batch", type=int, default=4096, help="proofs in the prove side-measurement of the default (verify) run; 0 = skip")
     ap.add_argument("--cpu-sample-prove", type=int, default=4, help="proofs in the bounded CPU sample")
     ap.add_argument("--batch", type=int, default=8192, help="proofs (or MSMs) per GPU per step")
     ap.add_argument("--n", type=int, default=128)

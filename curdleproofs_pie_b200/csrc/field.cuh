@@ -126,6 +126,17 @@ CPG_HD Fp<C> pow_public(const Fp<C>& a, const uint32_t (&e)[EW]) {
 typedef Fp<FqCfg> Fq;
 typedef Fp<FrCfg> Fr;
 
+// Fq products as real calls (device only, -DCPG_FIELD_CALLS): the ABI passes both operands and the
+// result in registers (no stack traffic), each call costs ~50 register moves, and the kernels shrink
+// from ~80 KB of straight-line SASS per point addition to a ~5 KB multiply body that stays in the
+// instruction cache.  Measured choice: see DESIGN.md "instruction cache".
+#if defined(__CUDA_ARCH__) && defined(CPG_FIELD_CALLS)
+static __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { Fq r; mont_mul_n<12>(r.l, a.l, b.l, FqCfg::p(), FqCfg::INV); return r; }
+static __device__ __noinline__ Fq fq_sqr_call(Fq a) { Fq r; mont_sqr_n<12>(r.l, a.l, FqCfg::p(), FqCfg::INV); return r; }
+__device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
+__device__ __forceinline__ Fq sqr(const Fq& a) { return fq_sqr_call(a); }
+#endif
+
 // Fq inversion a^(p-2) and square root candidate a^((p+1)/4) (p = 3 mod 4).
 CPG_HD Fq fq_inv(const Fq& a) {
     const uint32_t e[12] = {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
