@@ -476,8 +476,19 @@ int cpg_g1_fold(const void* L, const void* R, const uint8_t* x, size_t rows, siz
 }
 
 /* ---- batched Pippenger ---- */
+static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint32_t* d_base_off, const uint8_t* d_scalars,
+                            size_t B, size_t n, int window, void* d_out);
 int cpg_g1_msm_batched(const void* d_bases, size_t base_stride, const uint8_t* d_scalars,
                        size_t B, size_t n, int window, void* d_out) {
+    return msm_batched_impl(d_bases, base_stride, nullptr, d_scalars, B, n, window, d_out);
+}
+int cpg_g1_msm_batched_off(const void* d_bases, const uint32_t* d_base_off, const uint8_t* d_scalars,
+                           size_t B, size_t n, int window, void* d_out) {
+    if (!d_base_off) return fail("cpg_g1_msm_batched_off: null offsets");
+    return msm_batched_impl(d_bases, 0, d_base_off, d_scalars, B, n, window, d_out);
+}
+static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint32_t* d_base_off, const uint8_t* d_scalars,
+                            size_t B, size_t n, int window, void* d_out) {
     NEED_INIT();
     if (!B) return 0;
     if (n == 0) {  // empty sums are the identity (compute_MSM returns Z1 for empty input)
@@ -488,7 +499,7 @@ int cpg_g1_msm_batched(const void* d_bases, size_t base_stride, const uint8_t* d
     uint32_t c = window > 0 ? (uint32_t)window : pick_window(n);
     if (c < 2 || c > 20) return fail("cpg_g1_msm_batched: window must be in [2, 20]");
     Recode rc = make_recode(c);
-    MsmShape s; s.n = (uint32_t)n; s.c = c; s.W = rc.W; s.NB = 1u << (c - 1); s.base_stride = base_stride;
+    MsmShape s; s.n = (uint32_t)n; s.c = c; s.W = rc.W; s.NB = 1u << (c - 1); s.base_stride = base_stride; s.base_off = nullptr;
     // bound scratch to ~6 GiB per chunk of MSMs
     size_t per_msm = (size_t)s.W * ((size_t)(s.NB + 1) * 4 + (size_t)n * 6 + (size_t)s.NB * (sizeof(Xyzz) + 2) + sizeof(Xyzz));
     size_t chunk = (size_t)6 << 30;
@@ -507,7 +518,8 @@ int cpg_g1_msm_batched(const void* d_bases, size_t base_stride, const uint8_t* d
         Xyzz* wsum = sc.get<Xyzz>(BW);
         if (!boff || !sorted || !buckets || !wsum) return fail("cpg_g1_msm_batched: scratch allocation failed");
         const uint32_t* ks = (const uint32_t*)d_scalars + (uint64_t)b0 * n * 8;
-        const Aff* bases = (const Aff*)d_bases + (uint64_t)b0 * base_stride;
+        const Aff* bases = (const Aff*)d_bases + (d_base_off ? 0 : (uint64_t)b0 * base_stride);
+        s.base_off = d_base_off ? d_base_off + b0 : nullptr;
         int16_t* dig = sc.get<int16_t>((uint64_t)nb * n * s.W);
         if (!dig) return fail("cpg_g1_msm_batched: scratch allocation failed");
         if (int r = launch(RecodeDigits{s, rc, ks, dig}, (uint64_t)nb * n)) return r;
@@ -558,7 +570,7 @@ int cpg_g1_msm_fixed_batched(const void* table, const uint8_t* d_scalars, size_t
     Scratch sc;
     Xyzz* partial = sc.get<Xyzz>((uint64_t)B * t->s.W);
     if (!partial) return fail("cpg_g1_msm_fixed_batched: scratch allocation failed");
-    if (int r = launch(FixedMsmWindow{t->s, rc, (uint32_t)B, t->table, (const uint32_t*)d_scalars, partial}, (uint64_t)B * t->s.W)) return r;
+    if (int r = launch<128, 3>(FixedMsmWindow{t->s, rc, (uint32_t)B, t->table, (const uint32_t*)d_scalars, partial}, (((uint64_t)B + 31) / 32) * 32 * t->s.W)) return r;
     return launch(SumWindows{t->s.W, partial, (Jac*)d_out, accumulate}, B);
 }
 

@@ -46,7 +46,8 @@ CPG_HD int recode_digit(const Recode& rc, const uint32_t* kp, uint32_t w) {
 
 struct MsmShape {
     uint32_t B, n, c, W, NB;      // NB = 2^(c-1)
-    uint64_t base_stride;         // bases of msm m start at m*base_stride (0 = shared by all)
+    uint64_t base_stride;         // bases of msm m start at m*base_stride (0 = shared by all) ...
+    const uint32_t* base_off;     // ... unless this is set: bases of msm m start at base_off[m] (in points)
 };
 
 // 0 --- signed digits of one scalar, all windows ---------------------------------------------
@@ -153,7 +154,7 @@ struct BucketAccumulate {
         uint32_t m = (uint32_t)(mw / s.W);
         const uint32_t* off = boff + mw * (uint64_t)(s.NB + 1);
         const uint32_t* lst = sorted + mw * (uint64_t)s.n;
-        const Aff* P = bases + (uint64_t)m * s.base_stride;
+        const Aff* P = bases + (s.base_off ? (uint64_t)s.base_off[m] : (uint64_t)m * s.base_stride);
         Xyzz acc = xyzz_inf();
         uint32_t lo = off[b], hi = off[b + 1];
         if (lo < hi) {
@@ -234,27 +235,34 @@ struct AffToJac {
     const Aff* in; Jac* out;
     CPG_HD void operator()(uint64_t t) const { out[t] = to_jac(in[t]); }
 };
-struct FixedMsmWindow {            // thread = (msm, window): sum_i +-T[i][w][|d|-1]
+struct FixedMsmWindow {            // sum_i +-T[i][w][|d|-1] for one (msm, window)
     static constexpr const char* kName = "FixedMsmWindow";
     FixedShape s; Recode rc;
     uint32_t B;
     const Aff* table;
     const uint32_t* scalars;       // [B][nb][8]
     Xyzz* partial;                 // [B*W]
+    // A warp = one window of 32 consecutive MSMs (lane = msm): all lanes walk the same bases of the same
+    // table segment, and callers that order their MSMs by kind (the prover: output-major) give every
+    // lane the same pattern of structurally zero coefficients, so the zero skips do not diverge.
     CPG_HD void operator()(uint64_t t) const {
-        uint32_t m = (uint32_t)(t / s.W), w = (uint32_t)(t % s.W);
-        const uint32_t* ks = scalars + (uint64_t)m * s.nb * 8;
+        uint32_t lane = (uint32_t)(t % 32), w = (uint32_t)((t / 32) % s.W);
+        uint64_t m = (t / (32ull * s.W)) * 32 + lane;
+        if (m >= B) return;
+        const uint32_t* ks = scalars + m * s.nb * 8;
         Xyzz acc = xyzz_inf();
         uint32_t kp[8];
         for (uint32_t i = 0; i < s.nb; i++) {
-            recode_add(rc, ks + 8 * (uint64_t)i, kp);
+            const uint32_t* k = ks + 8 * (uint64_t)i;
+            if ((k[0] | k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) == 0) continue;   // zero coefficient: every digit is zero
+            recode_add(rc, k, kp);
             int d = recode_digit(rc, kp, w);
             if (!d) continue;
             uint32_t a = (uint32_t)(d < 0 ? -d : d);
             Aff q = table[((uint64_t)i * s.W + w) * s.NB + (a - 1)];
             acc = xyzz_add_mixed(acc, cneg(q, d < 0));
         }
-        partial[t] = acc;
+        partial[m * s.W + w] = acc;
     }
 };
 struct SumWindows {                // thread = msm: plain sum of W partials (no doublings)

@@ -58,14 +58,14 @@ struct PBuffers {
     PState* st;                   // [B]
     HFr* vec;                     // [B][PV_COUNT][n]
     uint8_t* outs48;              // [B][NOUT][48]   compressed outputs, by output id
-    uint8_t* fs;                  // [B][P_MAX_OUT][NF][32]  fixed-base coefficient rows of the round being prepared
+    uint8_t* fs;                  // [P_MAX_OUT][B][NF][32]  fixed-base coefficient rows of the round being prepared (output-major)
     uint8_t* vs;                  // [P_MAX_VAR][B][ell][32] variable-base coefficient rows
     uint8_t* proof;               // [B][proof_len]  wire proof (without M), filled at the end
     uint64_t B;
 };
 
 CPG_HD HFr* pvec(const PShape& sh, const PBuffers& pb, size_t b, int which) { return pb.vec + (b * PV_COUNT + (size_t)which) * sh.n; }
-CPG_HD uint8_t* frow(const PShape& sh, const PBuffers& pb, size_t b, uint32_t o) { return pb.fs + (b * P_MAX_OUT + o) * (size_t)sh.NF * 32; }
+CPG_HD uint8_t* frow(const PShape& sh, const PBuffers& pb, size_t b, uint32_t o) { return pb.fs + ((size_t)o * pb.B + b) * (size_t)sh.NF * 32; }
 CPG_HD uint8_t* vrow(const PShape& sh, const PBuffers& pb, size_t b, uint32_t o) { return pb.vs + ((size_t)o * pb.B + b) * (size_t)sh.ell * 32; }
 CPG_HD HFr prand(const PBuffers& pb, const PShape& sh, size_t b, uint32_t i) {
     HFr v; cpgh::fr_from_bytes(&v, pb.rand + (b * sh.NR + i) * 32); return v;
@@ -279,16 +279,13 @@ CPG_HD void prove_step(const PShape& sh, const POut& O, const PBuffers& pb, uint
         }
         s.r_t = prand(pb, sh, b, RO.r_t); s.r_u = prand(pb, sh, b, RO.r_u);
         s.r_a = prand(pb, sh, b, RO.r_a); s.r_b = prand(pb, sh, b, RO.r_b); s.r_k = prand(pb, sh, b, RO.r_k);
-        zero_rows(sh, pb, b, 10, 6);
-        // order: Rp Sp T1 T2 U1 U2 A1 A2 B1 B2 ; var rows: 0 Rp(R) 1 Sp(S) 2 T2(R) 3 U2(S) 4 A2(R) 5 B2(S)
-        uint8_t *vR = vrow(sh, pb, b, 0), *vS = vrow(sh, pb, b, 1), *vT2 = vrow(sh, pb, b, 2), *vU2 = vrow(sh, pb, b, 3), *vA2 = vrow(sh, pb, b, 4), *vB2 = vrow(sh, pb, b, 5);
+        zero_rows(sh, pb, b, 10, 2);
+        // order: Rp Sp T1 T2 U1 U2 A1 A2 B1 B2 ; var rows: 0 R' = MSM(vec_R, a), 1 S' = MSM(vec_S, a); the
+        // commitments' k R', r_k R', k S', r_k S' are one scalar-mul each of those results (ProveCombine)
+        uint8_t *vR = vrow(sh, pb, b, 0), *vS = vrow(sh, pb, b, 1);
         for (uint32_t i = 0; i < ell; i++) {
             fr_to_bytes(vR + 32 * (size_t)i, a[i]);
             memcpy(vS + 32 * (size_t)i, vR + 32 * (size_t)i, 32);
-            fr_to_bytes(vT2 + 32 * (size_t)i, fr_mul(s.k, a[i]));
-            memcpy(vU2 + 32 * (size_t)i, vT2 + 32 * (size_t)i, 32);
-            fr_to_bytes(vA2 + 32 * (size_t)i, fr_mul(s.r_k, a[i]));
-            memcpy(vB2 + 32 * (size_t)i, vA2 + 32 * (size_t)i, 32);
         }
         const size_t iH = n, iGt = n + 1, iGu = n + 2;
         fr_to_bytes(frow(sh, pb, b, 2) + 32 * iGt, s.r_t);      // cm_T = (G_t r_t, R' k + H r_t)
@@ -434,21 +431,34 @@ struct ProveShuffle {
     }
 };
 
-// out[b][id] = compress(fixed[b][o] (+ var[o_var][b])), thread = (proof, output of the round)
+// out[b][id] = compress(fixed[o][b] + scale * var[row][b]), thread = (output of the round, proof)
 struct ProveCombine {
     static constexpr const char* kName = "ProveCombine";
     uint32_t nout, NOUT; uint64_t B;
     uint32_t out_id[P_MAX_OUT];
     int32_t var_row[P_MAX_OUT];   // -1: no variable-base part
-    const Jac* fixed;             // [B][nout]
+    const uint32_t* scale[P_MAX_OUT];   // optional per-proof scalar multiplying the variable-base part ...
+    uint32_t scale_stride[P_MAX_OUT];   // ... at scale[o] + b*scale_stride[o] (u32 words)
+    const Jac* fixed;             // [nout][B]
     const Jac* var;               // [nvar][B]
     uint8_t* outs48;              // [B][NOUT][48]
     CPG_HD void operator()(uint64_t t) const {
-        uint64_t b = t / nout; uint32_t o = (uint32_t)(t % nout);
+        uint32_t o = (uint32_t)(t / B); uint64_t b = t % B;
         Jac p = fixed[t];
-        if (var_row[o] >= 0) p = jac_add(p, var[(uint64_t)var_row[o] * B + b]);
+        if (var_row[o] >= 0) {
+            Jac v = var[(uint64_t)var_row[o] * B + b];
+            if (scale[o]) v = jac_mul(v, scale[o] + b * scale_stride[o]);
+            p = jac_add(p, v);
+        }
         aff_compress(jac_to_aff(p), outs48 + (b * NOUT + out_id[o]) * 48);
     }
+};
+
+// base offset (in points) of variable-base instance t = v*B + b: proof b's row [R|S|T|U], vector set[v]
+struct VarOffsets {
+    static constexpr const char* kName = "VarOffsets";
+    uint64_t B; uint32_t ell; uint32_t set[P_MAX_VAR]; uint32_t* off;
+    CPG_HD void operator()(uint64_t t) const { uint64_t v = t / B, b = t % B; off[t] = (uint32_t)(b * 4 * ell + set[v] * ell); }
 };
 
 struct Prover {
@@ -460,11 +470,11 @@ struct Prover {
     int var_window = 0;
     size_t cap = 0, lastB = 0;
     uint8_t *d_in48 = nullptr, *d_tu48 = nullptr, *d_k = nullptr, *d_rand = nullptr, *d_outs = nullptr, *d_fs = nullptr, *d_vs = nullptr, *d_proof = nullptr, *d_err = nullptr;
-    uint32_t* d_perm = nullptr; Aff* d_bases = nullptr; PState* d_st = nullptr; HFr* d_vec = nullptr; Jac *d_fix = nullptr, *d_var = nullptr;
-    std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_bases, d_st, d_vec, d_fix, d_var}; }
+    uint32_t *d_perm = nullptr, *d_off = nullptr; Aff* d_bases = nullptr; PState* d_st = nullptr; HFr* d_vec = nullptr; Jac *d_fix = nullptr, *d_var = nullptr;
+    std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_off, d_bases, d_st, d_vec, d_fix, d_var}; }
     void release() {
         for (void* q : all()) cpg_free(q);
-        d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = nullptr; d_bases = nullptr; d_st = nullptr; d_vec = nullptr; d_fix = d_var = nullptr;
+        d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = d_off = nullptr; d_bases = nullptr; d_st = nullptr; d_vec = nullptr; d_fix = d_var = nullptr;
         cap = 0;
     }
     int reserve(size_t B, uint32_t NOUT) {
@@ -476,6 +486,7 @@ struct Prover {
         d_outs = (uint8_t*)cpg_malloc(B * NOUT * 48);        d_fs = (uint8_t*)cpg_malloc(B * P_MAX_OUT * sh.NF * 32);
         d_vs = (uint8_t*)cpg_malloc(B * P_MAX_VAR * ell * 32); d_proof = (uint8_t*)cpg_malloc(B * proof_len);
         d_err = (uint8_t*)cpg_malloc(B * 2 * ell);           d_perm = (uint32_t*)cpg_malloc(B * ell * 4);
+        d_off = (uint32_t*)cpg_malloc(B * P_MAX_VAR * 4);
         d_bases = (Aff*)cpg_malloc(sizeof(Aff) * B * 4 * ell); d_st = (PState*)cpg_malloc(sizeof(PState) * B);
         d_vec = (HFr*)cpg_malloc(sizeof(HFr) * B * PV_COUNT * n);
         d_fix = (Jac*)cpg_malloc(sizeof(Jac) * B * P_MAX_OUT); d_var = (Jac*)cpg_malloc(sizeof(Jac) * B * P_MAX_VAR);
@@ -511,7 +522,7 @@ int prove_device_all(Prover& p, size_t B) {
     pb.st = p.d_st; pb.vec = p.d_vec; pb.outs48 = p.d_outs; pb.fs = p.d_fs; pb.vs = p.d_vs; pb.proof = p.d_proof; pb.B = B;
 
     // per round: (first output id, count) and which outputs carry a variable-base part over which vector
-    struct RoundPlan { uint32_t nout; uint32_t ids[P_MAX_OUT]; int32_t var_row[P_MAX_OUT]; uint32_t nvar; uint32_t var_set[P_MAX_VAR]; };
+    struct RoundPlan { uint32_t nout; uint32_t ids[P_MAX_OUT]; int32_t var_row[P_MAX_OUT]; uint32_t nvar; uint32_t var_set[P_MAX_VAR]; int scale_kind[P_MAX_OUT]; };
     auto plan_for = [&](uint32_t r) {
         RoundPlan pl; memset(&pl, 0, sizeof pl);
         for (uint32_t i = 0; i < P_MAX_OUT; i++) pl.var_row[i] = -1;
@@ -522,7 +533,13 @@ int prove_device_all(Prover& p, size_t B) {
         else if (r == 3) add(O.C, -1);
         else if (r == 4) { add(O.D, -1); add(O.Bc, -1); add(O.Bd, -1); }
         else if (r < 5 + lg) { for (uint32_t k = 0; k < 4; k++) add(O.ipa0 + 4 * (r - 5) + k, -1); }
-        else if (r == 5 + lg) { add(O.Rp, 0); add(O.Sp, 1); add(O.T1, -1); add(O.T2, 0); add(O.U1, -1); add(O.U2, 1); add(O.A1, -1); add(O.A2, 0); add(O.B1, -1); add(O.B2, 1); }
+        else if (r == 5 + lg) {
+            // R' = MSM(vec_R, a) and S' = MSM(vec_S, a) are the only MSMs; cm_T2/cm_A2 reuse R' scaled by k / r_k,
+            // cm_U2/cm_B2 reuse S' (curdleproofs.py:97-102, same_scalar.py:43-44)
+            add(O.Rp, 0); add(O.Sp, 1); add(O.T1, -1); add(O.T2, -1); add(O.U1, -1); add(O.U2, -1); add(O.A1, -1); add(O.A2, -1); add(O.B1, -1); add(O.B2, -1);
+            pl.var_row[3] = 0; pl.scale_kind[3] = 1; pl.var_row[5] = 1; pl.scale_kind[5] = 1;      // T2 = k R' + ..., U2 = k S' + ...
+            pl.var_row[7] = 0; pl.scale_kind[7] = 2; pl.var_row[9] = 1; pl.scale_kind[9] = 2;      // A2 = r_k R' + ..., B2 = r_k S' + ...
+        }
         else if (r == 6 + lg) { add(O.Ap, -1); add(O.Ba, -1); add(O.Bt, 2); add(O.Bu, 3); }
         else if (r < 7 + 2 * lg) { uint32_t base = O.msm0 + 6 * (r - 7 - lg); add(base, -1); add(base + 1, 2); add(base + 2, 3); add(base + 3, -1); add(base + 4, 2); add(base + 5, 3); }
         return pl;
@@ -531,29 +548,23 @@ int prove_device_all(Prover& p, size_t B) {
         if (int rc = launch<64>(ProveStep{sh, O, pb, r}, B)) return rc;
         if (r == 7 + 2 * lg) break;
         RoundPlan pl = plan_for(r);
-        // fixed-base part of every output of the round: B*nout MSMs over the CRS table.  Rows were
-        // written [b][o] with stride P_MAX_OUT, so compact them when nout < P_MAX_OUT.
-        uint8_t* fs_rows = p.d_fs;
-        Scratch sc;
-        if (pl.nout != P_MAX_OUT) {
-            uint8_t* packed = sc.get<uint8_t>(B * (size_t)pl.nout * sh.NF * 32);
-            if (!packed) return fail("cpg_prove_batch: scratch allocation failed");
-#ifndef CPG_HOST_EMU
-            CK(cudaMemcpy2DAsync(packed, (size_t)pl.nout * sh.NF * 32, p.d_fs, (size_t)P_MAX_OUT * sh.NF * 32,
-                                 (size_t)pl.nout * sh.NF * 32, B, cudaMemcpyDeviceToDevice, cur()));
-#else
-            for (size_t b = 0; b < B; b++) memcpy(packed + b * (size_t)pl.nout * sh.NF * 32, p.d_fs + b * (size_t)P_MAX_OUT * sh.NF * 32, (size_t)pl.nout * sh.NF * 32);
-#endif
-            fs_rows = packed;
-        }
-        if (int rc = cpg_g1_msm_fixed_batched(p.table, fs_rows, B * pl.nout, 0, p.d_fix)) return rc;
-        for (uint32_t v = 0; v < pl.nvar; v++) {        // variable-base parts: one batched MSM per output
-            const Aff* bases = p.d_bases + (size_t)pl.var_set[v] * ell;
-            if (int rc = cpg_g1_msm_batched(bases, 4 * (size_t)ell, p.d_vs + (size_t)v * B * ell * 32, B, ell, p.var_window, p.d_var + (size_t)v * B)) return rc;
+        // fixed-base part of every output of the round: B*nout MSMs over the CRS table (rows are output-major)
+        if (int rc = cpg_g1_msm_fixed_batched(p.table, p.d_fs, B * pl.nout, 0, p.d_fix)) return rc;
+        if (pl.nvar) {                                  // variable-base parts: ONE batched MSM over all B*nvar instances
+            VarOffsets vo; vo.B = B; vo.ell = ell; vo.off = p.d_off;
+            for (uint32_t v = 0; v < P_MAX_VAR; v++) vo.set[v] = v < pl.nvar ? pl.var_set[v] : 0;
+            if (int rc = launch(vo, B * pl.nvar)) return rc;
+            if (int rc = cpg_g1_msm_batched_off(p.d_bases, p.d_off, p.d_vs, B * pl.nvar, ell, p.var_window, p.d_var)) return rc;
         }
         ProveCombine pc;
         pc.nout = pl.nout; pc.NOUT = O.NOUT; pc.B = B; pc.fixed = p.d_fix; pc.var = p.d_var; pc.outs48 = p.d_outs;
-        for (uint32_t i = 0; i < P_MAX_OUT; i++) { pc.out_id[i] = pl.ids[i]; pc.var_row[i] = pl.var_row[i]; }
+        const PRand RO(sh.n);
+        for (uint32_t i = 0; i < P_MAX_OUT; i++) {
+            pc.out_id[i] = pl.ids[i]; pc.var_row[i] = pl.var_row[i];
+            pc.scale[i] = nullptr; pc.scale_stride[i] = 0;
+            if (pl.scale_kind[i] == 1) { pc.scale[i] = (const uint32_t*)p.d_k; pc.scale_stride[i] = 8; }
+            if (pl.scale_kind[i] == 2) { pc.scale[i] = (const uint32_t*)p.d_rand + (size_t)RO.r_k * 8; pc.scale_stride[i] = sh.NR * 8; }
+        }
         if (int rc = launch(pc, B * pl.nout)) return rc;
     }
     return 0;

@@ -58,6 +58,7 @@ _SIGS = {
     "cpg_g1_mul": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_void_p]),
     "cpg_g1_fold": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_void_p]),
     "cpg_g1_msm_batched": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_void_p]),
+    "cpg_g1_msm_batched_off": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_void_p]),
     "cpg_fixed_table_create": (_c.c_void_p, [_c.c_void_p, _c.c_size_t, _c.c_int]),
     "cpg_fixed_table_free": (_c.c_int, [_c.c_void_p]),
     "cpg_fixed_table_bytes": (_c.c_size_t, [_c.c_void_p]),

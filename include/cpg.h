@@ -96,6 +96,10 @@ int cpg_g1_fold(const void* d_L_jac, const void* d_R_jac, const uint8_t* d_x, si
  * scalars are [B][n] x 32 B.  window = 0 picks the window width from n. */
 int cpg_g1_msm_batched(const void* d_bases_aff, size_t base_stride, const uint8_t* d_scalars,
                        size_t B, size_t n, int window, void* d_out_jac);
+/* same, with an explicit start (in points) of every MSM's base vector: bases of MSM b are
+ * d_bases_aff[d_base_off[b] ...] - lets MSMs over different sub-vectors share one call */
+int cpg_g1_msm_batched_off(const void* d_bases_aff, const uint32_t* d_base_off, const uint8_t* d_scalars,
+                           size_t B, size_t n, int window, void* d_out_jac);
 /* fixed-base tables for generators shared by every proof (the CRS, cp/crs.py:19-36):
  * T[i][w][d] = (d+1) 2^(c w) G_i.  Returns NULL on failure. */
 void* cpg_fixed_table_create(const void* d_bases_aff, size_t nb, int window);
