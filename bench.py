@@ -522,6 +522,104 @@ def run_ours_prove(args, rank, world, dist):
 
 
 
+# ------------------------------------------------------------------------------------------------
+def run_ours_msm_large(args, rank, world, dist):
+    """ONE n-term MSM (G1Point.multiexp_unchecked, BASELINE config 2's sweep / config 5's building block).
+    N = 1: all windows on one GPU.  N > 1: Pippenger windows split across ranks (every rank holds all
+    bases and scalars), one NCCL all-gather of the W window sums (W*144 B), Horner on every rank:
+    strong scaling.  The result is compared with the oracle on a structured instance."""
+    from curdleproofs_pie_b200 import msm as msm_mod
+    from curdleproofs_pie_b200 import runtime as rt
+    from curdleproofs_pie_b200 import sharding
+
+    lib = rt.get_lib()
+    assert lib.backend == "cuda-sm_100a"
+    n = args.n if args.n != 128 else 1 << 20
+    rng = random.Random(7)                                  # identical inputs on every rank
+    nuniq = 4096
+    base_jac = device_random_points(lib, rt, rng, nuniq)
+    uaff = lib.jac_to_aff(base_jac, nuniq)
+    bases = lib.alloc(n * rt.AFF)                           # n bases drawn from 4096 distinct points
+    have = 0
+    while have < n:
+        cnt = min(nuniq, n - have)
+        lib.check(lib.c.cpg_d2d(bases.ptr + have * rt.AFF, uaff.ptr, cnt * rt.AFF))
+        have += cnt
+    sc_bytes = bytearray(rng.randbytes(32 * n))             # seeded: every rank must hold the same scalars
+    sc_bytes[31::32] = bytes(b & 0x3F for b in sc_bytes[31::32])      # < 2^254 < r
+    scalars = lib.upload(bytes(sc_bytes))
+    c = args.window or int(lib.c.cpg_msm_pick_window(n))
+    dev = "cuda" if dist is not None else "cpu"
+
+    def step():
+        return msm_mod.msm_large(lib, bases, scalars, n, window=c, dist=dist, device=dev)
+
+    def barrier():
+        lib.sync()
+        if dist is not None:
+            dist.barrier()
+
+    out = step()
+    # parity on this very instance: aggregate the scalars per distinct base on the host, oracle MSM of 4096 terms
+    if rank == 0:
+        from oracle import cref_binding
+
+        cref = cref_binding.load()
+        agg = [0] * nuniq
+        for i in range(n):
+            agg[i % nuniq] += int.from_bytes(sc_bytes[32 * i:32 * i + 32], "little")
+        enc = lib.compress_aff(uaff, nuniq)
+        blobs = [cref.decompress(enc[48 * i:48 * i + 48], False) for i in range(nuniq)]
+        want = cref.compress(cref.msm(blobs, [a % R_ORDER for a in agg]))
+        assert lib.compress_jac(out, 1) == want, "large MSM differs from the oracle"
+    for _ in range(max(args.warmup, 3) - 1):
+        step()
+    barrier()
+    sampler = ClockSampler(lib.device) if rank == 0 else None
+    lib.profile(True)
+    launches0 = lib.launch_count()
+    barrier()
+    t0 = time.perf_counter()
+    lib.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms_dev = lib.timer_stop()
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    launches = lib.launch_count() - launches0
+    prof = lib.profile_report()
+    lib.profile(False)
+    clocks = sampler.stop() if sampler else None
+    # with N > 1 a step contains host-side plumbing (D2H of the slice, all-gather, H2D): use the wall clock
+    ms = sharding.max_over_ranks(wall if dist is not None else ms_dev, dist, device=dev)
+    if rank != 0:
+        return None
+    peak_mac, _ = lib.bench_int_pipe(0, 20000)
+    model = msm_model(n, c)
+    ba = prof.get("BucketAccumulate", {"ms": 0.0, "launches": 1})
+    ba_ms = ba["ms"] / max(1, ba["launches"])
+    W = model["W"]
+    my_windows = (W + world - 1) // world
+    ba_macs = n * my_windows * 10 * MAC_PER_MODMUL
+    cpu = cpu_msm_rate(min(n, 1 << 14), sample=1, procs=1)
+    return {
+        "metric": "g1_msm_mpoints_per_s", "value": n * args.steps / (ms * 1e-3) / 1e6, "unit": "Mpoints/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fq, 255-bit Fr)", "data": "synthetic",
+        "config": {"workload": "one G1 MSM of n=%d terms (multiexp_unchecked), window c=%d, W=%d windows%s; result checked against the oracle"
+                               % (n, c, W, "" if world == 1 else " split over %d GPUs + one all-gather of %d B" % (world, W * 144)),
+                   "n": n, "window": c, "l2": "inputs_larger_than_l2" if n * 128 > 126 << 20 else "scratch_larger_than_l2"},
+        "e2e": {"value": n * args.steps / (ms * 1e-3) / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": 0 if world == 1 else W * 144,
+                "d2h_bytes_per_step": 0 if world == 1 else my_windows * 144, "note": "bases and scalars are device-resident in this workload"},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "int_pipe", "kernel": "BucketAccumulate", "achieved": ba_macs / (ba_ms * 1e-3) / 1e9 if ba_ms else 0.0, "peak": peak_mac / 1e9,
+                     "unit": "GMAC/s", "frac": ba_macs / (ba_ms * 1e-3) / peak_mac if ba_ms and peak_mac else None, "traffic": None,
+                     "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}},
+        "cpu_baseline": cpu,
+    }
+
+
+
 def run_ours(args, rank, world, dist):
     import ctypes
 
@@ -726,12 +824,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="verify", choices=["verify", "prove", "msm"])
+    ap.add_argument("--workload", default="verify", choices=["verify", "prove", "msm", "msm_large"])
     ap.add_argument("--prove-window", type=int, default=0, help="bucket window of the prover's variable-base MSMs (0 = model)")
     ap.add_argument("--prove-batch", type=int, default=4096, help="proofs in the prove side-measurement of the default (verify) run; 0 = skip")
     ap.add_argument("--cpu-sample-prove", type=int, default=4, help="proofs in the bounded CPU sample")
     ap.add_argument("--batch", type=int, default=8192, help="proofs (or MSMs) per GPU per step")
-    ap.add_argument("--n", type=int, default=128)
+    ap.add_argument("--terms", dest="n", type=int, default=128, help="terms per MSM (msm workloads)")
     ap.add_argument("--window", type=int, default=0, help="bucket window width (0 = from the work model)")
     ap.add_argument("--transcript", default="device", choices=["device", "host"], help="where the Fiat-Shamir transcript + coefficient algebra run")
     ap.add_argument("--streams", type=int, default=1, help="sub-batches in flight on separate CUDA streams")
@@ -760,7 +858,7 @@ def main():
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist = dist_mod
     os.environ["CPG_DEVICE"] = str(local)
-    line = {"verify": run_ours_verify, "prove": run_ours_prove, "msm": run_ours}[args.workload](args, rank, world, dist)
+    line = {"verify": run_ours_verify, "prove": run_ours_prove, "msm": run_ours, "msm_large": run_ours_msm_large}[args.workload](args, rank, world, dist)
     if line is not None:
         print(json.dumps(line), flush=True)
     if dist is not None:

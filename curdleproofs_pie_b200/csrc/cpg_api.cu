@@ -9,6 +9,7 @@
 #include "../../include/cpg.h"
 #include "msm.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <stdio.h>
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(SORT_BLOCK) k_sort_digits_smem(SortDigits f, u
     uint16_t* rk_base = (uint16_t*)(sort_smem + (size_t)(s.NB + 1) * SORT_BLOCK) + threadIdx.x;
     uint64_t t = blockIdx.x * (uint64_t)SORT_BLOCK + threadIdx.x;
     if (t >= n_threads) return;
-    uint32_t m = (uint32_t)(t / s.W), w = (uint32_t)(t % s.W);
+    uint32_t m = (uint32_t)(t / s.wn), w = s.w0 + (uint32_t)(t % s.wn);
     StridedView<uint32_t> off{off_base, SORT_BLOCK};
     StridedView<uint16_t> rk{rk_base, SORT_BLOCK};
     sort_digits_body(s, f.dig + (uint64_t)m * s.n * s.W + w, f.sorted + t * (uint64_t)s.n, off, rk, f.rank != nullptr);
@@ -169,6 +170,27 @@ uint32_t pick_window(size_t n) {
         double W = windows_for(c), NB = (double)(1u << (c - 1));
         double cost = (double)n * W * 10.0 + W * NB * 2.0 * 14.0 + W * (c * 9.0 + 14.0);
         if (cost < best) { best = cost; bc = c; }
+    }
+    return bc;
+}
+
+// Single big MSMs are launched with few (msm, window) pairs, so besides the total work the longest
+// SERIAL chain matters: a bucket list is walked by one thread, and a window whose digit has only tw bits
+// (the top window holds 255 - c(W-1) bits) concentrates n terms in 2^tw lists.  Estimated time =
+// total products / pipe rate + serial products * single-thread latency.
+uint32_t pick_window_large(size_t n) {
+    double best = 1e300; uint32_t bc = 8;
+    for (uint32_t c = 6; c <= 16; c++) {
+        double W = windows_for(c), NB = (double)(1u << (c - 1));
+        int tw = 255 - (int)c * ((int)W - 1);
+        double top_lists = tw <= 0 ? 2.0 : (double)(1u << tw);
+        if (top_lists > NB) top_lists = NB;
+        double longest = std::max((double)n / top_lists, (double)n / NB);
+        double nch = NB / REDUCE_CH;
+        double serial = longest * 10.0 + (NB >= 4 * REDUCE_CH ? (nch >= 4 * REDUCE_CH ? 3.0 * REDUCE_CH + 3.0 * nch / REDUCE_CH : 3.0 * nch) * 14.0 : 2.0 * NB * 14.0);
+        double total = (double)n * W * 10.0 + W * NB * 2.0 * 14.0;
+        double t = total / 3.0e10 + serial * 1.5e-6;
+        if (t < best) { best = t; bc = c; }
     }
     return bc;
 }
@@ -477,7 +499,7 @@ int cpg_g1_fold(const void* L, const void* R, const uint8_t* x, size_t rows, siz
 
 /* ---- batched Pippenger ---- */
 static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint32_t* d_base_off, const uint8_t* d_scalars,
-                            size_t B, size_t n, int window, void* d_out);
+                            size_t B, size_t n, int window, void* d_out, uint32_t w0 = 0, uint32_t wn = 0);
 int cpg_g1_msm_batched(const void* d_bases, size_t base_stride, const uint8_t* d_scalars,
                        size_t B, size_t n, int window, void* d_out) {
     return msm_batched_impl(d_bases, base_stride, nullptr, d_scalars, B, n, window, d_out);
@@ -487,8 +509,30 @@ int cpg_g1_msm_batched_off(const void* d_bases, const uint32_t* d_base_off, cons
     if (!d_base_off) return fail("cpg_g1_msm_batched_off: null offsets");
     return msm_batched_impl(d_bases, 0, d_base_off, d_scalars, B, n, window, d_out);
 }
+int cpg_msm_window_count(size_t n, int window) {
+    uint32_t c = window > 0 ? (uint32_t)window : (n > 2048 ? pick_window_large(n) : pick_window(n ? n : 1));
+    return (int)windows_for(c);
+}
+int cpg_msm_pick_window(size_t n) { return (int)(n > 2048 ? pick_window_large(n) : pick_window(n ? n : 1)); }
+/* window sums S_w, w in [w_begin, w_end), of ONE n-term MSM as Jacobian points (the unit of the
+ * multi-GPU window split: every rank computes a slice, the slices are all-gathered, then combined) */
+int cpg_g1_msm_window_sums(const void* d_bases, const uint8_t* d_scalars, size_t n, int window,
+                           int w_begin, int w_end, void* d_out_jac) {
+    if (window <= 0) return fail("cpg_g1_msm_window_sums: the window width must be given (all ranks must agree)");
+    int W = (int)windows_for((uint32_t)window);
+    if (w_begin < 0 || w_end > W || w_begin >= w_end) return fail("cpg_g1_msm_window_sums: bad window range");
+    if (!n) { for (int w = w_begin; w < w_end; w++) if (int rc = cpg_g1_identity((Jac*)d_out_jac + (w - w_begin))) return rc; return 0; }
+    return msm_batched_impl(d_bases, 0, nullptr, d_scalars, 1, n, window, d_out_jac, (uint32_t)w_begin, (uint32_t)(w_end - w_begin));
+}
+/* out = sum_w 2^(c w) S_w over all W = cpg_msm_window_count windows (Horner) */
+int cpg_g1_msm_combine_windows(const void* d_wsums_jac, int window, void* d_out_jac) {
+    NEED_INIT();
+    if (window <= 0) return fail("cpg_g1_msm_combine_windows: bad window");
+    return launch(HornerJac{windows_for((uint32_t)window), (uint32_t)window, (const Jac*)d_wsums_jac, (Jac*)d_out_jac}, 1);
+}
+// wn = 0: all windows and the final Horner; wn > 0: only windows [w0, w0+wn), output = their sums (B must be 1)
 static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint32_t* d_base_off, const uint8_t* d_scalars,
-                            size_t B, size_t n, int window, void* d_out) {
+                            size_t B, size_t n, int window, void* d_out, uint32_t w0, uint32_t wn) {
     NEED_INIT();
     if (!B) return 0;
     if (n == 0) {  // empty sums are the identity (compute_MSM returns Z1 for empty input)
@@ -496,38 +540,77 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
         return 0;
     }
     if (n >= 0x7fffffffULL) return fail("cpg_g1_msm_batched: n too large");
-    uint32_t c = window > 0 ? (uint32_t)window : pick_window(n);
-    if (c < 2 || c > 20) return fail("cpg_g1_msm_batched: window must be in [2, 20]");
+    uint32_t c = window > 0 ? (uint32_t)window : (n > 2048 && B == 1 ? pick_window_large(n) : pick_window(n));
+    if (c < 2 || c > 16) return fail("cpg_g1_msm_batched: window must be in [2, 16]");
     Recode rc = make_recode(c);
+    const bool slice = wn != 0;
+    if (slice && B != 1) return fail("cpg_g1_msm_batched: window slices are for single MSMs");
     MsmShape s; s.n = (uint32_t)n; s.c = c; s.W = rc.W; s.NB = 1u << (c - 1); s.base_stride = base_stride; s.base_off = nullptr;
+    s.w0 = slice ? w0 : 0; s.wn = slice ? wn : rc.W;
+    // thousands of small MSMs: per-(msm, window) threads; few big MSMs: per-term threads with atomics
+    const bool large = n > 2048 || s.NB > 256;
+    const bool chunked_reduce = s.NB >= 4 * REDUCE_CH;
     // bound scratch to ~6 GiB per chunk of MSMs
-    size_t per_msm = (size_t)s.W * ((size_t)(s.NB + 1) * 4 + (size_t)n * 6 + (size_t)s.NB * (sizeof(Xyzz) + 2) + sizeof(Xyzz));
+    size_t per_msm = (size_t)s.wn * ((size_t)(s.NB + 1) * 4 + (size_t)n * 4 + (size_t)s.NB * (sizeof(Xyzz) + 2) + 3 * sizeof(Xyzz) * (s.NB / REDUCE_CH + 1)) + (size_t)s.W * n * 2;
     size_t chunk = (size_t)6 << 30;
     chunk = chunk / per_msm; if (chunk < 1) chunk = 1; if (chunk > B) chunk = B;
     for (size_t b0 = 0; b0 < B; b0 += chunk) {
         size_t nb = B - b0 < chunk ? B - b0 : chunk;
         s.B = (uint32_t)nb;
-        uint64_t BW = (uint64_t)nb * s.W;
+        uint64_t BW = (uint64_t)nb * s.wn;
         Scratch sc;
         uint32_t* boff = sc.get<uint32_t>(BW * (s.NB + 1));
         uint32_t* sorted = sc.get<uint32_t>(BW * n);
-        const bool balanced = s.NB <= 256;
+        const bool balanced = !large && s.NB <= 256;
         uint16_t* rank = balanced ? sc.get<uint16_t>(BW * s.NB) : nullptr;
         if (balanced && !rank) return fail("cpg_g1_msm_batched: scratch allocation failed");
         Xyzz* buckets = sc.get<Xyzz>(BW * s.NB);
         Xyzz* wsum = sc.get<Xyzz>(BW);
-        if (!boff || !sorted || !buckets || !wsum) return fail("cpg_g1_msm_batched: scratch allocation failed");
+        int16_t* dig = sc.get<int16_t>((uint64_t)nb * n * s.W);
+        if (!boff || !sorted || !buckets || !wsum || !dig) return fail("cpg_g1_msm_batched: scratch allocation failed");
         const uint32_t* ks = (const uint32_t*)d_scalars + (uint64_t)b0 * n * 8;
         const Aff* bases = (const Aff*)d_bases + (d_base_off ? 0 : (uint64_t)b0 * base_stride);
         s.base_off = d_base_off ? d_base_off + b0 : nullptr;
-        int16_t* dig = sc.get<int16_t>((uint64_t)nb * n * s.W);
-        if (!dig) return fail("cpg_g1_msm_batched: scratch allocation failed");
         if (int r = launch(RecodeDigits{s, rc, ks, dig}, (uint64_t)nb * n)) return r;
-        if (int r = launch_sort_digits(SortDigits{s, dig, boff, sorted, rank}, BW)) return r;
-        uint64_t nthreads = balanced ? (((uint64_t)nb + 31) / 32) * 32 * s.W * s.NB : BW * s.NB;
+        if (!large) {
+            if (int r = launch_sort_digits(SortDigits{s, dig, boff, sorted, rank}, BW)) return r;
+        } else {
+            uint32_t* totals = sc.get<uint32_t>(BW);
+            if (!totals) return fail("cpg_g1_msm_batched: scratch allocation failed");
+            if (int r = cpg_memset(boff, 0, BW * (s.NB + 1) * 4)) return r;
+            if (int r = launch(LargeCount{s, dig, boff}, (uint64_t)nb * n)) return r;
+            if (int r = launch(LargeScan{s, boff, totals}, BW)) return r;
+            if (int r = launch(LargeScatter{s, dig, boff, sorted}, (uint64_t)nb * n)) return r;
+            if (int r = launch(LargeFinish{s, boff, totals}, BW)) return r;
+        }
+        uint64_t nthreads = balanced ? (((uint64_t)nb + 31) / 32) * 32 * s.wn * s.NB : BW * s.NB;
         if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, rank, BW, buckets}, nthreads)) return r;
-        if (int r = launch(WindowReduce{s, buckets, wsum}, BW)) return r;
-        if (int r = launch(Horner{s, wsum, (Jac*)d_out + b0}, nb)) return r;
+        if (!chunked_reduce) {
+            if (int r = launch(WindowReduce{s, buckets, wsum}, BW)) return r;
+        } else {
+            uint64_t nch = BW * (s.NB / REDUCE_CH);
+            Xyzz* cS = sc.get<Xyzz>(nch);
+            Xyzz* cT = sc.get<Xyzz>(nch);
+            if (!cS || !cT) return fail("cpg_g1_msm_batched: scratch allocation failed");
+            if (int r = launch(WindowReduceChunks{s, buckets, cS, cT}, nch)) return r;
+            uint32_t per_w = s.NB / REDUCE_CH;
+            if (per_w >= 4 * REDUCE_CH) {                          // very wide windows: one more level
+                uint32_t nsup = per_w / REDUCE_CH;
+                Xyzz* sA = sc.get<Xyzz>(BW * nsup);
+                Xyzz* sS = sc.get<Xyzz>(BW * nsup);
+                Xyzz* sT = sc.get<Xyzz>(BW * nsup);
+                if (!sA || !sS || !sT) return fail("cpg_g1_msm_batched: scratch allocation failed");
+                if (int r = launch(WindowReduceSuper{cS, cT, sA, sS, sT}, BW * nsup)) return r;
+                if (int r = launch(WindowReduceFinal{nsup, sA, sS, sT, wsum}, BW)) return r;
+            } else {
+                if (int r = launch(WindowReduceCombine{s, cS, cT, wsum}, BW)) return r;
+            }
+        }
+        if (slice) {
+            if (int r = launch(XyzzToJac{wsum, (Jac*)d_out}, BW)) return r;
+        } else {
+            if (int r = launch(Horner{s, wsum, (Jac*)d_out + b0}, nb)) return r;
+        }
     }
     return 0;
 }

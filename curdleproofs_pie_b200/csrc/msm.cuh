@@ -46,6 +46,8 @@ CPG_HD int recode_digit(const Recode& rc, const uint32_t* kp, uint32_t w) {
 
 struct MsmShape {
     uint32_t B, n, c, W, NB;      // NB = 2^(c-1)
+    uint32_t w0, wn;              // windows [w0, w0 + wn) are processed (wn = W: all); per-(msm, window)
+                                  // arrays are indexed mw = msm*wn + (w - w0)
     uint64_t base_stride;         // bases of msm m start at m*base_stride (0 = shared by all) ...
     const uint32_t* base_off;     // ... unless this is set: bases of msm m start at base_off[m] (in points)
 };
@@ -116,7 +118,7 @@ struct SortDigits {
     uint32_t* sorted;             // [B*W][n] term index | sign<<31, grouped by bucket (out)
     uint16_t* rank;               // [B*W][NB] buckets of this window ordered by list length, longest first (out; may be null)
     CPG_HD void operator()(uint64_t t) const {
-        uint32_t m = (uint32_t)(t / s.W), w = (uint32_t)(t % s.W);
+        uint32_t m = (uint32_t)(t / s.wn), w = s.w0 + (uint32_t)(t % s.wn);
         LinView<uint32_t> off{boff + t * (uint64_t)(s.NB + 1)};
         LinView<uint16_t> rk{rank ? rank + t * (uint64_t)s.NB : nullptr};
         sort_digits_body(s, dig + (uint64_t)m * s.n * s.W + w, sorted + t * (uint64_t)s.n, off, rk, rank != nullptr);
@@ -143,15 +145,15 @@ struct BucketAccumulate {
         if (rank) {
             uint32_t lane = (uint32_t)(t % 32), r = (uint32_t)((t / 32) % s.NB);
             uint64_t q = t / (32ull * s.NB);
-            uint32_t w = (uint32_t)(q % s.W);
-            uint64_t msm = (q / s.W) * 32 + lane;
+            uint32_t w = (uint32_t)(q % s.wn);              // window index relative to w0
+            uint64_t msm = (q / s.wn) * 32 + lane;
             if (msm >= s.B) return;
-            mw = msm * s.W + w;
+            mw = msm * s.wn + w;
             b = rank[mw * s.NB + r];
         } else {
             mw = t / s.NB; b = (uint32_t)(t % s.NB);
         }
-        uint32_t m = (uint32_t)(mw / s.W);
+        uint32_t m = (uint32_t)(mw / s.wn);
         const uint32_t* off = boff + mw * (uint64_t)(s.NB + 1);
         const uint32_t* lst = sorted + mw * (uint64_t)s.n;
         const Aff* P = bases + (s.base_off ? (uint64_t)s.base_off[m] : (uint64_t)m * s.base_stride);
@@ -203,6 +205,153 @@ struct Horner {
             acc = xyzz_add(acc, ws[w]);
         }
         out[m] = xyzz_to_jac(acc);
+    }
+};
+
+// ---- large-n path (single big MSMs, n up to 2^20 and beyond) ----------------------------------
+// The per-(msm, window) serial counting sort and window reduction above are right for thousands of
+// small MSMs; for one MSM of a million terms the same stages are spread over (msm, term) threads
+// with atomics and over bucket chunks.  Bucket order inside a list depends on atomic arrival order,
+// which is harmless: the group is commutative and results leave as canonical encodings.
+#ifdef __CUDA_ARCH__
+CPG_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+#else
+CPG_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+#endif
+struct LargeCount {                // thread = (msm, term): off[mw][|d|] += 1  (off zeroed beforehand)
+    static constexpr const char* kName = "LargeCount";
+    MsmShape s; const int16_t* dig; uint32_t* boff;
+    CPG_HD void operator()(uint64_t t) const {
+        uint64_t m = t / s.n;
+        const int16_t* dg = dig + t * (uint64_t)s.W;
+        for (uint32_t k = 0; k < s.wn; k++) {
+            int d = dg[s.w0 + k];
+            if (d) atomic_add_u32(boff + (m * s.wn + k) * (uint64_t)(s.NB + 1) + (uint32_t)(d < 0 ? -d : d), 1u);
+        }
+    }
+};
+struct LargeScan {                 // thread = (msm, window): off[a] = END of bucket a-1; totals[mw] = list length
+    static constexpr const char* kName = "LargeScan";
+    MsmShape s; uint32_t* boff; uint32_t* totals;
+    CPG_HD void operator()(uint64_t t) const {
+        uint32_t* off = boff + t * (uint64_t)(s.NB + 1);
+        uint32_t run = 0;
+        for (uint32_t b = 1; b <= s.NB; b++) { run += off[b]; off[b] = run; }
+        totals[t] = run;
+    }
+};
+struct LargeScatter {              // thread = (msm, term): claim a slot from the END of its bucket
+    static constexpr const char* kName = "LargeScatter";
+    MsmShape s; const int16_t* dig; uint32_t* boff; uint32_t* sorted;
+    CPG_HD void operator()(uint64_t t) const {
+        uint64_t m = t / s.n; uint32_t i = (uint32_t)(t % s.n);
+        const int16_t* dg = dig + t * (uint64_t)s.W;
+        for (uint32_t k = 0; k < s.wn; k++) {
+            int d = dg[s.w0 + k];
+            if (!d) continue;
+            uint64_t mw = m * s.wn + k;
+            uint32_t a = (uint32_t)(d < 0 ? -d : d);
+            uint32_t pos = atomic_add_u32(boff + mw * (uint64_t)(s.NB + 1) + a, 0xffffffffu) - 1;   // fetch-and-decrement
+            sorted[mw * (uint64_t)s.n + pos] = i | (d < 0 ? 0x80000000u : 0u);
+        }
+    }
+};
+struct LargeFinish {               // thread = (msm, window): cursors are now bucket STARTS shifted by one
+    static constexpr const char* kName = "LargeFinish";
+    MsmShape s; uint32_t* boff; const uint32_t* totals;
+    CPG_HD void operator()(uint64_t t) const {
+        uint32_t* off = boff + t * (uint64_t)(s.NB + 1);
+        for (uint32_t b = 0; b < s.NB; b++) off[b] = off[b + 1];
+        off[s.NB] = totals[t];
+    }
+};
+// window reduction in chunks of CH buckets: S_c = sum_{b in chunk} (b - b0 + 1) B_b and T_c = sum B_b,
+// then  sum_b (b+1) B_b = sum_c S_c + CH * sum_c c T_c  (second-level running sum, CH a power of two)
+constexpr uint32_t REDUCE_CH = 64;
+struct WindowReduceChunks {        // thread = (msm, window, chunk)
+    static constexpr const char* kName = "WindowReduceChunks";
+    MsmShape s; const Xyzz* buckets; Xyzz* chunk_S; Xyzz* chunk_T;
+    CPG_HD void operator()(uint64_t t) const {
+        const Xyzz* bk = buckets + t * (uint64_t)REDUCE_CH;      // chunks tile the [mw][NB] array exactly
+        Xyzz run = xyzz_inf(), tot = xyzz_inf();
+        for (uint32_t b = REDUCE_CH; b-- > 0;) {
+            run = xyzz_add(run, bk[b]);
+            tot = xyzz_add(tot, run);
+        }
+        chunk_S[t] = tot; chunk_T[t] = run;
+    }
+};
+struct WindowReduceCombine {       // thread = (msm, window)
+    static constexpr const char* kName = "WindowReduceCombine";
+    MsmShape s; const Xyzz* chunk_S; const Xyzz* chunk_T; Xyzz* wsum;
+    CPG_HD void operator()(uint64_t t) const {
+        uint32_t nch = s.NB / REDUCE_CH;
+        const Xyzz* S = chunk_S + t * (uint64_t)nch;
+        const Xyzz* T = chunk_T + t * (uint64_t)nch;
+        Xyzz run = xyzz_inf(), acc = xyzz_inf(), sum = S[0];
+        for (uint32_t c = nch; c-- > 1;) {
+            run = xyzz_add(run, T[c]);
+            acc = xyzz_add(acc, run);                              // acc = sum_{c>=1} c T_c
+            sum = xyzz_add(sum, S[c]);
+        }
+        for (uint32_t k = REDUCE_CH; k > 1; k >>= 1) acc = xyzz_dbl(acc);
+        wsum[t] = xyzz_add(sum, acc);
+    }
+};
+// three-level variant for very wide windows (NB/REDUCE_CH > 4*REDUCE_CH chunks): super-chunks of CH chunks
+//   A_C = sum S_c,  S'_C = sum (c - c0) T_c,  T'_C = sum T_c      (thread = (msm, window, super-chunk))
+//   total = sum_C A_C + CH * ( sum_C S'_C + CH * sum_C C T'_C )    (thread = (msm, window))
+struct WindowReduceSuper {
+    static constexpr const char* kName = "WindowReduceSuper";
+    const Xyzz* chunk_S; const Xyzz* chunk_T; Xyzz* sup_A; Xyzz* sup_S; Xyzz* sup_T;
+    CPG_HD void operator()(uint64_t t) const {
+        const Xyzz* S = chunk_S + t * (uint64_t)REDUCE_CH;
+        const Xyzz* T = chunk_T + t * (uint64_t)REDUCE_CH;
+        Xyzz run = xyzz_inf(), acc = xyzz_inf(), sum = S[0];
+        for (uint32_t c = REDUCE_CH; c-- > 1;) {
+            run = xyzz_add(run, T[c]);
+            acc = xyzz_add(acc, run);
+            sum = xyzz_add(sum, S[c]);
+        }
+        sup_A[t] = sum; sup_S[t] = acc; sup_T[t] = xyzz_add(run, T[0]);
+    }
+};
+struct WindowReduceFinal {
+    static constexpr const char* kName = "WindowReduceFinal";
+    uint32_t nsup; const Xyzz* sup_A; const Xyzz* sup_S; const Xyzz* sup_T; Xyzz* wsum;
+    CPG_HD void operator()(uint64_t t) const {
+        const Xyzz* A = sup_A + t * (uint64_t)nsup;
+        const Xyzz* S = sup_S + t * (uint64_t)nsup;
+        const Xyzz* T = sup_T + t * (uint64_t)nsup;
+        Xyzz run = xyzz_inf(), acc = xyzz_inf(), sumA = A[0], sumS = S[0];
+        for (uint32_t c = nsup; c-- > 1;) {
+            run = xyzz_add(run, T[c]);
+            acc = xyzz_add(acc, run);                              // sum_{C>=1} C T'_C
+            sumA = xyzz_add(sumA, A[c]);
+            sumS = xyzz_add(sumS, S[c]);
+        }
+        for (uint32_t k = REDUCE_CH; k > 1; k >>= 1) acc = xyzz_dbl(acc);
+        acc = xyzz_add(acc, sumS);
+        for (uint32_t k = REDUCE_CH; k > 1; k >>= 1) acc = xyzz_dbl(acc);
+        wsum[t] = xyzz_add(sumA, acc);
+    }
+};
+struct XyzzToJac {
+    static constexpr const char* kName = "XyzzToJac";
+    const Xyzz* in; Jac* out;
+    CPG_HD void operator()(uint64_t t) const { out[t] = xyzz_to_jac(in[t]); }
+};
+struct HornerJac {                 // thread = msm: combine W Jacobian window sums (window-split MSMs)
+    static constexpr const char* kName = "HornerJac";
+    uint32_t W, c; const Jac* wsum; Jac* out;
+    CPG_HD void operator()(uint64_t m) const {
+        const Jac* ws = wsum + m * (uint64_t)W;
+        Jac acc = ws[W - 1];
+        for (uint32_t w = W - 1; w-- > 0;) {
+            for (uint32_t j = 0; j < c; j++) acc = jac_dbl(acc);
+            acc = jac_add(acc, ws[w]);
+        }
+        out[m] = acc;
     }
 };
 

@@ -100,6 +100,15 @@ int cpg_g1_msm_batched(const void* d_bases_aff, size_t base_stride, const uint8_
  * d_bases_aff[d_base_off[b] ...] - lets MSMs over different sub-vectors share one call */
 int cpg_g1_msm_batched_off(const void* d_bases_aff, const uint32_t* d_base_off, const uint8_t* d_scalars,
                            size_t B, size_t n, int window, void* d_out_jac);
+/* Window split of ONE large MSM (BASELINE configs 2 and 5): the W = cpg_msm_window_count
+ * windows are independent; a rank computes the Jacobian window sums S_w of its slice, the slices are
+ * exchanged by one small all-gather (W * 144 B in total), and every rank finishes with
+ * sum_w 2^(c w) S_w.  `window` must be the same on every rank (cpg_msm_pick_window(n)). */
+int cpg_msm_pick_window(size_t n);
+int cpg_msm_window_count(size_t n, int window);
+int cpg_g1_msm_window_sums(const void* d_bases_aff, const uint8_t* d_scalars, size_t n, int window,
+                           int w_begin, int w_end, void* d_out_jac);
+int cpg_g1_msm_combine_windows(const void* d_wsums_jac, int window, void* d_out_jac);
 /* fixed-base tables for generators shared by every proof (the CRS, cp/crs.py:19-36):
  * T[i][w][d] = (d+1) 2^(c w) G_i.  Returns NULL on failure. */
 void* cpg_fixed_table_create(const void* d_bases_aff, size_t nb, int window);

@@ -167,3 +167,36 @@ def case_fr(lib, k, seed=6):
     assert ints(lib.fr_op("sub", da, db, k)) == [(x - y) % R for x, y in zip(a, b)]
     assert ints(lib.fr_op("mul", da, db, k)) == [x * y % R for x, y in zip(a, b)]
     assert ints(lib.fr_op("inverse", da, None, k)) == [pow(x, -1, R) if x else 0 for x in a]
+
+
+def case_msm_large(lib, cref, n, window, seed=8, slices=3):
+    """One large MSM through the per-term (atomic) sort and the chunked window reduction, then the same
+    value recomputed from window slices (the multi-GPU split) - all equal to the oracle."""
+    rng = random.Random(seed * 77 + n)
+    nuniq = min(n, 64)                                   # few distinct points, many terms: keeps the oracle fast
+    ublobs, uenc = rand_points(cref, rng, nuniq, with_identity=True)
+    idx = [rng.randrange(nuniq) for _ in range(n)]
+    enc = [uenc[i] for i in idx]
+    ks = [rng.randrange(R) for _ in range(n)]
+    ks[0] = 0; ks[1] = R - 1
+    aff, _ = upload_points(lib, enc)
+    dk = lib.upload(rt.scalars_to_bytes(ks))
+    # oracle: group the scalars per distinct base first (same value, far fewer scalar-muls)
+    agg = [0] * nuniq
+    for i, k in zip(idx, ks):
+        agg[i] = (agg[i] + k) % R
+    want = cref.compress(cref.msm(ublobs, agg))
+    out = lib.msm_batched(aff, 0, dk, 1, n, window)
+    assert split48(lib.compress_jac(out, 1)) == [want]
+    c = window or int(lib.c.cpg_msm_pick_window(n))
+    W = int(lib.c.cpg_msm_window_count(n, c))
+    wsums = lib.alloc(W * rt.JAC)
+    bounds = [W * i // slices for i in range(slices + 1)]
+    for lo, hi in zip(bounds, bounds[1:]):
+        if hi > lo:
+            part = lib.alloc((hi - lo) * rt.JAC)
+            lib.check(lib.c.cpg_g1_msm_window_sums(aff.ptr, dk.ptr, n, c, lo, hi, part.ptr), "cpg_g1_msm_window_sums")
+            lib.check(lib.c.cpg_d2d(wsums.ptr + lo * rt.JAC, part.ptr, (hi - lo) * rt.JAC))
+    res = lib.alloc(rt.JAC)
+    lib.check(lib.c.cpg_g1_msm_combine_windows(wsums.ptr, c, res.ptr), "cpg_g1_msm_combine_windows")
+    assert split48(lib.compress_jac(res, 1)) == [want]

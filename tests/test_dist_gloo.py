@@ -63,3 +63,54 @@ def test_shard_range_properties():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _msm_worker(rank, world, port, n, q):
+    """Window-split large MSM: each rank computes its slice of Pippenger windows on the host-emulated
+    kernels, one gloo all-gather exchanges the window sums, every rank combines."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import random
+
+    import torch.distributed as dist
+
+    import conftest
+    import parity_cases as pc
+    from curdleproofs_pie_b200 import msm, runtime
+    from oracle import cref_binding
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = runtime.CpgLib(conftest.SEAM_SO, 0)
+    cref = cref_binding.load()
+    rng = random.Random(31)                       # same inputs on every rank
+    blobs, enc = pc.rand_points(cref, rng, 16)
+    idx = [rng.randrange(16) for _ in range(n)]
+    ks = [rng.randrange(pc.R) for _ in range(n)]
+    aff, _ = pc.upload_points(lib, [enc[i] for i in idx])
+    dk = lib.upload(runtime.scalars_to_bytes(ks))
+    out = msm.msm_large(lib, aff, dk, n, window=6, dist=dist)
+    got = lib.compress_jac(out, 1)
+    agg = [0] * 16
+    for i, k in zip(idx, ks):
+        agg[i] = (agg[i] + k) % pc.R
+    want = cref.compress(cref.msm(blobs, agg))
+    dist.barrier()
+    q.put((rank, got == want))
+    dist.destroy_process_group()
+
+
+def test_two_rank_window_split_msm(seam_lib):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_msm_worker, args=(r, 2, port, 200, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]

@@ -149,3 +149,8 @@ def test_prove_batch_bytes_equal_reference(gpu_lib, name, copies):
 
 def test_prove_then_verify_full_size(gpu_lib):
     prc.check_prove_then_verify(gpu_lib, "shuffle_N128_seed4096.json", B=96)
+
+
+@pytest.mark.parametrize("n,window", [(5000, 0), (3000, 10), (1 << 16, 13), (100000, 0)])
+def test_msm_large_and_window_slices(gpu_lib, cref, n, window):
+    pc.case_msm_large(gpu_lib, cref, n, window)

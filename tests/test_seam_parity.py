@@ -39,3 +39,8 @@ def test_fixed_base(seam_lib, cref):
 
 def test_fr(seam_lib):
     pc.case_fr(seam_lib, 16)
+
+
+@pytest.mark.parametrize("n,window", [(2100, 5), (300, 10), (2500, 9), (600, 16), (3000, 0)])
+def test_msm_large_and_window_slices(seam_lib, cref, n, window):
+    pc.case_msm_large(seam_lib, cref, n, window)
