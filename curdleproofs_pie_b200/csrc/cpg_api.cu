@@ -684,12 +684,14 @@ namespace {
 // version of this probe measured the ALU pipe that way).  SASS: one IMAD.WIDE.U32 per step.
 #define CPG_WIDE_DEP(lo, hi, a) asm volatile("{ .reg .u32 t; mov.u32 t, %0; mad.lo.cc.u32 %0, %2, t, %0; madc.hi.u32 %1, %2, t, %1; }" : "+r"(lo), "+r"(hi) : "r"(a))
 __global__ void __launch_bounds__(256) k_imad_wide(uint64_t iters, uint32_t a0, uint32_t b0, uint64_t* sink) {
-    uint32_t a[8], lo[8], hi[8];
+    // one fixed multiplier register, data-dependent multiplicand: the highest sustained rate of the
+    // probe family in profiles/r01_imad_probe.txt (9.16 TMAC/s; distinct multipliers per chain: 8.5)
+    uint32_t a = a0 + threadIdx.x, lo[8], hi[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { lo[j] = j + threadIdx.x + b0; hi[j] = j + blockIdx.x; a[j] = a0 * (j + 1) + threadIdx.x; }
+    for (int j = 0; j < 8; j++) { lo[j] = j + threadIdx.x + b0; hi[j] = j + blockIdx.x; }
     for (uint64_t i = 0; i < iters; i++) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) CPG_WIDE_DEP(lo[j], hi[j], a[j]);
+        for (int j = 0; j < 8; j++) CPG_WIDE_DEP(lo[j], hi[j], a);
     }
     uint32_t s = 0;
 #pragma unroll
