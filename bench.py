@@ -195,7 +195,6 @@ def run_ours_verify(args, rank, world, dist):
         step_dev()
     barrier()
     sampler = ClockSampler(lib.device) if rank == 0 else None
-    lib.profile(True)
     launches0 = lib.launch_count()
     barrier()
     lib.timer_start()
@@ -204,8 +203,17 @@ def run_ours_verify(args, rank, world, dist):
     ms = lib.timer_stop()
     barrier()
     launches = lib.launch_count() - launches0
+    # per-kernel device times for the roofline: a separate pass on ONE stream with an event pair around
+    # every launch (with several sub-batch streams the kernels overlap and per-kernel times are meaningless)
+    ver.set_streams(1)
+    step_dev()
+    lib.sync()
+    lib.profile(True)
+    for _ in range(args.steps):
+        step_dev()
     prof = lib.profile_report()
     lib.profile(False)
+    ver.set_streams(args.streams)
     # verdicts of the replayed device pass (no host-side rejects in a replay: all lanes decode)
     lib.check(lib.c.cpg_verify_replay_device(ver.handle, out))
     assert out.raw[:B] == expected, "device replay verdicts differ"
@@ -832,7 +840,7 @@ def main():
     ap.add_argument("--terms", dest="n", type=int, default=128, help="terms per MSM (msm workloads)")
     ap.add_argument("--window", type=int, default=0, help="bucket window width (0 = from the work model)")
     ap.add_argument("--transcript", default="device", choices=["device", "host"], help="where the Fiat-Shamir transcript + coefficient algebra run")
-    ap.add_argument("--streams", type=int, default=1, help="sub-batches in flight on separate CUDA streams")
+    ap.add_argument("--streams", type=int, default=2, help="sub-batches in flight on separate CUDA streams")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads for the transcript (0 = all cores)")
     ap.add_argument("--cpu-sample", type=int, default=400, help="MSMs in the bounded CPU sample (msm workload)")
     ap.add_argument("--cpu-sample-verify", type=int, default=24, help="verifications in the bounded CPU sample")

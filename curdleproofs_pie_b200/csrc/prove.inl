@@ -56,7 +56,7 @@ struct PBuffers {
     const uint8_t* rand;          // [B][NR][32]     m_bl(4) a_bl(2) c_bl(4) ipa_r(n) ipa_z(n-2) r_t r_u r_a r_b r_k msm_r(n)
     const uint8_t* crs48;         // CRS wire bytes
     PState* st;                   // [B]
-    HFr* vec;                     // [B][PV_COUNT][n]
+    HFr* vec;                     // [PV_COUNT][n][B]  (batch-innermost, see FrVec)
     uint8_t* outs48;              // [B][NOUT][48]   compressed outputs, by output id
     uint8_t* fs;                  // [P_MAX_OUT][B][NF][32]  fixed-base coefficient rows of the round being prepared (output-major)
     uint8_t* vs;                  // [P_MAX_VAR][B][ell][32] variable-base coefficient rows
@@ -64,7 +64,14 @@ struct PBuffers {
     uint64_t B;
 };
 
-CPG_HD HFr* pvec(const PShape& sh, const PBuffers& pb, size_t b, int which) { return pb.vec + (b * PV_COUNT + (size_t)which) * sh.n; }
+// A per-proof Fr vector.  Storage is batch-innermost, vec[which][i][b]: the 32 lanes of a warp (32
+// consecutive proofs) touch 32 consecutive elements, instead of 32 rows that lie 13*n*32 bytes apart.
+struct FrVec {
+    HFr* p; uint64_t stride;
+    CPG_HD HFr& operator[](uint32_t i) const { return p[(uint64_t)i * stride]; }
+    CPG_HD FrVec operator+(uint32_t k) const { return FrVec{p + (uint64_t)k * stride, stride}; }
+};
+CPG_HD FrVec pvec(const PShape& sh, const PBuffers& pb, size_t b, int which) { return FrVec{pb.vec + (size_t)which * sh.n * pb.B + b, pb.B}; }
 CPG_HD uint8_t* frow(const PShape& sh, const PBuffers& pb, size_t b, uint32_t o) { return pb.fs + ((size_t)o * pb.B + b) * (size_t)sh.NF * 32; }
 CPG_HD uint8_t* vrow(const PShape& sh, const PBuffers& pb, size_t b, uint32_t o) { return pb.vs + ((size_t)o * pb.B + b) * (size_t)sh.ell * 32; }
 CPG_HD HFr prand(const PBuffers& pb, const PShape& sh, size_t b, uint32_t i) {
@@ -74,7 +81,7 @@ CPG_HD void zero_rows(const PShape& sh, const PBuffers& pb, size_t b, uint32_t n
     for (uint32_t o = 0; o < nfix; o++) memset(frow(sh, pb, b, o), 0, (size_t)sh.NF * 32);
     for (uint32_t o = 0; o < nvar; o++) memset(vrow(sh, pb, b, o), 0, (size_t)sh.ell * 32);
 }
-CPG_HD HFr ip(const HFr* a, const HFr* b, uint32_t n) {
+CPG_HD HFr ip(const FrVec& a, const FrVec& b, uint32_t n) {
     HFr acc = cpgh::fr_zero();
     for (uint32_t i = 0; i < n; i++) acc = cpgh::fr_add(acc, cpgh::fr_mul(a[i], b[i]));
     return acc;
@@ -94,19 +101,19 @@ CPG_HD void prove_step(const PShape& sh, const POut& O, const PBuffers& pb, uint
     const PRand RO(n);
     PState& s = pb.st[b];
     const uint8_t* outs = pb.outs48 + b * (size_t)O.NOUT * 48;
-    HFr* a = pvec(sh, pb, b, PV_A);
-    HFr* aperm = pvec(sh, pb, b, PV_APERM);
-    HFr* fact = pvec(sh, pb, b, PV_FACT);
-    HFr* c = pvec(sh, pb, b, PV_C);
-    HFr* d = pvec(sh, pb, b, PV_D);
-    HFr* x = pvec(sh, pb, b, PV_X);
-    HFr* wG = pvec(sh, pb, b, PV_WG);
-    HFr* wGp = pvec(sh, pb, b, PV_WGP);
-    HFr* w2 = pvec(sh, pb, b, PV_W2);
-    HFr* Acoef = pvec(sh, pb, b, PV_ACOEF);
-    HFr* Mcoef = pvec(sh, pb, b, PV_MCOEF);
-    HFr* Bcoef = pvec(sh, pb, b, PV_BCOEF);
-    HFr* uvec = pvec(sh, pb, b, PV_U);
+    FrVec a = pvec(sh, pb, b, PV_A);
+    FrVec aperm = pvec(sh, pb, b, PV_APERM);
+    FrVec fact = pvec(sh, pb, b, PV_FACT);
+    FrVec c = pvec(sh, pb, b, PV_C);
+    FrVec d = pvec(sh, pb, b, PV_D);
+    FrVec x = pvec(sh, pb, b, PV_X);
+    FrVec wG = pvec(sh, pb, b, PV_WG);
+    FrVec wGp = pvec(sh, pb, b, PV_WGP);
+    FrVec w2 = pvec(sh, pb, b, PV_W2);
+    FrVec Acoef = pvec(sh, pb, b, PV_ACOEF);
+    FrVec Mcoef = pvec(sh, pb, b, PV_MCOEF);
+    FrVec Bcoef = pvec(sh, pb, b, PV_BCOEF);
+    FrVec uvec = pvec(sh, pb, b, PV_U);
     const uint32_t* perm = pb.perm + b * (size_t)ell;
     Transcript tr;
     if (round > 0) tr = s.tr;
@@ -198,7 +205,7 @@ CPG_HD void prove_step(const PShape& sh, const POut& O, const PBuffers& pb, uint
         for (uint32_t i = 0; i < 4; i++) { d[ell + i] = fr_mul(beta_l1, d[ell + i]); uvec[ell + i] = ui; }   // ui = beta^-(ell+1)
         s.z = fr_sub(fr_add(fr_mul(s.r_p, beta_l1), fr_mul(s.gprod, beta_l)), fr_one());
         // IPA blinders (ipa.py:27-48): r in x (scratch), z in w2 (scratch)
-        HFr* r = x; HFr* zz = w2;
+        FrVec r = x, zz = w2;
         for (uint32_t i = 0; i < n; i++) r[i] = prand(pb, sh, b, RO.ipa_r + i);
         for (uint32_t i = 0; i + 2 < n; i++) zz[i] = prand(pb, sh, b, RO.ipa_z + i);
         HFr omega = fr_add(ip(r, d, n), ip(zz, c, n - 2));

@@ -352,7 +352,7 @@ struct Verifier {
 #else
     void* streams[8] = {};
 #endif
-    int nstreams = 1;
+    int nstreams = 2;
 #ifndef CPG_HOST_EMU
     cudaStream_t side_stream = nullptr;
     cudaEvent_t side_ev[2] = {};

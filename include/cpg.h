@@ -141,7 +141,7 @@ int cpg_verifier_set_window(void* verifier, int var_window);
 /* where the Fiat-Shamir transcript + coefficient algebra run: 1 = one proof per GPU thread (default;
  * only wire bytes cross PCIe), 0 = on `host_threads` host threads (the reference's placement) */
 int cpg_verifier_set_transcript(void* verifier, int on_device);
-/* sub-batches in flight on separate CUDA streams (1..8, default 1; device transcript only) */
+/* sub-batches in flight on separate CUDA streams (1..8, default 2; device transcript only) */
 int cpg_verifier_set_streams(void* verifier, int nstreams);
 int cpg_verify_batch(void* verifier, const uint8_t* inputs, const uint8_t* proofs, size_t B, uint8_t* verdicts);
 /* re-run the device side (decompress, D/A', MSM, test) of the last batch on its resident inputs */
