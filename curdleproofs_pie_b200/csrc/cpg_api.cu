@@ -10,6 +10,7 @@
 #include "msm.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <mutex>
 #include <stdio.h>
@@ -29,6 +30,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 int g_device = -1;
+int g_msm_path = 0;          // cpg_msm_force_path: 0 = by shape, 1 = per-(msm, window) threads, 2 = per-term threads
 std::mutex g_init_mu;
 Jac* g_generator = nullptr;  // device copy of the generator (Jacobian)
 
@@ -174,22 +176,35 @@ uint32_t pick_window(size_t n) {
     return bc;
 }
 
-// Single big MSMs are launched with few (msm, window) pairs, so besides the total work the longest
-// SERIAL chain matters: a bucket list is walked by one thread, and a window whose digit has only tw bits
+// chunk width of the level-wise window reduction (ReduceLevel); CPG_REDUCE_CH overrides it for tuning
+uint32_t reduce_ch() {
+    static uint32_t ch = [] {
+        const char* e = getenv("CPG_REDUCE_CH");
+        uint32_t v = e ? (uint32_t)atoi(e) : 4;
+        return (v == 2 || v == 4 || v == 8 || v == 16) ? v : 4u;
+    }();
+    return ch;
+}
+
+// Single MSMs are launched with few (msm, window) pairs, so besides the total work the longest SERIAL
+// chain matters: a bucket list is walked by one thread, and a window whose digit has only tw bits
 // (the top window holds 255 - c(W-1) bits) concentrates n terms in 2^tw lists.  Estimated time =
-// total products / pipe rate + serial products * single-thread latency.
+// total products / pipe rate + serial products * single-thread product latency (0.9 us measured).
 uint32_t pick_window_large(size_t n) {
     double best = 1e300; uint32_t bc = 8;
-    for (uint32_t c = 6; c <= 16; c++) {
+    const double ch = reduce_ch();
+    for (uint32_t c = 4; c <= 16; c++) {
         double W = windows_for(c), NB = (double)(1u << (c - 1));
         int tw = 255 - (int)c * ((int)W - 1);
-        double top_lists = tw <= 0 ? 2.0 : (double)(1u << tw);
+        double top_lists = tw <= 0 ? 1.0 : (double)(1u << tw);
         if (top_lists > NB) top_lists = NB;
-        double longest = std::max((double)n / top_lists, (double)n / NB);
-        double nch = NB / REDUCE_CH;
-        double serial = longest * 10.0 + (NB >= 4 * REDUCE_CH ? (nch >= 4 * REDUCE_CH ? 3.0 * REDUCE_CH + 3.0 * nch / REDUCE_CH : 3.0 * nch) * 14.0 : 2.0 * NB * 14.0);
-        double total = (double)n * W * 10.0 + W * NB * 2.0 * 14.0;
-        double t = total / 3.0e10 + serial * 1.5e-6;
+        double lam = (double)n / NB, lam_top = (double)n / top_lists / (tw <= 0 ? 2.0 : 1.0);
+        double longest = std::max(lam + 4.0 * std::sqrt(lam) + 4.0, lam_top + 4.0 * std::sqrt(lam_top));
+        if (longest > (double)n) longest = (double)n;
+        double levels = std::ceil((c - 1) / std::log2(ch));
+        double serial = longest * 10.0 + levels * (2.0 * ch - 3.0) * 14.0 + levels * 14.0 + (c - 1) * 9.0;
+        double total = (double)n * W * 10.0 + W * NB * 3.0 * 14.0;
+        double t = total / 2.7e10 + serial * 0.9e-6;
         if (t < best) { best = t; bc = c; }
     }
     return bc;
@@ -510,10 +525,16 @@ int cpg_g1_msm_batched_off(const void* d_bases, const uint32_t* d_base_off, cons
     return msm_batched_impl(d_bases, 0, d_base_off, d_scalars, B, n, window, d_out);
 }
 int cpg_msm_window_count(size_t n, int window) {
-    uint32_t c = window > 0 ? (uint32_t)window : (n > 2048 ? pick_window_large(n) : pick_window(n ? n : 1));
+    uint32_t c = window > 0 ? (uint32_t)window : pick_window_large(n ? n : 1);
     return (int)windows_for(c);
 }
-int cpg_msm_pick_window(size_t n) { return (int)(n > 2048 ? pick_window_large(n) : pick_window(n ? n : 1)); }
+int cpg_msm_force_path(int path) {
+    if (path < 0 || path > 2) return fail("cpg_msm_force_path: 0 (by shape), 1 (per-window threads) or 2 (per-term threads)");
+    g_msm_path = path;
+    return 0;
+}
+/* window width this library uses for ONE n-term MSM (a function of n only, so all ranks agree) */
+int cpg_msm_pick_window(size_t n) { return (int)pick_window_large(n ? n : 1); }
 /* window sums S_w, w in [w_begin, w_end), of ONE n-term MSM as Jacobian points (the unit of the
  * multi-GPU window split: every rank computes a slice, the slices are all-gathered, then combined) */
 int cpg_g1_msm_window_sums(const void* d_bases, const uint8_t* d_scalars, size_t n, int window,
@@ -540,76 +561,97 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
         return 0;
     }
     if (n >= 0x7fffffffULL) return fail("cpg_g1_msm_batched: n too large");
-    uint32_t c = window > 0 ? (uint32_t)window : (n > 2048 && B == 1 ? pick_window_large(n) : pick_window(n));
+    // thousands of small MSMs: per-(msm, window) threads; few (or big) MSMs: per-term threads with atomics,
+    // buckets ordered by list length, level-wise window reduction
+    const bool few = g_msm_path == 0 ? B * 32 < 8192 : g_msm_path == 2;
+    uint32_t c = window > 0 ? (uint32_t)window : (few ? pick_window_large(n) : pick_window(n));
     if (c < 2 || c > 16) return fail("cpg_g1_msm_batched: window must be in [2, 16]");
     Recode rc = make_recode(c);
     const bool slice = wn != 0;
     if (slice && B != 1) return fail("cpg_g1_msm_batched: window slices are for single MSMs");
     MsmShape s; s.n = (uint32_t)n; s.c = c; s.W = rc.W; s.NB = 1u << (c - 1); s.base_stride = base_stride; s.base_off = nullptr;
     s.w0 = slice ? w0 : 0; s.wn = slice ? wn : rc.W;
-    // thousands of small MSMs: per-(msm, window) threads; few big MSMs: per-term threads with atomics
-    const bool large = n > 2048 || s.NB > 256;
-    const bool chunked_reduce = s.NB >= 4 * REDUCE_CH;
+    const bool large = few || n > 2048 || s.NB > 256;
+    if (g_msm_path == 1 && large) return fail("cpg_g1_msm_batched: the per-window path handles n <= 2048 and windows <= 9 bits");
+    // reduction levels: NB = prod ch_j
+    uint32_t nlev = 0; uint8_t lg_ch[16]; uint32_t chs[16];
+    size_t lvl_elems = 0;                                          // largest level output, in points per (msm, window)
+    if (large) {
+        for (uint32_t len = s.NB; len > 1;) {
+            uint32_t ch = reduce_ch(); while (ch > len) ch >>= 1;
+            chs[nlev] = ch; uint8_t lg = 0; while ((1u << lg) < ch) lg++; lg_ch[nlev] = lg;
+            len /= ch; nlev++;
+            lvl_elems = std::max(lvl_elems, (size_t)(nlev + 1) * len);
+        }
+    }
     // bound scratch to ~6 GiB per chunk of MSMs
-    size_t per_msm = (size_t)s.wn * ((size_t)(s.NB + 1) * 4 + (size_t)n * 4 + (size_t)s.NB * (sizeof(Xyzz) + 2) + 3 * sizeof(Xyzz) * (s.NB / REDUCE_CH + 1)) + (size_t)s.W * n * 2;
+    size_t per_msm = (size_t)s.wn * ((size_t)(s.NB + 1) * 8 + (size_t)n * 4 + (size_t)s.NB * (sizeof(Xyzz) + 6) + 2 * sizeof(Xyzz) * (lvl_elems + 1)) + (size_t)s.W * n * 2;
     size_t chunk = (size_t)6 << 30;
     chunk = chunk / per_msm; if (chunk < 1) chunk = 1; if (chunk > B) chunk = B;
+    if (large) while (chunk > 1 && (uint64_t)chunk * s.wn * s.NB >= 0xffffffffULL) chunk /= 2;
     for (size_t b0 = 0; b0 < B; b0 += chunk) {
         size_t nb = B - b0 < chunk ? B - b0 : chunk;
         s.B = (uint32_t)nb;
         uint64_t BW = (uint64_t)nb * s.wn;
+        if (large && BW * s.NB >= 0xffffffffULL) return fail("cpg_g1_msm_batched: window too wide for this many windows");
         Scratch sc;
         uint32_t* boff = sc.get<uint32_t>(BW * (s.NB + 1));
         uint32_t* sorted = sc.get<uint32_t>(BW * n);
-        const bool balanced = !large && s.NB <= 256;
+        const bool balanced = !large;
         uint16_t* rank = balanced ? sc.get<uint16_t>(BW * s.NB) : nullptr;
         if (balanced && !rank) return fail("cpg_g1_msm_batched: scratch allocation failed");
         Xyzz* buckets = sc.get<Xyzz>(BW * s.NB);
-        Xyzz* wsum = sc.get<Xyzz>(BW);
         int16_t* dig = sc.get<int16_t>((uint64_t)nb * n * s.W);
-        if (!boff || !sorted || !buckets || !wsum || !dig) return fail("cpg_g1_msm_batched: scratch allocation failed");
+        if (!boff || !sorted || !buckets || !dig) return fail("cpg_g1_msm_batched: scratch allocation failed");
         const uint32_t* ks = (const uint32_t*)d_scalars + (uint64_t)b0 * n * 8;
         const Aff* bases = (const Aff*)d_bases + (d_base_off ? 0 : (uint64_t)b0 * base_stride);
         s.base_off = d_base_off ? d_base_off + b0 : nullptr;
         if (int r = launch(RecodeDigits{s, rc, ks, dig}, (uint64_t)nb * n)) return r;
         if (!large) {
+            Xyzz* wsum = sc.get<Xyzz>(BW);
+            if (!wsum) return fail("cpg_g1_msm_batched: scratch allocation failed");
             if (int r = launch_sort_digits(SortDigits{s, dig, boff, sorted, rank}, BW)) return r;
-        } else {
-            uint32_t* totals = sc.get<uint32_t>(BW);
-            if (!totals) return fail("cpg_g1_msm_batched: scratch allocation failed");
-            if (int r = cpg_memset(boff, 0, BW * (s.NB + 1) * 4)) return r;
-            if (int r = launch(LargeCount{s, dig, boff}, (uint64_t)nb * n)) return r;
-            if (int r = launch(LargeScan{s, boff, totals}, BW)) return r;
-            if (int r = launch(LargeScatter{s, dig, boff, sorted}, (uint64_t)nb * n)) return r;
-            if (int r = launch(LargeFinish{s, boff, totals}, BW)) return r;
-        }
-        uint64_t nthreads = balanced ? (((uint64_t)nb + 31) / 32) * 32 * s.wn * s.NB : BW * s.NB;
-        if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, rank, BW, buckets}, nthreads)) return r;
-        if (!chunked_reduce) {
+            uint64_t nthreads = (((uint64_t)nb + 31) / 32) * 32 * s.wn * s.NB;
+            if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, rank, nullptr, BW, buckets}, nthreads)) return r;
             if (int r = launch(WindowReduce{s, buckets, wsum}, BW)) return r;
-        } else {
-            uint64_t nch = BW * (s.NB / REDUCE_CH);
-            Xyzz* cS = sc.get<Xyzz>(nch);
-            Xyzz* cT = sc.get<Xyzz>(nch);
-            if (!cS || !cT) return fail("cpg_g1_msm_batched: scratch allocation failed");
-            if (int r = launch(WindowReduceChunks{s, buckets, cS, cT}, nch)) return r;
-            uint32_t per_w = s.NB / REDUCE_CH;
-            if (per_w >= 4 * REDUCE_CH) {                          // very wide windows: one more level
-                uint32_t nsup = per_w / REDUCE_CH;
-                Xyzz* sA = sc.get<Xyzz>(BW * nsup);
-                Xyzz* sS = sc.get<Xyzz>(BW * nsup);
-                Xyzz* sT = sc.get<Xyzz>(BW * nsup);
-                if (!sA || !sS || !sT) return fail("cpg_g1_msm_batched: scratch allocation failed");
-                if (int r = launch(WindowReduceSuper{cS, cT, sA, sS, sT}, BW * nsup)) return r;
-                if (int r = launch(WindowReduceFinal{nsup, sA, sS, sT, wsum}, BW)) return r;
-            } else {
-                if (int r = launch(WindowReduceCombine{s, cS, cT, wsum}, BW)) return r;
-            }
-        }
-        if (slice) {
-            if (int r = launch(XyzzToJac{wsum, (Jac*)d_out}, BW)) return r;
-        } else {
             if (int r = launch(Horner{s, wsum, (Jac*)d_out + b0}, nb)) return r;
+            continue;
+        }
+        // counting sort of the digits: counts (atomics), three-pass scan, scatter
+        const uint32_t sch = s.NB < SCAN_CH ? s.NB : SCAN_CH, nsc = s.NB / sch;
+        uint32_t* cnt = sc.get<uint32_t>(BW * (s.NB + 1));
+        uint32_t* ctot = sc.get<uint32_t>(BW * nsc);
+        uint32_t* hist = sc.get<uint32_t>(LEN_BINS);
+        uint32_t* order = sc.get<uint32_t>(BW * s.NB);
+        Xyzz* lvA = sc.get<Xyzz>(BW * lvl_elems);
+        Xyzz* lvB = sc.get<Xyzz>(BW * lvl_elems);
+        Jac* wsum = slice ? (Jac*)d_out : sc.get<Jac>(BW);
+        if (!cnt || !ctot || !hist || !order || !lvA || !lvB || !wsum) return fail("cpg_g1_msm_batched: scratch allocation failed");
+        if (int r = cpg_memset(cnt, 0, BW * (s.NB + 1) * 4)) return r;
+        if (int r = cpg_memset(hist, 0, LEN_BINS * 4)) return r;
+        if (int r = launch(LargeCount{s, dig, cnt}, (uint64_t)nb * n)) return r;
+        if (int r = launch(LargeScanChunks{s, sch, nsc, cnt, ctot}, BW * nsc)) return r;
+        if (int r = launch(LargeScanTop{nsc, ctot}, BW)) return r;
+        if (int r = launch(LargeScanApply{s, sch, nsc, cnt, ctot, boff}, BW * nsc)) return r;
+        if (int r = launch(LargeScatter{s, dig, boff, cnt, sorted}, (uint64_t)nb * n)) return r;
+        // buckets by list length, longest first
+        if (int r = launch(LenHist{s, boff, hist}, BW * s.NB)) return r;
+        if (int r = launch(LenScan{hist}, 1)) return r;
+        if (int r = launch(LenScatter{s, boff, hist, order}, BW * s.NB)) return r;
+        if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, nullptr, order, BW, buckets}, BW * s.NB)) return r;
+        // level-wise window reduction
+        const Xyzz* in = buckets; Xyzz* out = lvA;
+        uint32_t len = s.NB;
+        for (uint32_t j = 0; j < nlev; j++) {
+            uint32_t ch = chs[j];
+            if (int r = launch(ReduceLevel{j + 1, ch, len, BW, in, out}, (uint64_t)(j + 1) * BW * (len / ch))) return r;
+            len /= ch; in = out; out = (out == lvA) ? lvB : lvA;
+        }
+        ReduceFinal fin; fin.levels = nlev; fin.BW = BW; fin.in = in; fin.wsum = wsum;
+        for (int k = 0; k < 16; k++) fin.lg_ch[k] = k < (int)nlev ? lg_ch[k] : 0;
+        if (int r = launch(fin, BW)) return r;
+        if (!slice) {
+            if (int r = launch(HornerJac{s.W, s.c, wsum, (Jac*)d_out + b0}, nb)) return r;
         }
     }
     return 0;

@@ -138,11 +138,15 @@ struct BucketAccumulate {
     const uint32_t* boff;
     const uint32_t* sorted;
     const uint16_t* rank;         // from SortDigits, or null
+    const uint32_t* order;        // from LenScatter (large path: all buckets of the launch by list length), or null
     uint64_t BW;                  // B*W
     Xyzz* buckets;                // [B*W][NB] (out)
     CPG_HD void operator()(uint64_t t) const {
         uint64_t mw; uint32_t b;
-        if (rank) {
+        if (order) {
+            uint32_t id = order[t];
+            mw = id / s.NB; b = id % s.NB;
+        } else if (rank) {
             uint32_t lane = (uint32_t)(t % 32), r = (uint32_t)((t / 32) % s.NB);
             uint64_t q = t / (32ull * s.NB);
             uint32_t w = (uint32_t)(q % s.wn);              // window index relative to w0
@@ -218,31 +222,57 @@ CPG_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return atomicAdd(p, v)
 #else
 CPG_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 #endif
-struct LargeCount {                // thread = (msm, term): off[mw][|d|] += 1  (off zeroed beforehand)
+struct LargeCount {                // thread = (msm, term): cnt[mw][|d|] += 1  (cnt zeroed beforehand)
     static constexpr const char* kName = "LargeCount";
-    MsmShape s; const int16_t* dig; uint32_t* boff;
+    MsmShape s; const int16_t* dig; uint32_t* cnt;
     CPG_HD void operator()(uint64_t t) const {
         uint64_t m = t / s.n;
         const int16_t* dg = dig + t * (uint64_t)s.W;
         for (uint32_t k = 0; k < s.wn; k++) {
             int d = dg[s.w0 + k];
-            if (d) atomic_add_u32(boff + (m * s.wn + k) * (uint64_t)(s.NB + 1) + (uint32_t)(d < 0 ? -d : d), 1u);
+            if (d) atomic_add_u32(cnt + (m * s.wn + k) * (uint64_t)(s.NB + 1) + (uint32_t)(d < 0 ? -d : d), 1u);
         }
     }
 };
-struct LargeScan {                 // thread = (msm, window): off[a] = END of bucket a-1; totals[mw] = list length
-    static constexpr const char* kName = "LargeScan";
-    MsmShape s; uint32_t* boff; uint32_t* totals;
+// Exclusive scan of the NB counts of every (msm, window) in three short per-thread passes (a window of
+// 2^15 buckets scanned by ONE thread was a millisecond of pure latency): chunk totals, a scan of the
+// <= NB/SCAN_CH totals, then the starts.  boff[b] = start of bucket b (digit b+1), boff[NB] = list length.
+constexpr uint32_t SCAN_CH = 64;
+struct LargeScanChunks {           // thread = (mw, chunk)
+    static constexpr const char* kName = "LargeScanChunks";
+    MsmShape s; uint32_t ch, nch; const uint32_t* cnt; uint32_t* ctot;
     CPG_HD void operator()(uint64_t t) const {
-        uint32_t* off = boff + t * (uint64_t)(s.NB + 1);
-        uint32_t run = 0;
-        for (uint32_t b = 1; b <= s.NB; b++) { run += off[b]; off[b] = run; }
-        totals[t] = run;
+        uint64_t mw = t / nch; uint32_t k = (uint32_t)(t % nch);
+        const uint32_t* c = cnt + mw * (uint64_t)(s.NB + 1) + 1 + (uint64_t)k * ch;
+        uint32_t sum = 0;
+        for (uint32_t i = 0; i < ch; i++) sum += c[i];
+        ctot[t] = sum;
     }
 };
-struct LargeScatter {              // thread = (msm, term): claim a slot from the END of its bucket
+struct LargeScanTop {              // thread = mw: chunk totals -> exclusive chunk starts
+    static constexpr const char* kName = "LargeScanTop";
+    uint32_t nch; uint32_t* ctot;
+    CPG_HD void operator()(uint64_t mw) const {
+        uint32_t* c = ctot + mw * (uint64_t)nch;
+        uint32_t run = 0;
+        for (uint32_t k = 0; k < nch; k++) { uint32_t v = c[k]; c[k] = run; run += v; }
+    }
+};
+struct LargeScanApply {            // thread = (mw, chunk): bucket starts; the counts become zeroed scatter cursors
+    static constexpr const char* kName = "LargeScanApply";
+    MsmShape s; uint32_t ch, nch; uint32_t* cnt; const uint32_t* ctot; uint32_t* boff;
+    CPG_HD void operator()(uint64_t t) const {
+        uint64_t mw = t / nch; uint32_t k = (uint32_t)(t % nch);
+        uint32_t* c = cnt + mw * (uint64_t)(s.NB + 1) + 1 + (uint64_t)k * ch;
+        uint32_t* o = boff + mw * (uint64_t)(s.NB + 1) + (uint64_t)k * ch;
+        uint32_t run = ctot[t];
+        for (uint32_t i = 0; i < ch; i++) { o[i] = run; run += c[i]; c[i] = 0; }
+        if (k == nch - 1) o[ch] = run;
+    }
+};
+struct LargeScatter {              // thread = (msm, term): claim the next slot of its bucket
     static constexpr const char* kName = "LargeScatter";
-    MsmShape s; const int16_t* dig; uint32_t* boff; uint32_t* sorted;
+    MsmShape s; const int16_t* dig; const uint32_t* boff; uint32_t* cursor; uint32_t* sorted;
     CPG_HD void operator()(uint64_t t) const {
         uint64_t m = t / s.n; uint32_t i = (uint32_t)(t % s.n);
         const int16_t* dg = dig + t * (uint64_t)s.W;
@@ -251,89 +281,77 @@ struct LargeScatter {              // thread = (msm, term): claim a slot from th
             if (!d) continue;
             uint64_t mw = m * s.wn + k;
             uint32_t a = (uint32_t)(d < 0 ? -d : d);
-            uint32_t pos = atomic_add_u32(boff + mw * (uint64_t)(s.NB + 1) + a, 0xffffffffu) - 1;   // fetch-and-decrement
+            uint32_t pos = boff[mw * (uint64_t)(s.NB + 1) + a - 1] + atomic_add_u32(cursor + mw * (uint64_t)(s.NB + 1) + a, 1u);
             sorted[mw * (uint64_t)s.n + pos] = i | (d < 0 ? 0x80000000u : 0u);
         }
     }
 };
-struct LargeFinish {               // thread = (msm, window): cursors are now bucket STARTS shifted by one
-    static constexpr const char* kName = "LargeFinish";
-    MsmShape s; uint32_t* boff; const uint32_t* totals;
+// Buckets ordered by list length, longest first (counting sort over all (msm, window, bucket) of the
+// launch): a warp of BucketAccumulate then walks 32 lists of equal length instead of waiting for its
+// longest lane (Poisson-distributed lengths cost a third of the kernel otherwise).
+constexpr uint32_t LEN_BINS = 1024;
+CPG_HD uint32_t len_bin(uint32_t len) { return len < LEN_BINS ? len : LEN_BINS - 1; }
+struct LenHist {                   // thread = (mw, bucket)
+    static constexpr const char* kName = "LenHist";
+    MsmShape s; const uint32_t* boff; uint32_t* hist;
     CPG_HD void operator()(uint64_t t) const {
-        uint32_t* off = boff + t * (uint64_t)(s.NB + 1);
-        for (uint32_t b = 0; b < s.NB; b++) off[b] = off[b + 1];
-        off[s.NB] = totals[t];
+        uint64_t mw = t / s.NB; uint32_t b = (uint32_t)(t % s.NB);
+        const uint32_t* o = boff + mw * (uint64_t)(s.NB + 1) + b;
+        atomic_add_u32(hist + len_bin(o[1] - o[0]), 1u);
     }
 };
-// window reduction in chunks of CH buckets: S_c = sum_{b in chunk} (b - b0 + 1) B_b and T_c = sum B_b,
-// then  sum_b (b+1) B_b = sum_c S_c + CH * sum_c c T_c  (second-level running sum, CH a power of two)
-constexpr uint32_t REDUCE_CH = 64;
-struct WindowReduceChunks {        // thread = (msm, window, chunk)
-    static constexpr const char* kName = "WindowReduceChunks";
-    MsmShape s; const Xyzz* buckets; Xyzz* chunk_S; Xyzz* chunk_T;
-    CPG_HD void operator()(uint64_t t) const {
-        const Xyzz* bk = buckets + t * (uint64_t)REDUCE_CH;      // chunks tile the [mw][NB] array exactly
-        Xyzz run = xyzz_inf(), tot = xyzz_inf();
-        for (uint32_t b = REDUCE_CH; b-- > 0;) {
-            run = xyzz_add(run, bk[b]);
-            tot = xyzz_add(tot, run);
-        }
-        chunk_S[t] = tot; chunk_T[t] = run;
+struct LenScan {                   // one thread: histogram -> first slot of every length, longest first
+    static constexpr const char* kName = "LenScan";
+    uint32_t* hist;
+    CPG_HD void operator()(uint64_t) const {
+        uint32_t run = 0;
+        for (uint32_t l = LEN_BINS; l-- > 0;) { uint32_t v = hist[l]; hist[l] = run; run += v; }
     }
 };
-struct WindowReduceCombine {       // thread = (msm, window)
-    static constexpr const char* kName = "WindowReduceCombine";
-    MsmShape s; const Xyzz* chunk_S; const Xyzz* chunk_T; Xyzz* wsum;
+struct LenScatter {                // thread = (mw, bucket)
+    static constexpr const char* kName = "LenScatter";
+    MsmShape s; const uint32_t* boff; uint32_t* hist; uint32_t* order;
     CPG_HD void operator()(uint64_t t) const {
-        uint32_t nch = s.NB / REDUCE_CH;
-        const Xyzz* S = chunk_S + t * (uint64_t)nch;
-        const Xyzz* T = chunk_T + t * (uint64_t)nch;
-        Xyzz run = xyzz_inf(), acc = xyzz_inf(), sum = S[0];
-        for (uint32_t c = nch; c-- > 1;) {
-            run = xyzz_add(run, T[c]);
-            acc = xyzz_add(acc, run);                              // acc = sum_{c>=1} c T_c
-            sum = xyzz_add(sum, S[c]);
-        }
-        for (uint32_t k = REDUCE_CH; k > 1; k >>= 1) acc = xyzz_dbl(acc);
-        wsum[t] = xyzz_add(sum, acc);
+        uint64_t mw = t / s.NB; uint32_t b = (uint32_t)(t % s.NB);
+        const uint32_t* o = boff + mw * (uint64_t)(s.NB + 1) + b;
+        order[atomic_add_u32(hist + len_bin(o[1] - o[0]), 1u)] = (uint32_t)t;
     }
 };
-// three-level variant for very wide windows (NB/REDUCE_CH > 4*REDUCE_CH chunks): super-chunks of CH chunks
-//   A_C = sum S_c,  S'_C = sum (c - c0) T_c,  T'_C = sum T_c      (thread = (msm, window, super-chunk))
-//   total = sum_C A_C + CH * ( sum_C S'_C + CH * sum_C C T'_C )    (thread = (msm, window))
-struct WindowReduceSuper {
-    static constexpr const char* kName = "WindowReduceSuper";
-    const Xyzz* chunk_S; const Xyzz* chunk_T; Xyzz* sup_A; Xyzz* sup_S; Xyzz* sup_T;
+// Window reduction  sum_b (b+1) B_b  in log-depth levels.  With zero-based weights and chunks of CH,
+//   R0(X) = sum_i i X_i = sum_c S_c + CH * R0(T),   S_c = sum_j j X[c CH + j],  T_c = sum_j X[c CH + j],
+// so every level maps the weighted array to its chunk totals T (the next weighted array) and emits one
+// plain-sum array S; earlier levels' S arrays are chunk-summed alongside by their own threads ("roles").
+// At length 1:  sum_b (b+1) B_b = T + S^0 + CH_0 (S^1 + CH_1 (S^2 + ...)).  A thread's serial chain is
+// 2 CH - 3 additions per level instead of 2 NB for the whole window.
+struct ReduceLevel {               // thread = (role, mw, chunk); arrays are [role][BW][len]
+    static constexpr const char* kName = "ReduceLevel";
+    uint32_t roles, ch, len_in; uint64_t BW; const Xyzz* in; Xyzz* out;
     CPG_HD void operator()(uint64_t t) const {
-        const Xyzz* S = chunk_S + t * (uint64_t)REDUCE_CH;
-        const Xyzz* T = chunk_T + t * (uint64_t)REDUCE_CH;
-        Xyzz run = xyzz_inf(), acc = xyzz_inf(), sum = S[0];
-        for (uint32_t c = REDUCE_CH; c-- > 1;) {
-            run = xyzz_add(run, T[c]);
-            acc = xyzz_add(acc, run);
-            sum = xyzz_add(sum, S[c]);
+        uint32_t len_out = len_in / ch;
+        uint64_t c = t % len_out, q = t / len_out, mw = q % BW; uint32_t r = (uint32_t)(q / BW);
+        const Xyzz* X = in + (r * BW + mw) * (uint64_t)len_in + c * ch;
+        if (r == 0) {
+            Xyzz run = X[ch - 1], acc = run;
+            for (uint32_t j = ch - 1; j-- > 1;) { run = xyzz_add(run, X[j]); acc = xyzz_add(acc, run); }
+            out[mw * (uint64_t)len_out + c] = xyzz_add(run, X[0]);
+            out[((uint64_t)roles * BW + mw) * len_out + c] = acc;
+        } else {
+            Xyzz sum = X[0];
+            for (uint32_t j = 1; j < ch; j++) sum = xyzz_add(sum, X[j]);
+            out[(r * BW + mw) * (uint64_t)len_out + c] = sum;
         }
-        sup_A[t] = sum; sup_S[t] = acc; sup_T[t] = xyzz_add(run, T[0]);
     }
 };
-struct WindowReduceFinal {
-    static constexpr const char* kName = "WindowReduceFinal";
-    uint32_t nsup; const Xyzz* sup_A; const Xyzz* sup_S; const Xyzz* sup_T; Xyzz* wsum;
-    CPG_HD void operator()(uint64_t t) const {
-        const Xyzz* A = sup_A + t * (uint64_t)nsup;
-        const Xyzz* S = sup_S + t * (uint64_t)nsup;
-        const Xyzz* T = sup_T + t * (uint64_t)nsup;
-        Xyzz run = xyzz_inf(), acc = xyzz_inf(), sumA = A[0], sumS = S[0];
-        for (uint32_t c = nsup; c-- > 1;) {
-            run = xyzz_add(run, T[c]);
-            acc = xyzz_add(acc, run);                              // sum_{C>=1} C T'_C
-            sumA = xyzz_add(sumA, A[c]);
-            sumS = xyzz_add(sumS, S[c]);
+struct ReduceFinal {               // thread = mw; in = [levels + 1][BW][1]; window sums leave as Jacobian
+    static constexpr const char* kName = "ReduceFinal";
+    uint32_t levels; uint8_t lg_ch[16]; uint64_t BW; const Xyzz* in; Jac* wsum;
+    CPG_HD void operator()(uint64_t mw) const {
+        Xyzz acc = in[(uint64_t)levels * BW + mw];
+        for (uint32_t j = levels - 1; j-- > 0;) {
+            for (uint32_t k = 0; k < lg_ch[j]; k++) acc = xyzz_dbl(acc);
+            acc = xyzz_add(acc, in[(uint64_t)(j + 1) * BW + mw]);
         }
-        for (uint32_t k = REDUCE_CH; k > 1; k >>= 1) acc = xyzz_dbl(acc);
-        acc = xyzz_add(acc, sumS);
-        for (uint32_t k = REDUCE_CH; k > 1; k >>= 1) acc = xyzz_dbl(acc);
-        wsum[t] = xyzz_add(sumA, acc);
+        wsum[mw] = xyzz_to_jac(xyzz_add(acc, in[mw]));
     }
 };
 struct XyzzToJac {

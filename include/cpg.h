@@ -100,6 +100,10 @@ int cpg_g1_msm_batched(const void* d_bases_aff, size_t base_stride, const uint8_
  * d_bases_aff[d_base_off[b] ...] - lets MSMs over different sub-vectors share one call */
 int cpg_g1_msm_batched_off(const void* d_bases_aff, const uint32_t* d_base_off, const uint8_t* d_scalars,
                            size_t B, size_t n, int window, void* d_out_jac);
+/* Which kernel pipeline cpg_g1_msm_batched uses: 0 (default) by shape - thousands of small MSMs run one
+ * thread per (msm, window) for the sort/reduce stages, few or large MSMs run one thread per term with
+ * atomics, length-ordered buckets and a level-wise window reduction; 1 / 2 force either (tests, tuning). */
+int cpg_msm_force_path(int path);
 /* Window split of ONE large MSM (BASELINE configs 2 and 5): the W = cpg_msm_window_count
  * windows are independent; a rank computes the Jacobian window sums S_w of its slice, the slices are
  * exchanged by one small all-gather (W * 144 B in total), and every rank finishes with

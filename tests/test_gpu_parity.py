@@ -35,6 +35,17 @@ def test_msm(gpu_lib, cref, B, n, window, shared):
     pc.case_msm(gpu_lib, cref, B, n, window, shared)
 
 
+@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("B,n,window,shared", [(64, 128, 0, False), (8, 627, 7, False), (5, 7, 2, False), (16, 33, 7, True)])
+def test_msm_both_pipelines(gpu_lib, cref, B, n, window, shared, path):
+    gpu_lib.check(gpu_lib.c.cpg_msm_force_path(path))
+    try:
+        pc.case_msm(gpu_lib, cref, B, n, window, shared)
+        pc.case_msm(gpu_lib, cref, 6, 40, 4, shared=False, edge=True)
+    finally:
+        gpu_lib.check(gpu_lib.c.cpg_msm_force_path(0))
+
+
 def test_msm_edges(gpu_lib, cref):
     pc.case_msm(gpu_lib, cref, 6, 40, 4, shared=False, edge=True)
     pc.case_msm(gpu_lib, cref, 5, 128, 0, shared=True, edge=True)

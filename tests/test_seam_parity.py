@@ -23,6 +23,20 @@ def test_msm(seam_lib, cref, B, n, window, shared):
     pc.case_msm(seam_lib, cref, B, n, window, shared)
 
 
+@pytest.mark.parametrize("path", [1, 2])
+@pytest.mark.parametrize("B,n,window,shared", [(3, 16, 0, False), (2, 33, 5, True), (2, 7, 2, False), (1, 40, 8, False)])
+def test_msm_both_pipelines(seam_lib, cref, B, n, window, shared, path):
+    """path 1 = one thread per (msm, window) (the batched-proofs pipeline), 2 = per-term threads with the
+    level-wise reduction (single / large MSMs); by shape these small batches would all take path 2"""
+    seam_lib.check(seam_lib.c.cpg_msm_force_path(path))
+    try:
+        pc.case_msm(seam_lib, cref, B, n, window, shared)
+        if path == 1:
+            pc.case_msm(seam_lib, cref, 4, 12, 4, shared=False, edge=True)
+    finally:
+        seam_lib.check(seam_lib.c.cpg_msm_force_path(0))
+
+
 def test_msm_edges(seam_lib, cref):
     pc.case_msm(seam_lib, cref, 4, 12, 4, shared=False, edge=True)
     pc.case_msm(seam_lib, cref, 3, 12, 3, shared=True, edge=True)
