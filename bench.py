@@ -133,8 +133,8 @@ def pick_window(n):
     return bc
 
 
-def make_verify_batch(case, B):
-    """B lanes of (inputs, proof, expected verdict): the golden proof, 1 lane in 64 corrupted."""
+def make_verify_batch(case, B, every=64):
+    """B lanes of (inputs, proof, expected verdict): the golden proof, 1 lane in `every` corrupted."""
     cat = lambda k: b"".join(bytes.fromhex(h) for h in case[k])  # noqa: E731
     R, S, T, U = cat("vec_R"), cat("vec_S"), cat("vec_T"), cat("vec_U")
     good_in = R + S + T + U
@@ -143,8 +143,8 @@ def make_verify_batch(case, B):
     bad_proof = bytearray(proof); bad_proof[48 * 9 + 7] ^= 1; bad_proof = bytes(bad_proof)   # flipped bit in cm_U / B
     ins, prs, exp = [], [], bytearray(B)
     for i in range(B):
-        if i % 64 == 63:
-            if (i // 64) % 2 == 0:
+        if every and i % every == every - 1:
+            if (i // every) % 2 == 0:
                 ins.append(bad_in); prs.append(proof)
             else:
                 ins.append(good_in); prs.append(bad_proof)
@@ -165,11 +165,12 @@ def run_ours_verify(args, rank, world, dist):
     B, ell, n = args.batch, 124, 128
     NV, NF = 4 * ell + 1 + 18 + 10 * 7 + 1, n + 3
     c = args.window or pick_window(NV)
-    ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), ell, host_threads=args.host_threads)
+    ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), ell, fixed_window=args.fixed_window, host_threads=args.host_threads)
     ver.set_window(c)
     ver.set_transcript(args.transcript == "device")
     ver.set_streams(args.streams)
-    inputs, proofs, expected = make_verify_batch(case, B)
+    ver.set_group(args.group, args.group_window)
+    inputs, proofs, expected = make_verify_batch(case, B, args.corrupt_every)
     out = ctypes.create_string_buffer(B)
 
     def barrier():
@@ -254,6 +255,7 @@ def run_ours_verify(args, rank, world, dist):
         "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
     }
     cpu = cpu_verify_rate(case, sample=args.cpu_sample_verify, procs=1)
+    ver_rechecked, ver_group = ver.rechecked(), ver.group()
     prove_side = None
     if args.prove_batch and world == 1:
         ver.close()
@@ -268,7 +270,8 @@ def run_ours_verify(args, rank, world, dist):
         "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (381-bit Fq, 255-bit Fr)", "data": "synthetic",
         "config": {"workload": "batch verification of Whisk-size (n=128, ell=124) curdleproofs, B=%d proofs per GPU per step; "
-                               "reference-generated golden proof replicated, lane-unique weights, 1/64 lanes corrupted, verdicts checked" % B,
+                               "reference-generated golden proof replicated, lane-unique weights, %s lanes corrupted, verdicts checked" % (B, "1/%d" % args.corrupt_every if args.corrupt_every else "no"),
+                   "group": args.group, "group_in_use": ver_group, "rechecked_per_step": ver_rechecked,
                    "B_per_gpu": B, "n": n, "var_terms": NV, "fixed_terms": NF, "window": c, "transcript": args.transcript, "streams": args.streams,
                    "l2": "inputs_larger_than_l2 (%.0f MB wire + scalars per step)" % (B * (NV * 80 + NF * 32) / 1e6), "sharding": "per-proof, no collective"},
         "e2e": {"value": total * args.steps / (ms_e2e * 1e-3), "unit": "verifications/s", "ms_per_step": ms_e2e / args.steps,
@@ -386,9 +389,10 @@ def measure_prove(args, lib, case, B, steps, dist=None):
 
     ell = case["N"] - 4
     crs = bytes.fromhex(case["crs"])
-    prover = whisk.BatchProver(crs, ell)
+    prover = whisk.BatchProver(crs, ell, fixed_window=args.fixed_window)
     c = args.prove_window or pick_window(ell)
     prover.set_window(c)
+    prover.set_lanes(args.prove_lanes)
     inputs, perms, ks, rands = make_prove_batch(case, prover, B, 4242)
     perm_arr = array.array("I", perms)
     pbuf = (ctypes.c_uint32 * len(perm_arr)).from_buffer(perm_arr)
@@ -514,7 +518,7 @@ def run_ours_prove(args, rank, world, dist):
         "vs_baseline": None, "dtype": "u32 limbs (381-bit Fq, 255-bit Fr)", "data": "synthetic",
         "config": {"workload": "batch generation of Whisk-size (n=128, ell=124) curdleproofs, B=%d proofs per GPU per step in lock-step; "
                                "pre-shuffle trackers from the reference-generated fixture, per-lane permutation / k / blinders; 256 of the proofs re-checked by the batched verifier" % B,
-                   "B_per_gpu": B, "n": 128, "window_var": r["window"], "window_fixed": 12, "sharding": "per-proof, no collective",
+                   "B_per_gpu": B, "n": 128, "window_var": r["window"], "window_fixed": args.fixed_window or 12, "lanes": args.prove_lanes, "sharding": "per-proof, no collective",
                    "l2": "inputs_larger_than_l2 (%.0f MB per step)" % (r["h2d"] / 1e6)},
         "e2e": {"value": total * args.steps / (ms_e2e * 1e-3), "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
@@ -834,12 +838,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="verify", choices=["verify", "prove", "msm", "msm_large"])
     ap.add_argument("--prove-window", type=int, default=0, help="bucket window of the prover's variable-base MSMs (0 = model)")
+    ap.add_argument("--prove-lanes", type=int, default=2, help="sub-batches of the prover issued alternately on separate streams")
+    ap.add_argument("--fixed-window", type=int, default=0, help="window of the CRS fixed-base tables (0 = library default 12; 16 = 6.6 GB table)")
     ap.add_argument("--prove-batch", type=int, default=4096, help="proofs in the prove side-measurement of the default (verify) run; 0 = skip")
     ap.add_argument("--cpu-sample-prove", type=int, default=4, help="proofs in the bounded CPU sample")
     ap.add_argument("--batch", type=int, default=8192, help="proofs (or MSMs) per GPU per step")
     ap.add_argument("--terms", dest="n", type=int, default=128, help="terms per MSM (msm workloads)")
     ap.add_argument("--window", type=int, default=0, help="bucket window width (0 = from the work model)")
     ap.add_argument("--transcript", default="device", choices=["device", "host"], help="where the Fiat-Shamir transcript + coefficient algebra run")
+    ap.add_argument("--group", type=int, default=0, help="cross-proof aggregation: proofs per aggregated MSM (1 = per-proof MSMs, 0 = adaptive); failing groups are re-checked per proof")
+    ap.add_argument("--group-window", type=int, default=0, help="window of the aggregated MSM (0 = model)")
+    ap.add_argument("--corrupt-every", type=int, default=64, help="one lane in this many carries a corrupted proof or input (0 = none)")
     ap.add_argument("--streams", type=int, default=2, help="sub-batches in flight on separate CUDA streams")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads for the transcript (0 = all cores)")
     ap.add_argument("--cpu-sample", type=int, default=400, help="MSMs in the bounded CPU sample (msm workload)")

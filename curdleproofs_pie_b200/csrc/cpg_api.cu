@@ -190,7 +190,7 @@ uint32_t reduce_ch() {
 // chain matters: a bucket list is walked by one thread, and a window whose digit has only tw bits
 // (the top window holds 255 - c(W-1) bits) concentrates n terms in 2^tw lists.  Estimated time =
 // total products / pipe rate + serial products * single-thread product latency (0.9 us measured).
-uint32_t pick_window_large(size_t n) {
+uint32_t pick_window_large(size_t n, size_t B = 1) {
     double best = 1e300; uint32_t bc = 8;
     const double ch = reduce_ch();
     for (uint32_t c = 4; c <= 16; c++) {
@@ -204,7 +204,7 @@ uint32_t pick_window_large(size_t n) {
         double levels = std::ceil((c - 1) / std::log2(ch));
         double serial = longest * 10.0 + levels * (2.0 * ch - 3.0) * 14.0 + levels * 14.0 + (c - 1) * 9.0;
         double total = (double)n * W * 10.0 + W * NB * 3.0 * 14.0;
-        double t = total / 2.7e10 + serial * 0.9e-6;
+        double t = (double)B * total / 2.7e10 + serial * 0.9e-6;
         if (t < best) { best = t; bc = c; }
     }
     return bc;
@@ -564,7 +564,7 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
     // thousands of small MSMs: per-(msm, window) threads; few (or big) MSMs: per-term threads with atomics,
     // buckets ordered by list length, level-wise window reduction
     const bool few = g_msm_path == 0 ? B * 32 < 8192 : g_msm_path == 2;
-    uint32_t c = window > 0 ? (uint32_t)window : (few ? pick_window_large(n) : pick_window(n));
+    uint32_t c = window > 0 ? (uint32_t)window : ((few || n > 2048) ? pick_window_large(n, B) : pick_window(n));
     if (c < 2 || c > 16) return fail("cpg_g1_msm_batched: window must be in [2, 16]");
     Recode rc = make_recode(c);
     const bool slice = wn != 0;

@@ -90,6 +90,8 @@ template <class C> CPG_HD Fp<C> sqr(const Fp<C>& a) {
     else mont_mul_n<C::N>(r.l, a.l, a.l, C::p(), C::INV);
     return r;
 }
+// a^(2^n).  The device build of Fq overrides it with ONE register-ABI call that loops inside the callee.
+template <class C> CPG_HD Fp<C> sqr_n(Fp<C> a, int n) { for (int i = 0; i < n; i++) a = sqr(a); return a; }
 template <class C> CPG_HD Fp<C> add(const Fp<C>& a, const Fp<C>& b) { Fp<C> r; mod_add_n<C::N>(r.l, a.l, b.l, C::p()); return r; }
 template <class C> CPG_HD Fp<C> sub(const Fp<C>& a, const Fp<C>& b) { Fp<C> r; mod_sub_n<C::N>(r.l, a.l, b.l, C::p()); return r; }
 template <class C> CPG_HD Fp<C> dbl(const Fp<C>& a) { return add(a, a); }
@@ -100,25 +102,38 @@ template <class C> CPG_HD Fp<C> from_mont(const Fp<C>& a) { Fp<C> o = Fp<C>::zer
 // true iff the plain integer a is < p
 template <class C> CPG_HD bool is_canonical(const Fp<C>& a) { return !geq_n<C::N>(a.l, C::p()); }
 
-// a^e for a public exponent given as little-endian u32 words (left-to-right, 4-bit fixed window).
-// The exponent is uniform across the warp, so table indexing does not diverge.
+// a^e for a public exponent given as little-endian u32 words: left-to-right sliding window of 5 bits over
+// the 16 odd powers a, a^3 .. a^31.  For the 379-bit sqrt / inversion exponents of Fq that is 376 squarings +
+// 81 products (a fixed 4-bit window needs 105 products).  The exponent is uniform across the warp, so
+// neither the window scan nor the table index diverges.
 template <class C, int EW>
 CPG_HD Fp<C> pow_public(const Fp<C>& a, const uint32_t (&e)[EW]) {
     Fp<C> tbl[16];
-    tbl[0] = Fp<C>::one();
-    tbl[1] = a;
-    for (int i = 2; i < 16; i++) tbl[i] = mul(tbl[i - 1], a);
+    tbl[0] = a;
+    Fp<C> a2 = sqr(a);
+    for (int i = 1; i < 16; i++) tbl[i] = mul(tbl[i - 1], a2);
     Fp<C> acc = Fp<C>::one();
     bool started = false;
-    for (int w = EW * 8 - 1; w >= 0; w--) {
-        uint32_t d = (e[w >> 3] >> ((w & 7) * 4)) & 15u;
-        if (started) {
-            acc = sqr(acc); acc = sqr(acc); acc = sqr(acc); acc = sqr(acc);
+    int i = EW * 32 - 1;
+    while (i >= 0) {
+        if (!((e[i >> 5] >> (i & 31)) & 1u)) {                // a run of clear bits: that many squarings in one call
+            int z = 1;
+            while (i - z >= 0 && !((e[(i - z) >> 5] >> ((i - z) & 31)) & 1u)) z++;
+            if (started) acc = sqr_n(acc, z);
+            i -= z;
+            continue;
         }
-        if (d) {
-            acc = started ? mul(acc, tbl[d]) : tbl[d];
+        int l = i >= 4 ? 5 : i + 1;                         // longest window <= 5 bits that ends in a set bit
+        while (!((e[(i - l + 1) >> 5] >> ((i - l + 1) & 31)) & 1u)) l--;
+        uint32_t v = 0;
+        for (int k = 0; k < l; k++) v = (v << 1) | ((e[(i - k) >> 5] >> ((i - k) & 31)) & 1u);
+        if (started) {
+            acc = mul(sqr_n(acc, l), tbl[v >> 1]);
+        } else {
+            acc = tbl[v >> 1];
             started = true;
         }
+        i -= l;
     }
     return acc;
 }
@@ -135,6 +150,13 @@ static __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) { Fq r; mont_mul_n<12>
 static __device__ __noinline__ Fq fq_sqr_call(Fq a) { Fq r; mont_sqr_n<12>(r.l, a.l, FqCfg::p(), FqCfg::INV); return r; }
 __device__ __forceinline__ Fq mul(const Fq& a, const Fq& b) { return fq_mul_call(a, b); }
 __device__ __forceinline__ Fq sqr(const Fq& a) { return fq_sqr_call(a); }
+// repeated squaring inside ONE call: the ~50 register moves of the call ABI are paid once per run, not per squaring
+static __device__ __noinline__ Fq fq_sqr_n_call(Fq a, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) mont_sqr_n<12>(a.l, a.l, FqCfg::p(), FqCfg::INV);
+    return a;
+}
+__device__ __forceinline__ Fq sqr_n(Fq a, int n) { return fq_sqr_n_call(a, n); }
 #endif
 
 // Fq inversion a^(p-2) and square root candidate a^((p+1)/4) (p = 3 mod 4).

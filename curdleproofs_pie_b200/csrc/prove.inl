@@ -468,6 +468,42 @@ struct VarOffsets {
     CPG_HD void operator()(uint64_t t) const { uint64_t v = t / B, b = t % B; off[t] = (uint32_t)(b * 4 * ell + set[v] * ell); }
 };
 
+// One lane = the device buffers of a contiguous sub-batch.  A batch is split over `nlanes` lanes whose
+// rounds are issued alternately on separate streams, so the latency-bound per-proof kernels of one lane
+// (ProveStep: one thread per proof, 32 warps for 4096 proofs) run under the MSM kernels of the other.
+struct ProverLane {
+    size_t cap = 0, B = 0;
+    uint8_t *d_in48 = nullptr, *d_tu48 = nullptr, *d_k = nullptr, *d_rand = nullptr, *d_outs = nullptr, *d_fs = nullptr, *d_vs = nullptr, *d_proof = nullptr, *d_err = nullptr;
+    uint32_t *d_perm = nullptr, *d_off = nullptr; Aff* d_bases = nullptr; PState* d_st = nullptr; HFr* d_vec = nullptr; Jac *d_fix = nullptr, *d_var = nullptr;
+#ifndef CPG_HOST_EMU
+    cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
+#endif
+    std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_off, d_bases, d_st, d_vec, d_fix, d_var}; }
+    void release() {
+        for (void* q : all()) cpg_free(q);
+        d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = d_off = nullptr; d_bases = nullptr; d_st = nullptr; d_vec = nullptr; d_fix = d_var = nullptr;
+        cap = 0;
+    }
+    int reserve(const PShape& sh, size_t proof_len, size_t Bn, uint32_t NOUT) {
+        if (Bn <= cap) return 0;
+        release();
+        const size_t ell = sh.ell, n = sh.n;
+        d_in48 = (uint8_t*)cpg_malloc(Bn * 2 * ell * 48);     d_tu48 = (uint8_t*)cpg_malloc(Bn * 2 * ell * 48);
+        d_k = (uint8_t*)cpg_malloc(Bn * 32);                  d_rand = (uint8_t*)cpg_malloc(Bn * sh.NR * 32);
+        d_outs = (uint8_t*)cpg_malloc(Bn * NOUT * 48);        d_fs = (uint8_t*)cpg_malloc(Bn * P_MAX_OUT * sh.NF * 32);
+        d_vs = (uint8_t*)cpg_malloc(Bn * P_MAX_VAR * ell * 32); d_proof = (uint8_t*)cpg_malloc(Bn * proof_len);
+        d_err = (uint8_t*)cpg_malloc(Bn * 2 * ell);           d_perm = (uint32_t*)cpg_malloc(Bn * ell * 4);
+        d_off = (uint32_t*)cpg_malloc(Bn * P_MAX_VAR * 4);
+        d_bases = (Aff*)cpg_malloc(sizeof(Aff) * Bn * 4 * ell); d_st = (PState*)cpg_malloc(sizeof(PState) * Bn);
+        d_vec = (HFr*)cpg_malloc(sizeof(HFr) * Bn * PV_COUNT * n);
+        d_fix = (Jac*)cpg_malloc(sizeof(Jac) * Bn * P_MAX_OUT); d_var = (Jac*)cpg_malloc(sizeof(Jac) * Bn * P_MAX_VAR);
+        for (void* q : all()) if (!q) { release(); return fail("cpg_prove_batch: device allocation failed"); }
+        cap = Bn;
+        return 0;
+    }
+};
+constexpr int P_MAX_LANES = 4;
+
 struct Prover {
     PShape sh;
     size_t proof_len;             // 1088 + 480 lg (without M)
@@ -475,39 +511,27 @@ struct Prover {
     Aff* d_crs = nullptr; uint8_t* d_crs48 = nullptr;
     void* table = nullptr;        // fixed-base table over vec_G | vec_H | H | G_t | G_u
     int var_window = 0;
-    size_t cap = 0, lastB = 0;
-    uint8_t *d_in48 = nullptr, *d_tu48 = nullptr, *d_k = nullptr, *d_rand = nullptr, *d_outs = nullptr, *d_fs = nullptr, *d_vs = nullptr, *d_proof = nullptr, *d_err = nullptr;
-    uint32_t *d_perm = nullptr, *d_off = nullptr; Aff* d_bases = nullptr; PState* d_st = nullptr; HFr* d_vec = nullptr; Jac *d_fix = nullptr, *d_var = nullptr;
-    std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_off, d_bases, d_st, d_vec, d_fix, d_var}; }
-    void release() {
-        for (void* q : all()) cpg_free(q);
-        d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = d_off = nullptr; d_bases = nullptr; d_st = nullptr; d_vec = nullptr; d_fix = d_var = nullptr;
-        cap = 0;
-    }
-    int reserve(size_t B, uint32_t NOUT) {
-        if (B <= cap) return 0;
-        release();
-        const size_t ell = sh.ell, n = sh.n;
-        d_in48 = (uint8_t*)cpg_malloc(B * 2 * ell * 48);     d_tu48 = (uint8_t*)cpg_malloc(B * 2 * ell * 48);
-        d_k = (uint8_t*)cpg_malloc(B * 32);                  d_rand = (uint8_t*)cpg_malloc(B * sh.NR * 32);
-        d_outs = (uint8_t*)cpg_malloc(B * NOUT * 48);        d_fs = (uint8_t*)cpg_malloc(B * P_MAX_OUT * sh.NF * 32);
-        d_vs = (uint8_t*)cpg_malloc(B * P_MAX_VAR * ell * 32); d_proof = (uint8_t*)cpg_malloc(B * proof_len);
-        d_err = (uint8_t*)cpg_malloc(B * 2 * ell);           d_perm = (uint32_t*)cpg_malloc(B * ell * 4);
-        d_off = (uint32_t*)cpg_malloc(B * P_MAX_VAR * 4);
-        d_bases = (Aff*)cpg_malloc(sizeof(Aff) * B * 4 * ell); d_st = (PState*)cpg_malloc(sizeof(PState) * B);
-        d_vec = (HFr*)cpg_malloc(sizeof(HFr) * B * PV_COUNT * n);
-        d_fix = (Jac*)cpg_malloc(sizeof(Jac) * B * P_MAX_OUT); d_var = (Jac*)cpg_malloc(sizeof(Jac) * B * P_MAX_VAR);
-        for (void* q : all()) if (!q) { release(); return fail("cpg_prove_batch: device allocation failed"); }
-        cap = B;
-        return 0;
+    int nlanes = 2, lastK = 1;
+    size_t lane_min = 256;        // proofs per lane below which a batch is not split
+    size_t lastB = 0;
+    ProverLane lanes[P_MAX_LANES];
+#ifndef CPG_HOST_EMU
+    cudaEvent_t fork = nullptr;
+#endif
+    void release() { for (ProverLane& L : lanes) L.release(); }
+    // contiguous split of B proofs; small batches stay on one lane (nothing to hide behind)
+    int split(size_t B, size_t* first, size_t* count) const {
+        int k = (B >= lane_min * (size_t)nlanes) ? nlanes : 1;
+        for (int i = 0; i < k; i++) { first[i] = B * i / k; count[i] = B * (i + 1) / k - first[i]; }
+        return k;
     }
 };
 
-// The device side of one batch (inputs already resident): decode, shuffle, 21 rounds, wire assembly.
-int prove_device_all(Prover& p, size_t B) {
-    const PShape sh = p.sh;
-    const POut O(sh.lg);
-    const uint32_t ell = sh.ell, lg = sh.lg;
+// The device side of one lane (inputs already resident): decode + shuffle, then 8 + 2 lg rounds.
+int prove_lane_prologue(Prover& pr, ProverLane& p) {
+    const PShape sh = pr.sh;
+    const uint32_t ell = sh.ell;
+    const size_t B = p.B;
     // decode R | S into the first half of each proof's base row, then the shuffle itself
     {
         Scratch sc;
@@ -522,10 +546,15 @@ int prove_device_all(Prover& p, size_t B) {
         for (size_t b = 0; b < B; b++) memcpy(p.d_bases + b * 4 * (size_t)ell, tmp + b * 2 * (size_t)ell, sizeof(Aff) * 2 * (size_t)ell);
 #endif
     }
-    if (int rc = launch(ProveShuffle{ell, p.d_bases, p.d_perm, (const uint32_t*)p.d_k, p.d_tu48}, B * 2 * (size_t)ell)) return rc;
-
+    return launch(ProveShuffle{ell, p.d_bases, p.d_perm, (const uint32_t*)p.d_k, p.d_tu48}, B * 2 * (size_t)ell);
+}
+int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
+    const PShape sh = pr.sh;
+    const POut O(sh.lg);
+    const uint32_t ell = sh.ell, lg = sh.lg;
+    const size_t B = p.B;
     PBuffers pb;
-    pb.in48 = p.d_in48; pb.tu48 = p.d_tu48; pb.perm = p.d_perm; pb.kbytes = p.d_k; pb.rand = p.d_rand; pb.crs48 = p.d_crs48;
+    pb.in48 = p.d_in48; pb.tu48 = p.d_tu48; pb.perm = p.d_perm; pb.kbytes = p.d_k; pb.rand = p.d_rand; pb.crs48 = pr.d_crs48;
     pb.st = p.d_st; pb.vec = p.d_vec; pb.outs48 = p.d_outs; pb.fs = p.d_fs; pb.vs = p.d_vs; pb.proof = p.d_proof; pb.B = B;
 
     // per round: (first output id, count) and which outputs carry a variable-base part over which vector
@@ -551,17 +580,17 @@ int prove_device_all(Prover& p, size_t B) {
         else if (r < 7 + 2 * lg) { uint32_t base = O.msm0 + 6 * (r - 7 - lg); add(base, -1); add(base + 1, 2); add(base + 2, 3); add(base + 3, -1); add(base + 4, 2); add(base + 5, 3); }
         return pl;
     };
-    for (uint32_t r = 0; r <= 7 + 2 * lg; r++) {
+    {
         if (int rc = launch<64>(ProveStep{sh, O, pb, r}, B)) return rc;
-        if (r == 7 + 2 * lg) break;
+        if (r == 7 + 2 * lg) return 0;
         RoundPlan pl = plan_for(r);
         // fixed-base part of every output of the round: B*nout MSMs over the CRS table (rows are output-major)
-        if (int rc = cpg_g1_msm_fixed_batched(p.table, p.d_fs, B * pl.nout, 0, p.d_fix)) return rc;
+        if (int rc = cpg_g1_msm_fixed_batched(pr.table, p.d_fs, B * pl.nout, 0, p.d_fix)) return rc;
         if (pl.nvar) {                                  // variable-base parts: ONE batched MSM over all B*nvar instances
             VarOffsets vo; vo.B = B; vo.ell = ell; vo.off = p.d_off;
             for (uint32_t v = 0; v < P_MAX_VAR; v++) vo.set[v] = v < pl.nvar ? pl.var_set[v] : 0;
             if (int rc = launch(vo, B * pl.nvar)) return rc;
-            if (int rc = cpg_g1_msm_batched_off(p.d_bases, p.d_off, p.d_vs, B * pl.nvar, ell, p.var_window, p.d_var)) return rc;
+            if (int rc = cpg_g1_msm_batched_off(p.d_bases, p.d_off, p.d_vs, B * pl.nvar, ell, pr.var_window, p.d_var)) return rc;
         }
         ProveCombine pc;
         pc.nout = pl.nout; pc.NOUT = O.NOUT; pc.B = B; pc.fixed = p.d_fix; pc.var = p.d_var; pc.outs48 = p.d_outs;
@@ -575,6 +604,36 @@ int prove_device_all(Prover& p, size_t B) {
         if (int rc = launch(pc, B * pl.nout)) return rc;
     }
     return 0;
+}
+// All lanes, rounds issued alternately.  The lane streams fork from the caller's stream and join it again,
+// so events recorded on the caller's stream (cpg_timer_*) bracket the whole batch.
+int prove_device_all(Prover& p, int k) {
+    const uint32_t rounds = 8 + 2 * p.sh.lg;
+#ifndef CPG_HOST_EMU
+    cudaStream_t caller = cur();
+    const bool had = t_stream_set; cudaStream_t prev = t_stream;
+    if (k > 1) {
+        CK(cudaEventRecord(p.fork, caller));
+        for (int i = 0; i < k; i++) CK(cudaStreamWaitEvent(p.lanes[i].stream, p.fork, 0));
+    }
+    auto enter = [&](int i) { if (k > 1) { t_stream = p.lanes[i].stream; t_stream_set = true; } };
+    auto leave = [&]() { t_stream = prev; t_stream_set = had; };
+#else
+    auto enter = [&](int) {};
+    auto leave = [&]() {};
+#endif
+    int rc = 0;
+    for (int i = 0; i < k && !rc; i++) { enter(i); rc = prove_lane_prologue(p, p.lanes[i]); }
+    for (uint32_t r = 0; r < rounds && !rc; r++)
+        for (int i = 0; i < k && !rc; i++) { enter(i); rc = prove_lane_round(p, p.lanes[i], r); }
+    leave();
+#ifndef CPG_HOST_EMU
+    if (k > 1) for (int i = 0; i < k; i++) {
+        CK(cudaEventRecord(p.lanes[i].done, p.lanes[i].stream));
+        CK(cudaStreamWaitEvent(caller, p.lanes[i].done, 0));
+    }
+#endif
+    return rc;
 }
 
 }  // namespace
@@ -603,7 +662,14 @@ void* cpg_prover_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders,
     cpg_free(derr);
     if (!rc) for (uint8_t e : err) if (e) { rc = fail("cpg_prover_create: CRS holds an invalid point encoding"); break; }
     if (!rc) { p->table = cpg_fixed_table_create(p->d_crs, n + 3, fixed_window > 0 ? fixed_window : 12); if (!p->table) rc = 1; }
-    if (rc) { cpg_free(p->d_crs); cpg_free(p->d_crs48); delete p; return nullptr; }
+#ifndef CPG_HOST_EMU
+    if (!rc) rc = ck(cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming), "cudaEventCreate");
+    for (ProverLane& L : p->lanes) {
+        if (!rc) rc = ck(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        if (!rc) rc = ck(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming), "cudaEventCreate");
+    }
+#endif
+    if (rc) { cpg_prover_free(p); return nullptr; }
     return p;
 }
 
@@ -611,6 +677,10 @@ int cpg_prover_free(void* handle) {
     if (!handle) return 0;
     Prover* p = (Prover*)handle;
     p->release();
+#ifndef CPG_HOST_EMU
+    for (ProverLane& L : p->lanes) { if (L.stream) cudaStreamDestroy(L.stream); if (L.done) cudaEventDestroy(L.done); }
+    if (p->fork) cudaEventDestroy(p->fork);
+#endif
     cpg_fixed_table_free(p->table);
     cpg_free(p->d_crs); cpg_free(p->d_crs48);
     delete p;
@@ -624,9 +694,16 @@ int cpg_prove_replay_device(void* handle) {
     if (!handle) return fail("cpg_prove_replay_device: null prover");
     Prover& p = *(Prover*)handle;
     if (!p.lastB) return fail("cpg_prove_replay_device: no batch resident");
-    return prove_device_all(p, p.lastB);
+    return prove_device_all(p, p.lastK);
 }
 int cpg_prover_set_window(void* handle, int w) { if (!handle) return 1; ((Prover*)handle)->var_window = w; return 0; }
+int cpg_prover_set_lanes(void* handle, int nlanes, size_t min_proofs_per_lane) {
+    if (!handle) return fail("cpg_prover_set_lanes: null prover");
+    if (nlanes < 1 || nlanes > P_MAX_LANES) return fail("cpg_prover_set_lanes: 1..4 lanes");
+    ((Prover*)handle)->nlanes = nlanes;
+    ((Prover*)handle)->lane_min = min_proofs_per_lane ? min_proofs_per_lane : 256;
+    return 0;
+}
 
 /* inputs   : [B][2*ell*48]  vec_R | vec_S            (pre-shuffle tracker halves)
  * perms    : [B][ell] u32   permutation (post[j] = k * pre[perm[j]])
@@ -645,19 +722,30 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
     const PShape sh = p.sh;
     const POut O(sh.lg);
     const uint32_t ell = sh.ell, lg = sh.lg;
-    if (int rc = p.reserve(B, O.NOUT)) return rc;
-    if (int rc = cpg_h2d(p.d_in48, inputs, B * 2 * (size_t)ell * 48)) return rc;
-    if (int rc = cpg_h2d(p.d_perm, perms, B * (size_t)ell * 4)) return rc;
-    if (int rc = cpg_h2d(p.d_k, ks, B * 32)) return rc;
-    if (int rc = cpg_h2d(p.d_rand, rand, B * (size_t)sh.NR * 32)) return rc;
-    p.lastB = B;
-    if (int rc = prove_device_all(p, B)) return rc;
+    size_t first[P_MAX_LANES], count[P_MAX_LANES];
+    const int k = p.split(B, first, count);
+    for (int i = 0; i < k; i++) {
+        ProverLane& L = p.lanes[i];
+        const size_t f = first[i], c = count[i];
+        if (int rc = L.reserve(sh, p.proof_len, c, O.NOUT)) return rc;
+        L.B = c;
+        if (int rc = cpg_h2d(L.d_in48, inputs + f * 2 * (size_t)ell * 48, c * 2 * (size_t)ell * 48)) return rc;
+        if (int rc = cpg_h2d(L.d_perm, perms + f * (size_t)ell, c * (size_t)ell * 4)) return rc;
+        if (int rc = cpg_h2d(L.d_k, ks + f * 32, c * 32)) return rc;
+        if (int rc = cpg_h2d(L.d_rand, rand + f * (size_t)sh.NR * 32, c * (size_t)sh.NR * 32)) return rc;
+    }
+    p.lastB = B; p.lastK = k;
+    if (int rc = prove_device_all(p, k)) return rc;
     // results: T|U, M|proof, per-lane status
-    if (int rc = cpg_d2h(out_tu, p.d_tu48, B * 2 * (size_t)ell * 48)) return rc;
     std::vector<uint8_t> outs(B * (size_t)O.NOUT * 48), proofs(B * p.proof_len), err(B * 2 * (size_t)ell);
-    if (int rc = cpg_d2h(outs.data(), p.d_outs, outs.size())) return rc;
-    if (int rc = cpg_d2h(proofs.data(), p.d_proof, proofs.size())) return rc;
-    if (int rc = cpg_d2h(err.data(), p.d_err, err.size())) return rc;
+    for (int i = 0; i < k; i++) {
+        ProverLane& L = p.lanes[i];
+        const size_t f = first[i], c = count[i];
+        if (int rc = cpg_d2h(out_tu + f * 2 * (size_t)ell * 48, L.d_tu48, c * 2 * (size_t)ell * 48)) return rc;
+        if (int rc = cpg_d2h(outs.data() + f * (size_t)O.NOUT * 48, L.d_outs, c * (size_t)O.NOUT * 48)) return rc;
+        if (int rc = cpg_d2h(proofs.data() + f * p.proof_len, L.d_proof, c * p.proof_len)) return rc;
+        if (int rc = cpg_d2h(err.data() + f * 2 * (size_t)ell, L.d_err, c * 2 * (size_t)ell)) return rc;
+    }
     for (size_t b = 0; b < B; b++) {
         uint8_t* w = out_proofs + b * (p.proof_len + 48);
         memcpy(w, outs.data() + (b * O.NOUT + O.M) * 48, 48);

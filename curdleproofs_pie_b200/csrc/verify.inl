@@ -321,6 +321,53 @@ struct AddFixedAndTest {          // thread = proof: verdict = !reject && (var +
     CPG_HD void operator()(uint64_t t) const { ok[t] = (!reject[t] && is_inf(jac_add(a[t], b[t]))) ? 1 : 0; }
 };
 
+// ---- cross-proof aggregation -------------------------------------------------------
+// The 12 batching weights of a proof are drawn per proof (secret- and lane-keyed), so the SUM of the
+// relations of G proofs is itself a random linear combination of all 12 G checks: a group of G proofs
+// is accepted by ONE MSM over G*NV variable bases (wider windows: ~40 % fewer Fq products per proof at
+// G = 8..32) plus ONE fixed-base MSM over the summed CRS coefficients.  A group that fails (or holds a
+// structurally rejected proof) is re-checked proof by proof, so per-proof verdicts stay exact.
+struct GroupSumFixed {            // thread = (group, i < NF): sum of the G proofs' coefficient of CRS base i
+    static constexpr const char* kName = "GroupSumFixed";
+    uint32_t G, NF; const uint8_t* fs; uint8_t* out;
+    CPG_HD void operator()(uint64_t t) const {
+        uint64_t g = t / NF; uint32_t i = (uint32_t)(t % NF);
+        HFr acc = cpgh::fr_zero();
+        for (uint32_t k = 0; k < G; k++) {
+            HFr v;                                                       // canonical integers < r: add mod r as they are
+            memcpy(v.l, fs + ((g * G + k) * (uint64_t)NF + i) * 32, 32);
+            acc = cpgh::fr_add(acc, v);
+        }
+        memcpy(out + t * 32, acc.l, 32);
+    }
+};
+struct GroupTest {                // thread = group: provisional verdict of its G proofs
+    static constexpr const char* kName = "GroupTest";
+    uint32_t G; const Jac* a; const Jac* b; const uint8_t* reject; uint8_t* gok; uint8_t* ok;
+    CPG_HD void operator()(uint64_t g) const {
+        bool fine = is_inf(jac_add(a[g], b[g]));
+        for (uint32_t k = 0; k < G; k++) fine = fine && !reject[g * G + k];
+        gok[g] = fine ? 1 : 0;
+        for (uint32_t k = 0; k < G; k++) ok[g * G + k] = fine ? 1 : 0;
+    }
+};
+struct Row16 { uint32_t w[4]; };
+struct GatherRows {               // thread = (k, 16-byte word j): dst[k] = src[idx[k]]
+    static constexpr const char* kName = "GatherRows";
+    const uint32_t* idx; uint32_t words; const Row16* src; Row16* dst;
+    CPG_HD void operator()(uint64_t t) const { uint64_t k = t / words, j = t % words; dst[t] = src[(uint64_t)idx[k] * words + j]; }
+};
+struct GatherMeta {               // thread = k: base offset (in points) and reject flag of proof idx[k]
+    static constexpr const char* kName = "GatherMeta";
+    const uint32_t* idx; uint32_t NV; const uint8_t* rej; uint32_t* off; uint8_t* rej_out;
+    CPG_HD void operator()(uint64_t k) const { off[k] = idx[k] * NV; rej_out[k] = rej[idx[k]]; }
+};
+struct ScatterVerdicts {          // thread = k: ok[idx[k]] = per-proof verdict
+    static constexpr const char* kName = "ScatterVerdicts";
+    const uint32_t* idx; const Jac* a; const Jac* b; const uint8_t* rej; uint8_t* ok;
+    CPG_HD void operator()(uint64_t k) const { ok[idx[k]] = (!rej[k] && is_inf(jac_add(a[k], b[k]))) ? 1 : 0; }
+};
+
 template <class F>
 void parallel_for(int threads, size_t n, F f) {
     if (threads <= 1 || n < 2) { for (size_t i = 0; i < n; i++) f(i); return; }
@@ -403,20 +450,24 @@ struct Verifier {
     void* table_gh = nullptr;     // fixed-base table over G_sum, H_sum
     uint8_t secret[32];
     int var_window = 0;
+    uint32_t group = 1;           // proofs per aggregated check (1 = every proof on its own MSM)
+    bool group_auto = false;      // re-pick `group` after every batch from the observed rate of failing proofs
+    int group_window = 0;
+    size_t rechecked = 0;         // proofs of the last batch that went through the per-proof fallback
     // device buffers of the current batch, kept (and grown on demand) between calls
     size_t cap = 0, lastB = 0;
     uint8_t *d_wire = nullptr, *d_psc = nullptr, *d_err = nullptr, *d_derived = nullptr, *d_t0 = nullptr, *d_vs = nullptr, *d_fs = nullptr,
-            *d_ok = nullptr, *d_rej = nullptr, *d_chal = nullptr;
+            *d_ok = nullptr, *d_rej = nullptr, *d_chal = nullptr, *d_gok = nullptr, *d_gfs = nullptr;
     Aff* d_bases = nullptr; Jac *d_var = nullptr, *d_fix = nullptr, *d_gh = nullptr;
     VState* d_st = nullptr; HFr *d_a = nullptr, *d_tmp = nullptr;
     // pinned host staging (grown on demand)
     size_t hcap = 0;
     uint8_t *h_wire = nullptr, *h_psc = nullptr;
 
-    std::vector<void*> all() { return {d_wire, d_psc, d_err, d_derived, d_t0, d_vs, d_fs, d_ok, d_rej, d_chal, d_bases, d_var, d_fix, d_gh, d_st, d_a, d_tmp}; }
+    std::vector<void*> all() { return {d_wire, d_psc, d_err, d_derived, d_t0, d_vs, d_fs, d_ok, d_rej, d_chal, d_gok, d_gfs, d_bases, d_var, d_fix, d_gh, d_st, d_a, d_tmp}; }
     void release() {
         for (void* q : all()) cpg_free(q);
-        d_wire = d_psc = d_err = d_derived = d_t0 = d_vs = d_fs = d_ok = d_rej = d_chal = nullptr;
+        d_wire = d_psc = d_err = d_derived = d_t0 = d_vs = d_fs = d_ok = d_rej = d_chal = d_gok = d_gfs = nullptr;
         d_bases = nullptr; d_var = d_fix = d_gh = nullptr; d_st = nullptr; d_a = d_tmp = nullptr;
         cap = 0;
     }
@@ -440,6 +491,7 @@ struct Verifier {
         d_gh = (Jac*)cpg_malloc(sizeof(Jac) * B);        d_ok = (uint8_t*)cpg_malloc(B);
         d_st = (VState*)cpg_malloc(sizeof(VState) * B);  d_a = (HFr*)cpg_malloc(sizeof(HFr) * B * sh.ell);
         d_tmp = (HFr*)cpg_malloc(sizeof(HFr) * B * 5 * sh.n);
+        d_gok = (uint8_t*)cpg_malloc(B);                 d_gfs = (uint8_t*)cpg_malloc((B / 2 + 1) * NF * 32);
         for (void* q : all()) if (!q) { release(); return fail("cpg_verify_batch: device allocation failed"); }
         cap = B;
         return 0;
@@ -461,10 +513,65 @@ struct Verifier {
                          d_derived + b0 * 96, d_t0 + b0};
         return launch(vd, nb);
     }
-    int device_check(size_t b0, size_t nb) {
+    int device_check_each(size_t b0, size_t nb) {
+        if (!nb) return 0;
         if (int rc = cpg_g1_msm_batched(d_bases + b0 * sh.NV, sh.NV, d_vs + b0 * sh.NV * 32, nb, sh.NV, var_window, d_var + b0)) return rc;
         if (int rc = cpg_g1_msm_fixed_batched(table, d_fs + b0 * sh.NF * 32, nb, 0, d_fix + b0)) return rc;
         return launch(AddFixedAndTest{d_var + b0, d_fix + b0, d_rej + b0, d_ok + b0}, nb);
+    }
+    // proofs [b0, b0 + nb), b0 a multiple of `group`: whole groups through one aggregated check each
+    // (provisional verdicts; recheck_failed_groups settles the failing ones), the tail proof by proof
+    int device_check(size_t b0, size_t nb) {
+        const size_t G = group;
+        const size_t ng = G > 1 ? nb / G : 0, g0 = G > 1 ? b0 / G : 0;
+        if (ng) {
+            if (int rc = cpg_g1_msm_batched(d_bases + b0 * sh.NV, G * sh.NV, d_vs + b0 * sh.NV * 32, ng, G * sh.NV, group_window, d_var + g0)) return rc;
+            if (int rc = launch(GroupSumFixed{(uint32_t)G, sh.NF, d_fs + b0 * sh.NF * 32, d_gfs + g0 * sh.NF * 32}, ng * sh.NF)) return rc;
+            if (int rc = cpg_g1_msm_fixed_batched(table, d_gfs + g0 * sh.NF * 32, ng, 0, d_fix + g0)) return rc;
+            if (int rc = launch(GroupTest{(uint32_t)G, d_var + g0, d_fix + g0, d_rej + b0, d_gok + g0, d_ok + b0}, ng)) return rc;
+        }
+        // the tail's scratch points share d_var/d_fix with the group results: indices >= b0 + ng*G > g0 + ng
+        return device_check_each(b0 + ng * G, nb - ng * G);
+    }
+    // Group size for the next batch.  Cost per proof relative to per-proof MSMs: the aggregated MSM over
+    // G*NV terms (measured at n = 128: 1, .85, .75, .68, .62, .60, .58 for G = 1..64) plus a per-proof
+    // re-check with the probability that the proof's group holds a bad proof, 1 - (1 - p)^G.
+    void adapt_group(double p_bad) {
+        static const double agg[7] = {1.0, 0.85, 0.75, 0.68, 0.62, 0.60, 0.58};
+        double best = 1e9; uint32_t bg = 1;
+        for (int k = 0; k < 7; k++) {
+            double G = (double)(1u << k);
+            double cost = agg[k] + (k ? 1.0 - std::pow(1.0 - p_bad, G) : 0.0);
+            if (cost < best - 1e-9) { best = cost; bg = 1u << k; }
+        }
+        group = bg < 2 ? 2 : bg;  // keep sampling the failure rate: at G = 1 nothing would be observed
+    }
+    // after every sub-batch has been joined: per-proof MSMs for the proofs of the failing groups
+    int recheck_failed_groups(size_t B) {
+        rechecked = 0;
+        const size_t G = group, ng = G > 1 ? B / G : 0;
+        if (!ng) return 0;
+        std::vector<uint8_t> gok(ng);
+        if (int rc = cpg_d2h(gok.data(), d_gok, ng)) return rc;
+        std::vector<uint32_t> idx;
+        for (size_t g = 0; g < ng; g++) if (!gok[g]) for (size_t k = 0; k < G; k++) idx.push_back((uint32_t)(g * G + k));
+        const size_t K = idx.size();
+        if (group_auto) adapt_group((double)(K / G) / (double)(ng * G));
+        if (!K) return 0;
+        rechecked = K;
+        Scratch sc;
+        uint32_t* d_idx = sc.get<uint32_t>(K); uint32_t* d_off = sc.get<uint32_t>(K);
+        uint8_t* vs2 = sc.get<uint8_t>(K * sh.NV * 32); uint8_t* fs2 = sc.get<uint8_t>(K * sh.NF * 32); uint8_t* rej2 = sc.get<uint8_t>(K);
+        Jac* var2 = sc.get<Jac>(K); Jac* fix2 = sc.get<Jac>(K);
+        if (!d_idx || !d_off || !vs2 || !fs2 || !rej2 || !var2 || !fix2) return fail("cpg_verify_batch: scratch allocation failed");
+        if (int rc = cpg_h2d(d_idx, idx.data(), K * 4)) return rc;
+        if (int rc = launch(GatherRows{d_idx, sh.NV * 2, (const Row16*)d_vs, (Row16*)vs2}, K * sh.NV * 2)) return rc;
+        if (int rc = launch(GatherRows{d_idx, sh.NF * 2, (const Row16*)d_fs, (Row16*)fs2}, K * sh.NF * 2)) return rc;
+        if (int rc = launch(GatherMeta{d_idx, sh.NV, d_rej, d_off, rej2}, K)) return rc;
+        if (int rc = cpg_g1_msm_batched_off(d_bases, d_off, vs2, K, sh.NV, var_window, var2)) return rc;
+        if (int rc = cpg_g1_msm_fixed_batched(table, fs2, K, 0, fix2)) return rc;
+        if (int rc = launch(ScatterVerdicts{d_idx, var2, fix2, rej2, d_ok}, K)) return rc;
+        return cpg_sync();                                               // idx (host) was read by an async copy
     }
     // Transcript on the device: nothing crosses PCIe between the stages.  The batch is cut into
     // sub-batches, each enqueued on its own stream, so the latency-bound kernels of one sub-batch
@@ -475,7 +582,8 @@ struct Verifier {
         VBuffers vb = device_buffers();
         size_t S = nstreams > 0 ? (size_t)nstreams : 1;
         if (B < 64 * S) S = 1;
-        size_t per = ((B + S - 1) / S + 31) / 32 * 32;      // warps of BucketAccumulate hold 32 MSMs
+        size_t align = group > 32 ? group : 32;             // warps of BucketAccumulate hold 32 MSMs; groups do not straddle sub-batches
+        size_t per = ((B + S - 1) / S + align - 1) / align * align;
         int rc = 0;
         size_t si = 0;
         for (size_t b0 = 0; b0 < B && !rc; b0 += per, si++) {
@@ -506,7 +614,9 @@ struct Verifier {
             if (!rc) rc = launch<64>(VerifyPhase2{sh, L, vb, b0}, nb);
             if (!rc) rc = device_check(b0, nb);
         }
-        return join_streams(rc);
+        rc = join_streams(rc);
+        if (!rc) rc = recheck_failed_groups(B);
+        return rc;
     }
 };
 
@@ -578,6 +688,17 @@ int cpg_verifier_set_streams(void* handle, int nstreams) {
     ((Verifier*)handle)->nstreams = nstreams;
     return 0;
 }
+int cpg_verifier_set_group(void* handle, int group, int group_window) {
+    if (!handle) return fail("cpg_verifier_set_group: null verifier");
+    if (group < 0 || group > 4096 || (group & (group - 1))) return fail("cpg_verifier_set_group: the group size must be 0 (adaptive) or a power of two in [1, 4096]");
+    if (group_window < 0 || group_window > 16) return fail("cpg_verifier_set_group: bad window");
+    Verifier& v = *(Verifier*)handle;
+    v.group_auto = group == 0;
+    v.group = group ? (uint32_t)group : 16; v.group_window = group_window;
+    return 0;
+}
+int cpg_verifier_group(const void* handle) { return handle ? (int)((const Verifier*)handle)->group : 0; }
+size_t cpg_verifier_rechecked(const void* handle) { return handle ? ((const Verifier*)handle)->rechecked : 0; }
 int cpg_verifier_set_transcript(void* handle, int on_device) { if (!handle) return 1; ((Verifier*)handle)->transcript_on_device = on_device ? 1 : 0; return 0; }
 
 /* inputs : [B][4*ell*48]   vec_R | vec_S | vec_T | vec_U   (tracker halves, whisk_interface.py:96-100)
@@ -636,6 +757,7 @@ int cpg_verify_batch(void* handle, const uint8_t* inputs, const uint8_t* proofs,
     if (int rc = cpg_h2d(v.d_fs, fs.data(), fs.size())) return rc;
     if (int rc = cpg_h2d(v.d_rej, reject.data(), B)) return rc;
     if (int rc = v.device_check(0, B)) return rc;
+    if (int rc = v.recheck_failed_groups(B)) return rc;
     return cpg_d2h(verdicts, v.d_ok, B);
 }
 
@@ -655,6 +777,7 @@ int cpg_verify_replay_device(void* handle, uint8_t* verdicts) {
         if (int rc = v.device_decode(0, v.lastB)) return rc;
         if (int rc = v.device_derive(0, v.lastB, L)) return rc;
         if (int rc = v.device_check(0, v.lastB)) return rc;
+        if (int rc = v.recheck_failed_groups(v.lastB)) return rc;
     }
     if (verdicts) return cpg_d2h(verdicts, v.d_ok, v.lastB);
     return 0;

@@ -79,6 +79,9 @@ _SIGS = {
     "cpg_verifier_set_window": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "cpg_verifier_set_transcript": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "cpg_verifier_set_streams": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "cpg_verifier_set_group": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int]),
+    "cpg_verifier_rechecked": (_c.c_size_t, [_c.c_void_p]),
+    "cpg_verifier_group": (_c.c_int, [_c.c_void_p]),
     "cpg_verify_batch": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_char_p, _c.c_size_t, _c.c_char_p]),
     "cpg_verify_replay_device": (_c.c_int, [_c.c_void_p, _c.c_char_p]),
     "cpg_prover_create": (_c.c_void_p, [_c.c_char_p, _c.c_size_t, _c.c_size_t, _c.c_int]),
@@ -86,6 +89,7 @@ _SIGS = {
     "cpg_prover_proof_bytes": (_c.c_size_t, [_c.c_void_p]),
     "cpg_prover_rand_scalars": (_c.c_size_t, [_c.c_void_p]),
     "cpg_prover_set_window": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "cpg_prover_set_lanes": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_size_t]),
     "cpg_prove_replay_device": (_c.c_int, [_c.c_void_p]),
     "cpg_prove_batch": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_char_p, _c.c_char_p, _c.c_size_t, _c.c_char_p, _c.c_char_p, _c.c_char_p]),
     "cpg_bench_int_pipe": (_c.c_int, [_c.c_int, _c.c_uint64, _c.POINTER(_c.c_double), _c.POINTER(_c.c_float)]),

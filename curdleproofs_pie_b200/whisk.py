@@ -38,6 +38,17 @@ class BatchVerifier:
     def set_streams(self, n):
         self.lib.check(self.lib.c.cpg_verifier_set_streams(self.handle, int(n)), "cpg_verifier_set_streams")
 
+    def set_group(self, group, window=0):
+        """Cross-proof aggregation: `group` consecutive proofs share one MSM; failing groups are re-checked
+        proof by proof (verdicts stay exact).  1 = off, 0 = adaptive (re-picked after every batch)."""
+        self.lib.check(self.lib.c.cpg_verifier_set_group(self.handle, int(group), int(window)), "cpg_verifier_set_group")
+
+    def group(self):
+        return int(self.lib.c.cpg_verifier_group(self.handle))
+
+    def rechecked(self):
+        return int(self.lib.c.cpg_verifier_rechecked(self.handle))
+
     def verify_raw(self, inputs, proofs, B):
         """inputs: B*input_len bytes, proofs: B*proof_len bytes -> bytes of B verdicts."""
         out = ctypes.create_string_buffer(max(1, B))
@@ -127,6 +138,9 @@ class BatchProver:
 
     def set_window(self, c):
         self.lib.check(self.lib.c.cpg_prover_set_window(self.handle, int(c)), "cpg_prover_set_window")
+
+    def set_lanes(self, k, min_proofs_per_lane=0):
+        self.lib.check(self.lib.c.cpg_prover_set_lanes(self.handle, int(k), int(min_proofs_per_lane)), "cpg_prover_set_lanes")
 
     def draw_randomness(self, rng):
         """Blinders for ONE proof in the reference's draw order, from a `random`-like

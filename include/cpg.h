@@ -147,6 +147,18 @@ int cpg_verifier_set_window(void* verifier, int var_window);
 int cpg_verifier_set_transcript(void* verifier, int on_device);
 /* sub-batches in flight on separate CUDA streams (1..8, default 2; device transcript only) */
 int cpg_verifier_set_streams(void* verifier, int nstreams);
+/* Cross-proof aggregation: `group` (a power of two, default 1 = off) consecutive proofs
+ * are accepted by ONE MSM over their group*NV variable bases and ONE fixed-base MSM over their summed
+ * CRS coefficients.  (Each proof's batching weights are already independent and secret-keyed, so the
+ * sum of the proofs' relations is a random linear combination of all their checks.)  Groups that fail
+ * are re-checked proof by proof: verdicts stay per proof and exact.
+ * group = 0: adaptive - the library re-picks the group size after every batch from the observed rate
+ * of failing proofs (cpg_verifier_group reads the current size).  group_window = 0 picks the window of
+ * the aggregated MSM from its size.  cpg_verifier_rechecked = proofs of the last batch that took the
+ * per-proof fallback. */
+int cpg_verifier_set_group(void* verifier, int group, int group_window);
+size_t cpg_verifier_rechecked(const void* verifier);
+int cpg_verifier_group(const void* verifier);
 int cpg_verify_batch(void* verifier, const uint8_t* inputs, const uint8_t* proofs, size_t B, uint8_t* verdicts);
 /* re-run the device side (decompress, D/A', MSM, test) of the last batch on its resident inputs */
 int cpg_verify_replay_device(void* verifier, uint8_t* verdicts_or_null);
@@ -170,6 +182,9 @@ int cpg_prover_free(void* prover);
 size_t cpg_prover_proof_bytes(const void* prover);
 size_t cpg_prover_rand_scalars(const void* prover);
 int cpg_prover_set_window(void* prover, int var_window);
+/* sub-batches ("lanes", 1..4, default 2) whose rounds are issued alternately on separate streams: the
+ * one-thread-per-proof transcript kernels of one lane run under the MSM kernels of the other */
+int cpg_prover_set_lanes(void* prover, int nlanes, size_t min_proofs_per_lane /* 0 = 256: smaller batches are not split */);
 int cpg_prove_replay_device(void* prover);   /* device side of the last batch again, inputs resident */
 int cpg_prove_batch(void* prover, const uint8_t* inputs, const uint32_t* perms, const uint8_t* ks, const uint8_t* rand,
                     size_t B, uint8_t* out_tu, uint8_t* out_proofs, uint8_t* status);

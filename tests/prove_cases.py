@@ -25,10 +25,12 @@ def replay_rng(case, prover):
     return perm, k, rand
 
 
-def check_prove(lib, name, copies=1, fixed_window=0, window=0):
+def check_prove(lib, name, copies=1, fixed_window=0, window=0, lanes=None):
     case = sc.load_case(name)
     ell = case["N"] - 4
     prover = whisk.BatchProver(bytes.fromhex(case["crs"]), ell, fixed_window=fixed_window, lib=lib)
+    if lanes:
+        prover.set_lanes(*lanes)
     if window:
         prover.set_window(window)
     perm, k, rand = replay_rng(case, prover)
@@ -44,13 +46,15 @@ def check_prove(lib, name, copies=1, fixed_window=0, window=0):
     return res
 
 
-def check_prove_then_verify(lib, name, B=3, fixed_window=0):
+def check_prove_then_verify(lib, name, B=3, fixed_window=0, lanes=None):
     """Fresh randomness per lane (different permutations and k): every proof must verify, and must stop
     verifying when paired with another lane's trackers."""
     case = sc.load_case(name)
     ell = case["N"] - 4
     crs = bytes.fromhex(case["crs"])
     prover = whisk.BatchProver(crs, ell, fixed_window=fixed_window, lib=lib)
+    if lanes:
+        prover.set_lanes(*lanes)
     rng = random.Random(2718)
     pre = b"".join(bytes.fromhex(h) for h in case["vec_R"] + case["vec_S"])
     perms, ks, rands = [], [], []

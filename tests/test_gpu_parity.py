@@ -132,6 +132,14 @@ def test_verify_batch(gpu_lib, name, copies, window):
     vc.check_batch(gpu_lib, name, copies=min(copies, 2), window=window, transcript_on_device=False)
 
 
+@pytest.mark.parametrize("name,copies,group", [("shuffle_N8_seed1234.json", 1, 2), ("shuffle_N16_seed77.json", 12, 8),
+                                               ("shuffle_N128_seed4096.json", 6, 16), ("shuffle_N64_seed2024.json", 40, 32)])
+def test_verify_batch_cross_proof_groups(gpu_lib, name, copies, group):
+    vc.check_batch(gpu_lib, name, copies=copies, transcript_on_device=True, group=group)
+    if copies <= 6:
+        vc.check_batch(gpu_lib, name, copies=2, transcript_on_device=False, group=group)
+
+
 def test_verify_replay_matches(gpu_lib):
     import ctypes
 
@@ -160,6 +168,12 @@ def test_prove_batch_bytes_equal_reference(gpu_lib, name, copies):
 
 def test_prove_then_verify_full_size(gpu_lib):
     prc.check_prove_then_verify(gpu_lib, "shuffle_N128_seed4096.json", B=96)
+
+
+def test_prove_sub_batches_on_stream_lanes(gpu_lib):
+    prc.check_prove(gpu_lib, "shuffle_N64_seed2024.json", copies=7, lanes=(3, 2))
+    prc.check_prove_then_verify(gpu_lib, "shuffle_N128_seed4096.json", B=96, lanes=(4, 16))
+    prc.check_prove_then_verify(gpu_lib, "shuffle_N8_seed1234.json", B=600)          # default: 2 lanes from 512 proofs
 
 
 @pytest.mark.parametrize("n,window", [(5000, 0), (3000, 10), (1 << 16, 13), (100000, 0)])

@@ -13,3 +13,9 @@ def test_prove_bytes_N16_two_lanes(seam_lib):
 
 def test_prove_then_verify_N8(seam_lib):
     pc.check_prove_then_verify(seam_lib, "shuffle_N8_seed1234.json", B=3, fixed_window=4)
+
+
+def test_prove_sub_batches_on_stream_lanes(seam_lib):
+    """the batch split over 3 lanes of unequal size (5 = 1 + 2 + 2): bytes still equal the reference's"""
+    pc.check_prove(seam_lib, "shuffle_N8_seed1234.json", copies=5, fixed_window=4, lanes=(3, 1))
+    pc.check_prove_then_verify(seam_lib, "shuffle_N8_seed1234.json", B=4, fixed_window=4, lanes=(2, 2))

@@ -16,3 +16,10 @@ def test_verify_batch_N8(seam_lib, on_device):
 @pytest.mark.parametrize("on_device", [True, False])
 def test_verify_batch_N16_two_copies(seam_lib, on_device):
     vc.check_batch(seam_lib, "shuffle_N16_seed77.json", copies=2, window=4, transcript_on_device=on_device, fixed_window=5)
+
+
+@pytest.mark.parametrize("on_device,group", [(True, 2), (False, 4)])
+def test_verify_batch_cross_proof_groups(seam_lib, on_device, group):
+    """SURVEY 8 f-2: groups of proofs share one aggregated MSM, failing groups fall back to per-proof checks;
+    the verdict of every lane (honest and corrupted variants side by side) still equals the reference's"""
+    vc.check_batch(seam_lib, "shuffle_N8_seed1234.json", transcript_on_device=on_device, fixed_window=4, group=group)

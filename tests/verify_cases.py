@@ -38,11 +38,12 @@ def variants(case):
     return out
 
 
-def check_batch(lib, name, copies=1, window=0, transcript_on_device=True, fixed_window=0):
+def check_batch(lib, name, copies=1, window=0, transcript_on_device=True, fixed_window=0, group=1):
     case = sc.load_case(name)
     ell = case["N"] - 4
     ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), ell, fixed_window=fixed_window, lib=lib)
     ver.set_transcript(transcript_on_device)
+    ver.set_group(group)
     if window:
         ver.set_window(window)
     vs = variants(case) * copies
@@ -52,4 +53,15 @@ def check_batch(lib, name, copies=1, window=0, transcript_on_device=True, fixed_
     # wrong lengths are rejected without touching the device result of the others
     got = ver.verify([vs[0][1], vs[0][1][:-1], vs[0][1]], [vs[0][2], vs[0][2], vs[0][2][:-1]])
     assert got == [True, False, False]
+    if group > 1:
+        # all-honest groups are settled by the aggregated check alone; one bad lane sends only its group back
+        honest = vs[0]
+        nb = 3 * group + 1
+        assert ver.verify([honest[1]] * nb, [honest[2]] * nb) == [True] * nb
+        assert ver.rechecked() == 0
+        bad = vs[1]
+        ins = [honest[1]] * nb; prs = [honest[2]] * nb
+        ins[group + 1], prs[group + 1] = bad[1], bad[2]
+        assert ver.verify(ins, prs) == [i != group + 1 for i in range(nb)]
+        assert ver.rechecked() == group
     ver.close()
