@@ -42,7 +42,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "dropin")]
 
 R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
-MAC_PER_MODMUL = 300          # 12-limb Montgomery product: 2*12^2 + 12
+MAC_PER_MODMUL = 300     # 12-limb Montgomery product: 2*12^2 + 12
+SQR_MAC = 222            # dedicated Montgomery squaring: 78 product + 144 reduction MACs
 
 
 def msm_model(n, c):
@@ -234,28 +235,54 @@ def run_ours_verify(args, rank, world, dist):
 
     peak_mac, _ = lib.bench_int_pipe(0, 20000)
     fq_rate, _ = lib.bench_int_pipe(2, 2000)
+    ver_rechecked, ver_group = ver.rechecked(), ver.group()
+    # ---- algorithmic Fq products per step, kernel by kernel (DESIGN.md "work model") ----
+    # decompress: x^3 + 4, the 376-squaring / 81-product square-root chain, y^2 check, Montgomery in/out
+    DEC_MAC = 378 * SQR_MAC + 86 * MAC_PER_MODMUL
     model = msm_model(NV, c)
-    ba = prof.get("BucketAccumulate", {"ms": 0.0, "launches": 1})
-    ba_ms = ba["ms"] / max(1, ba["launches"])
-    ba_macs = B * model["bucket_accumulate"] * MAC_PER_MODMUL
-    achieved = ba_macs / (ba_ms * 1e-3) if ba_ms else 0.0
+    per_proof = B if ver_group <= 1 else ver_rechecked                 # proofs on their own MSM
+    sub = B                                                            # the per-kernel pass runs on ONE stream: one sub-batch
+    if ver_group > 1:
+        cg = args.group_window or int(lib.c.cpg_msm_pick_window_batched(max(1, sub // ver_group), ver_group * NV))
+        gmodel = msm_model(ver_group * NV, cg)
+        ngroups = B // ver_group
+    else:
+        cg, gmodel, ngroups = None, {"bucket_accumulate": 0, "window_reduce": 0, "horner": 0}, 0
+    alg_mac = {
+        "Decompress": B * (NV - 1) * DEC_MAC,
+        "BucketAccumulate": (per_proof * model["bucket_accumulate"] + ngroups * gmodel["bucket_accumulate"]) * MAC_PER_MODMUL,
+        "WindowReduce": per_proof * model["window_reduce"] * MAC_PER_MODMUL,
+        "ReduceLevel": ngroups * gmodel["window_reduce"] * MAC_PER_MODMUL,
+        "FixedMsmWindow": (per_proof + ngroups) * NF * 22 * 10 * MAC_PER_MODMUL + B * 2 * 32 * 10 * MAC_PER_MODMUL,
+    }
+    kernels = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        ms_step = v["ms"] / args.steps
+        ent = {"ms_per_step": ms_step, "launches_per_step": v["launches"] / args.steps}
+        if k in alg_mac and ms_step > 0:
+            ent["achieved_gmac_s"] = alg_mac[k] / (ms_step * 1e-3) / 1e9
+            ent["frac"] = alg_mac[k] / (ms_step * 1e-3) / peak_mac if peak_mac else None
+        kernels[k] = ent
     total_kernel_ms = sum(v["ms"] for v in prof.values())
-    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
-    # whole device pass in algorithmic Fq products: var MSM + fixed MSM (W=32 @ c=8: nb*W madds) + decompress (~470) + D (2 scalar-muls)
-    modmul_step = B * (model["bucket_accumulate"] + model["window_reduce"] + model["horner"] + NF * 32 * 10 + (NV - 1) * 470 + 2 * 2900)
+    dom = max(prof.items(), key=lambda kv: kv[1]["ms"])[0]
+    dom_ms = prof[dom]["ms"] / args.steps
+    dom_launch_ms = prof[dom]["ms"] / max(1, prof[dom]["launches"])
+    dom_mac_launch = alg_mac.get(dom, 0) * args.steps / max(1, prof[dom]["launches"])
+    achieved = dom_mac_launch / (dom_launch_ms * 1e-3) if dom_launch_ms else 0.0
+    # whole device pass in algorithmic MACs: the kernels above + Horner + D (2 scalar-muls per proof)
+    mac_step = sum(alg_mac.values()) + (per_proof * model["horner"] + ngroups * gmodel["horner"] + B * 2 * 2900) * MAC_PER_MODMUL
     roofline = {
-        "bound": "int_pipe", "kernel": "BucketAccumulate", "achieved": achieved / 1e9, "peak": peak_mac / 1e9, "unit": "GMAC/s",
+        "bound": "int_pipe", "kernel": dom, "achieved": achieved / 1e9, "peak": peak_mac / 1e9, "unit": "GMAC/s",
         "frac": achieved / peak_mac if peak_mac else None, "traffic": None,
         "peak_source": "data-dependent IMAD.WIDE.U32 chains measured in this run (32 lanes/clk/SM; MEASURED_PEAKS.json has no integer-pipe entry)",
-        "kernel_ms_per_launch": ba_ms, "kernel_share_of_step": ba["ms"] / total_kernel_ms if total_kernel_ms else None,
-        "algorithmic_modmul_per_launch": B * model["bucket_accumulate"], "mac_per_modmul": MAC_PER_MODMUL,
-        "fq_mul_chain_per_s": fq_rate, "whole_step_modmul_per_s": modmul_step / (ms / args.steps * 1e-3),
-        "whole_step_frac_of_peak": modmul_step * MAC_PER_MODMUL / (ms / args.steps * 1e-3) / peak_mac if peak_mac else None,
-        "dominant_by_time": dom[0],
+        "kernel_ms_per_launch": dom_launch_ms, "kernel_share_of_step": dom_ms * args.steps / total_kernel_ms if total_kernel_ms else None,
+        "algorithmic_mac_per_launch": dom_mac_launch, "mac_per_modmul": MAC_PER_MODMUL, "mac_per_modsqr": SQR_MAC,
+        "fq_mul_chain_per_s": fq_rate, "whole_step_mac_per_s": mac_step / (ms / args.steps * 1e-3),
+        "whole_step_frac_of_peak": mac_step / (ms / args.steps * 1e-3) / peak_mac if peak_mac else None,
+        "group_window": cg, "kernels": kernels,
         "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
     }
     cpu = cpu_verify_rate(case, sample=args.cpu_sample_verify, procs=1)
-    ver_rechecked, ver_group = ver.rechecked(), ver.group()
     prove_side = None
     if args.prove_batch and world == 1:
         ver.close()
@@ -354,16 +381,6 @@ def run_reference_verify(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
-def prove_model(n, ell, lg, c_var, c_fix=12):
-    """Algorithmic Fq products of one proof on the linearised prover."""
-    nout, nf = 21 + 10 * lg, n + 3
-    wf = (256 + c_fix - 1) // c_fix
-    var = msm_model(ell, c_var)
-    nvar = 6 + 2 + 4 * lg
-    return {"fixed_msm": nout * nf * wf * 10, "var_msm": nvar * (var["bucket_accumulate"] + var["window_reduce"] + var["horner"]),
-            "shuffle": 2 * ell * 2900, "decompress": 2 * ell * 400, "compress": (nout + 2 * ell) * 470}
-
-
 def make_prove_batch(case, prover, B, seed):
     import random as pyrandom
 
@@ -420,15 +437,23 @@ def measure_prove(args, lib, case, B, steps, dist=None):
     for _ in range(2):
         step_dev()
     lib.sync()
-    lib.profile(True)
     launches0 = lib.launch_count()
     lib.timer_start()
     for _ in range(steps):
         step_dev()
     ms = lib.timer_stop()
     launches = lib.launch_count() - launches0
+    # per-kernel times: a separate pass with ONE lane (with several lanes the kernels overlap on streams)
+    prover.set_lanes(1)
+    step_e2e()
+    lib.sync()
+    lib.profile(True)
+    for _ in range(steps):
+        step_dev()
     prof = lib.profile_report()
     lib.profile(False)
+    prover.set_lanes(args.prove_lanes)
+    step_e2e()
     t0 = time.perf_counter()
     for _ in range(steps):
         step_e2e()
@@ -503,13 +528,34 @@ def run_ours_prove(args, rank, world, dist):
     if rank != 0:
         return None
     peak_mac, _ = lib.bench_int_pipe(0, 20000)
-    model = prove_model(128, 124, 7, r["window"])
-    total_modmul = B * sum(model.values())
     prof = r["prof"]
-    fm = prof.get("FixedMsmWindow", {"ms": 0.0, "launches": 1})
-    fm_ms_step = fm["ms"] / args.steps
-    fm_macs = B * model["fixed_msm"] * MAC_PER_MODMUL
+    # Algorithmic MACs per step.  Variable-base MSMs: R', S', B_t, B_u over all ell leaves and, per SameMSM
+    # round, L_T L_U R_T R_U over half of them (a fold only rescales leaf weights): 4 ell + 4 lg ell/2 non-zero
+    # terms per proof in 4 + 4 lg MSM instances.  The fixed-base kernel skips structurally zero coefficients,
+    # whose count is not modelled here, so it carries no roofline entry and the whole-step figure is a lower bound.
+    ell_, lg_ = 124, 7
+    var = msm_model(1, r["window"])
+    var_terms, var_inst = 4 * ell_ + 4 * lg_ * (ell_ // 2), 4 + 4 * lg_
+    DEC_MAC = 378 * SQR_MAC + 86 * MAC_PER_MODMUL
+    alg_mac = {
+        "BucketAccumulate": B * var_terms * var["W"] * 10 * MAC_PER_MODMUL,
+        "WindowReduce": B * var_inst * var["window_reduce"] * MAC_PER_MODMUL,
+        "Horner": B * var_inst * var["horner"] * MAC_PER_MODMUL,
+        "ProveShuffle": B * 2 * ell_ * (2900 * MAC_PER_MODMUL + DEC_MAC),
+        "Decompress": B * 2 * ell_ * DEC_MAC,
+    }
+    kernels = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        ms_step = v["ms"] / args.steps
+        ent = {"ms_per_step": ms_step, "launches_per_step": v["launches"] / args.steps}
+        if k in alg_mac and ms_step > 0:
+            ent["achieved_gmac_s"] = alg_mac[k] / (ms_step * 1e-3) / 1e9
+            ent["frac"] = alg_mac[k] / (ms_step * 1e-3) / peak_mac if peak_mac else None
+        kernels[k] = ent
     total_kernel_ms = sum(v["ms"] for v in prof.values())
+    ba = prof.get("BucketAccumulate", {"ms": 0.0, "launches": 1})
+    ba_launch_ms = ba["ms"] / max(1, ba["launches"])
+    ba_mac_launch = alg_mac["BucketAccumulate"] * args.steps / max(1, ba["launches"])
     cpu = cpu_prove_rate(case, sample=args.cpu_sample_prove, procs=1)
     total = B * world
     return {
@@ -523,11 +569,13 @@ def run_ours_prove(args, rank, world, dist):
         "e2e": {"value": total * args.steps / (ms_e2e * 1e-3), "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
         "gpu_launches": r["launches"], "clocks": clocks,
-        "roofline": {"bound": "int_pipe", "kernel": "FixedMsmWindow", "achieved": fm_macs / (fm_ms_step * 1e-3) / 1e9 if fm_ms_step else 0.0,
-                     "peak": peak_mac / 1e9, "unit": "GMAC/s", "frac": (fm_macs / (fm_ms_step * 1e-3) / peak_mac) if fm_ms_step and peak_mac else None,
-                     "traffic": None, "kernel_share_of_step": fm["ms"] / total_kernel_ms if total_kernel_ms else None,
-                     "whole_step_frac_of_peak": total_modmul * MAC_PER_MODMUL / (ms / args.steps * 1e-3) / peak_mac if peak_mac else None,
+        "roofline": {"bound": "int_pipe", "kernel": "BucketAccumulate", "achieved": ba_mac_launch / (ba_launch_ms * 1e-3) / 1e9 if ba_launch_ms else 0.0,
+                     "peak": peak_mac / 1e9, "unit": "GMAC/s", "frac": (ba_mac_launch / (ba_launch_ms * 1e-3) / peak_mac) if ba_launch_ms and peak_mac else None,
+                     "traffic": None, "kernel_ms_per_launch": ba_launch_ms, "algorithmic_mac_per_launch": ba_mac_launch,
+                     "kernel_share_of_step": ba["ms"] / total_kernel_ms if total_kernel_ms else None,
+                     "whole_step_frac_of_peak_lower_bound": sum(alg_mac.values()) / (ms / args.steps * 1e-3) / peak_mac if peak_mac else None,
                      "peak_source": "data-dependent IMAD.WIDE.U32 chains measured in this run",
+                     "kernels": kernels,
                      "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}},
         "cpu_baseline": cpu,
     }

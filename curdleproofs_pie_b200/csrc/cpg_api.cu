@@ -102,6 +102,13 @@ int launch(const F& f, uint64_t n) {
     g_launches++;
     return ck(cudaGetLastError(), "kernel launch");
 }
+// Point-arithmetic kernels: 3 resident blocks per SM (<= 168 registers, 12 warps) hide the dependent
+// IMAD.WIDE chains better than 2 blocks of 240 registers (Decompress 70.8 -> 65.3 ms per 4.8 M points,
+// verification +8 %).  Not for the scalar-multiplication kernels (jac_mul spills at 168: ProveShuffle
+// 122 -> 140 ms).  CPG_OCC1=1 restores the compiler's own register budget for A/B runs.
+bool occ1() { static const bool v = getenv("CPG_OCC1") != nullptr; return v; }
+template <class F>
+int launch_occ(const F& f, uint64_t n) { return occ1() ? launch<128, 1>(f, n) : launch<128, 3>(f, n); }
 int launch_sort_digits(const SortDigits& f, uint64_t n) {
     const MsmShape& s = f.s;
     size_t smem = (size_t)(s.NB + 1) * SORT_BLOCK * 4 + (size_t)s.NB * SORT_BLOCK * 2;
@@ -135,6 +142,8 @@ int launch(const F& f, uint64_t n) {
     for (int64_t t = 0; t < (int64_t)n; t++) f((uint64_t)t);
     return 0;
 }
+template <class F>
+int launch_occ(const F& f, uint64_t n) { return launch(f, n); }
 int launch_sort_digits(const SortDigits& f, uint64_t n) { return launch(f, n); }
 void* scratch_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void scratch_free(void* p) { free(p); }
@@ -443,11 +452,11 @@ int cpg_profile_report(char* buf, size_t cap) {
 /* ---- serialisation ---- */
 int cpg_g1_decompress(const uint8_t* d_in, size_t k, int check, void* d_out, uint8_t* d_err) {
     NEED_INIT();
-    return launch(Decompress{d_in, check, (Aff*)d_out, d_err}, k);
+    return launch_occ(Decompress{d_in, check, (Aff*)d_out, d_err}, k);
 }
 int cpg_g1_compress(const void* d_jac, size_t k, uint8_t* d_out) {
     NEED_INIT();
-    return launch(CompressJac{(const Jac*)d_jac, d_out}, k);
+    return launch_occ(CompressJac{(const Jac*)d_jac, d_out}, k);
 }
 int cpg_g1_compress_aff(const void* d_aff, size_t k, uint8_t* d_out) {
     NEED_INIT();
@@ -459,7 +468,7 @@ int cpg_g1_aff_to_jac(const void* d_aff, size_t k, void* d_out) {
 }
 int cpg_g1_jac_to_aff(const void* d_jac, size_t k, void* d_out) {
     NEED_INIT();
-    return launch(JacToAff{(const Jac*)d_jac, (Aff*)d_out}, k);
+    return launch_occ(JacToAff{(const Jac*)d_jac, (Aff*)d_out}, k);
 }
 int cpg_g1_generator(void* d_out) {
     NEED_INIT();
@@ -528,6 +537,13 @@ int cpg_msm_window_count(size_t n, int window) {
     uint32_t c = window > 0 ? (uint32_t)window : pick_window_large(n ? n : 1);
     return (int)windows_for(c);
 }
+/* window width cpg_g1_msm_batched picks (window = 0) for B MSMs of n terms each */
+int cpg_msm_pick_window_batched(size_t B, size_t n) {
+    if (!n) n = 1;
+    if (!B) B = 1;
+    const bool few = g_msm_path == 0 ? B * 32 < 8192 : g_msm_path == 2;
+    return (int)((few || n > 2048) ? pick_window_large(n, B) : pick_window(n));
+}
 int cpg_msm_force_path(int path) {
     if (path < 0 || path > 2) return fail("cpg_msm_force_path: 0 (by shape), 1 (per-window threads) or 2 (per-term threads)");
     g_msm_path = path;
@@ -564,7 +580,7 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
     // thousands of small MSMs: per-(msm, window) threads; few (or big) MSMs: per-term threads with atomics,
     // buckets ordered by list length, level-wise window reduction
     const bool few = g_msm_path == 0 ? B * 32 < 8192 : g_msm_path == 2;
-    uint32_t c = window > 0 ? (uint32_t)window : ((few || n > 2048) ? pick_window_large(n, B) : pick_window(n));
+    uint32_t c = window > 0 ? (uint32_t)window : (uint32_t)cpg_msm_pick_window_batched(B, n);
     if (c < 2 || c > 16) return fail("cpg_g1_msm_batched: window must be in [2, 16]");
     Recode rc = make_recode(c);
     const bool slice = wn != 0;
@@ -613,8 +629,8 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
             if (int r = launch_sort_digits(SortDigits{s, dig, boff, sorted, rank}, BW)) return r;
             uint64_t nthreads = (((uint64_t)nb + 31) / 32) * 32 * s.wn * s.NB;
             if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, rank, nullptr, BW, buckets}, nthreads)) return r;
-            if (int r = launch(WindowReduce{s, buckets, wsum}, BW)) return r;
-            if (int r = launch(Horner{s, wsum, (Jac*)d_out + b0}, nb)) return r;
+            if (int r = launch_occ(WindowReduce{s, buckets, wsum}, BW)) return r;
+            if (int r = launch_occ(Horner{s, wsum, (Jac*)d_out + b0}, nb)) return r;
             continue;
         }
         // counting sort of the digits: counts (atomics), three-pass scan, scatter
@@ -644,7 +660,7 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
         uint32_t len = s.NB;
         for (uint32_t j = 0; j < nlev; j++) {
             uint32_t ch = chs[j];
-            if (int r = launch(ReduceLevel{j + 1, ch, len, BW, in, out}, (uint64_t)(j + 1) * BW * (len / ch))) return r;
+            if (int r = launch_occ(ReduceLevel{j + 1, ch, len, BW, in, out}, (uint64_t)(j + 1) * BW * (len / ch))) return r;
             len /= ch; in = out; out = (out == lvA) ? lvB : lvA;
         }
         ReduceFinal fin; fin.levels = nlev; fin.BW = BW; fin.in = in; fin.wsum = wsum;
@@ -671,7 +687,7 @@ void* cpg_fixed_table_create(const void* d_bases, size_t nb, int window) {
     Jac* rows = (Jac*)cpg_malloc(entries * sizeof(Jac));
     int rc = (!t->table || !rows) ? fail("cpg_fixed_table_create: allocation failed") : 0;
     if (!rc) rc = launch(FixedTableRows{t->s, (const Aff*)d_bases, rows}, (uint64_t)nb * t->s.W);
-    if (!rc) rc = launch(JacToAff{rows, t->table}, entries);
+    if (!rc) rc = launch_occ(JacToAff{rows, t->table}, entries);
     if (!rc) rc = cpg_sync();
     cpg_free(rows);
     if (rc) { cpg_free(t->table); delete t; return nullptr; }
@@ -696,7 +712,7 @@ int cpg_g1_msm_fixed_batched(const void* table, const uint8_t* d_scalars, size_t
     Xyzz* partial = sc.get<Xyzz>((uint64_t)B * t->s.W);
     if (!partial) return fail("cpg_g1_msm_fixed_batched: scratch allocation failed");
     if (int r = launch<128, 3>(FixedMsmWindow{t->s, rc, (uint32_t)B, t->table, (const uint32_t*)d_scalars, partial}, (((uint64_t)B + 31) / 32) * 32 * t->s.W)) return r;
-    return launch(SumWindows{t->s.W, partial, (Jac*)d_out, accumulate}, B);
+    return launch_occ(SumWindows{t->s.W, partial, (Jac*)d_out, accumulate}, B);
 }
 
 /* ---- Fr vectors ---- */

@@ -601,7 +601,7 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
             if (pl.scale_kind[i] == 1) { pc.scale[i] = (const uint32_t*)p.d_k; pc.scale_stride[i] = 8; }
             if (pl.scale_kind[i] == 2) { pc.scale[i] = (const uint32_t*)p.d_rand + (size_t)RO.r_k * 8; pc.scale_stride[i] = sh.NR * 8; }
         }
-        if (int rc = launch(pc, B * pl.nout)) return rc;
+        if (int rc = launch_occ(pc, B * pl.nout)) return rc;
     }
     return 0;
 }

@@ -109,6 +109,7 @@ int cpg_msm_force_path(int path);
  * exchanged by one small all-gather (W * 144 B in total), and every rank finishes with
  * sum_w 2^(c w) S_w.  `window` must be the same on every rank (cpg_msm_pick_window(n)). */
 int cpg_msm_pick_window(size_t n);
+int cpg_msm_pick_window_batched(size_t B, size_t n);   /* what cpg_g1_msm_batched(window = 0) uses for B MSMs of n terms */
 int cpg_msm_window_count(size_t n, int window);
 int cpg_g1_msm_window_sums(const void* d_bases_aff, const uint8_t* d_scalars, size_t n, int window,
                            int w_begin, int w_end, void* d_out_jac);

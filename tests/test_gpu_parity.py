@@ -179,3 +179,11 @@ def test_prove_sub_batches_on_stream_lanes(gpu_lib):
 @pytest.mark.parametrize("n,window", [(5000, 0), (3000, 10), (1 << 16, 13), (100000, 0)])
 def test_msm_large_and_window_slices(gpu_lib, cref, n, window):
     pc.case_msm_large(gpu_lib, cref, n, window)
+
+
+# ---- large shuffles (BASELINE config 5 and a test-sized stand-in): digests of the reference's outputs ----
+import large_cases as lc  # noqa: E402
+
+
+def test_large_shuffle_N1024_bytes_and_verdicts_equal_reference(gpu_lib):
+    lc.check_large(gpu_lib, "large_N1024_seed6024.json", fixed_window=8)
