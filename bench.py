@@ -410,6 +410,7 @@ def measure_prove(args, lib, case, B, steps, dist=None):
     c = args.prove_window or pick_window(ell)
     prover.set_window(c)
     prover.set_lanes(args.prove_lanes)
+    prover.set_table_window(args.table_window)
     inputs, perms, ks, rands = make_prove_batch(case, prover, B, 4242)
     perm_arr = array.array("I", perms)
     pbuf = (ctypes.c_uint32 * len(perm_arr)).from_buffer(perm_arr)
@@ -886,6 +887,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="verify", choices=["verify", "prove", "msm", "msm_large"])
     ap.add_argument("--prove-window", type=int, default=0, help="bucket window of the prover's variable-base MSMs (0 = model)")
+    ap.add_argument("--table-window", type=int, default=6, help="prover: window of the per-base tables of T_i / U_i multiples (0 = bucket method)")
     ap.add_argument("--prove-lanes", type=int, default=2, help="sub-batches of the prover issued alternately on separate streams")
     ap.add_argument("--fixed-window", type=int, default=0, help="window of the CRS fixed-base tables (0 = library default 12; 16 = 6.6 GB table)")
     ap.add_argument("--prove-batch", type=int, default=4096, help="proofs in the prove side-measurement of the default (verify) run; 0 = skip")

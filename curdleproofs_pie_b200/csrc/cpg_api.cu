@@ -709,10 +709,21 @@ int cpg_g1_msm_fixed_batched(const void* table, const uint8_t* d_scalars, size_t
     const FixedTable* t = (const FixedTable*)table;
     Recode rc = make_recode(t->s.c);
     Scratch sc;
-    Xyzz* partial = sc.get<Xyzz>((uint64_t)B * t->s.W);
+    // few MSMs over many bases (a single large proof): split the bases so that no thread walks thousands of them
+    uint32_t nchunk = 1;
+    if ((uint64_t)B * t->s.W < 8192 && t->s.nb >= 1024) { nchunk = t->s.nb / 256; if (nchunk > 64) nchunk = 64; }
+    Xyzz* partial = sc.get<Xyzz>((uint64_t)B * t->s.W * nchunk);
     if (!partial) return fail("cpg_g1_msm_fixed_batched: scratch allocation failed");
-    if (int r = launch<128, 3>(FixedMsmWindow{t->s, rc, (uint32_t)B, t->table, (const uint32_t*)d_scalars, partial}, (((uint64_t)B + 31) / 32) * 32 * t->s.W)) return r;
-    return launch_occ(SumWindows{t->s.W, partial, (Jac*)d_out, accumulate}, B);
+    if (int r = launch<128, 3>(FixedMsmWindow{t->s, rc, (uint32_t)B, nchunk, t->table, (const uint32_t*)d_scalars, partial}, (((uint64_t)B + 31) / 32) * 32 * t->s.W * nchunk)) return r;
+    uint32_t np = t->s.W * nchunk;
+    if (np > 256) {                                                      // long partial lists: two stages of short serial sums
+        const uint32_t per = nchunk;                                     // np = W * nchunk: W groups of nchunk
+        Xyzz* stage = sc.get<Xyzz>((uint64_t)B * t->s.W);
+        if (!stage) return fail("cpg_g1_msm_fixed_batched: scratch allocation failed");
+        if (int r = launch_occ(SumPartials{per, partial, stage}, (uint64_t)B * t->s.W)) return r;
+        partial = stage; np = t->s.W;
+    }
+    return launch_occ(SumWindows{np, partial, (Jac*)d_out, accumulate}, B);
 }
 
 /* ---- Fr vectors ---- */

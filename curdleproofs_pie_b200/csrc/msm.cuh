@@ -402,34 +402,49 @@ struct AffToJac {
     const Aff* in; Jac* out;
     CPG_HD void operator()(uint64_t t) const { out[t] = to_jac(in[t]); }
 };
-struct FixedMsmWindow {            // sum_i +-T[i][w][|d|-1] for one (msm, window)
+struct FixedMsmWindow {            // sum_i +-T[i][w][|d|-1] for one (msm, window[, chunk of bases])
     static constexpr const char* kName = "FixedMsmWindow";
     FixedShape s; Recode rc;
     uint32_t B;
+    uint32_t nchunk;               // 1, or (few MSMs over many bases: one large proof) the bases split over nchunk threads
     const Aff* table;
     const uint32_t* scalars;       // [B][nb][8]
-    Xyzz* partial;                 // [B*W]
+    Xyzz* partial;                 // [B*W*nchunk]
     // A warp = one window of 32 consecutive MSMs (lane = msm): all lanes walk the same bases of the same
     // table segment, and callers that order their MSMs by kind (the prover: output-major) give every
     // lane the same pattern of structurally zero coefficients, so the zero skips do not diverge.
     CPG_HD void operator()(uint64_t t) const {
-        uint32_t lane = (uint32_t)(t % 32), w = (uint32_t)((t / 32) % s.W);
-        uint64_t m = (t / (32ull * s.W)) * 32 + lane;
+        uint32_t lane = (uint32_t)(t % 32);
+        uint64_t q = t / 32;
+        uint32_t ch = (uint32_t)(q % nchunk), w = (uint32_t)((q / nchunk) % s.W);
+        uint64_t m = (q / ((uint64_t)nchunk * s.W)) * 32 + lane;
         if (m >= B) return;
+        const uint32_t per = (s.nb + nchunk - 1) / nchunk;
+        const uint32_t i0 = ch * per, i1 = i0 + per < s.nb ? i0 + per : s.nb;
         const uint32_t* ks = scalars + m * s.nb * 8;
         Xyzz acc = xyzz_inf();
         uint32_t kp[8];
-        for (uint32_t i = 0; i < s.nb; i++) {
+        for (uint32_t i = i0; i < i1; i++) {
             const uint32_t* k = ks + 8 * (uint64_t)i;
             if ((k[0] | k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) == 0) continue;   // zero coefficient: every digit is zero
             recode_add(rc, k, kp);
             int d = recode_digit(rc, kp, w);
             if (!d) continue;
             uint32_t a = (uint32_t)(d < 0 ? -d : d);
-            Aff q = table[((uint64_t)i * s.W + w) * s.NB + (a - 1)];
-            acc = xyzz_add_mixed(acc, cneg(q, d < 0));
+            Aff q2 = table[((uint64_t)i * s.W + w) * s.NB + (a - 1)];
+            acc = xyzz_add_mixed(acc, cneg(q2, d < 0));
         }
-        partial[m * s.W + w] = acc;
+        partial[(m * s.W + w) * nchunk + ch] = acc;
+    }
+};
+struct SumPartials {               // thread = (msm, group): plain sum of `per` consecutive partials (first stage for long partial lists)
+    static constexpr const char* kName = "SumPartials";
+    uint32_t per; const Xyzz* partial; Xyzz* out;
+    CPG_HD void operator()(uint64_t t) const {
+        const Xyzz* ps = partial + t * (uint64_t)per;
+        Xyzz acc = ps[0];
+        for (uint32_t k = 1; k < per; k++) acc = xyzz_add(acc, ps[k]);
+        out[t] = acc;
     }
 };
 struct SumWindows {                // thread = msm: plain sum of W partials (no doublings)
@@ -444,6 +459,69 @@ struct SumWindows {                // thread = msm: plain sum of W partials (no 
         for (uint32_t w = 1; w < W; w++) acc = xyzz_add(acc, ps[w]);
         Jac r = xyzz_to_jac(acc);
         out[m] = accumulate ? jac_add(out[m], r) : r;
+    }
+};
+
+// ---- per-base tables for variable bases that enter MANY small MSMs ------------------------------
+// The prover's post-shuffle trackers T_i, U_i each appear in 8 of its 30 small MSMs (B_t / B_u and one of
+// L or R in every SameMSM round).  With a table of the multiples 1..TS of each base (TS = 2^(c-1), affine),
+// such an MSM is W window sums of plain table look-ups (mixed adds, no buckets, no bucket reduction) plus
+// one Horner pass: per proof 1984 terms x W x 10 products instead of the bucket method's accumulate +
+// 2 NB W full additions per MSM - the reduction was 37 % of the bucket method's work at n = 62.
+struct VarTableBuild {             // thread = one base: d * P for d = 1..TS, affine, one inversion per base
+    static constexpr const char* kName = "VarTableBuild";
+    uint32_t TS; const Aff* bases; uint64_t row_stride, first, count;   // base t = bases[(t / count) * row_stride + first + t % count]
+    uint64_t t0;                   // this launch handles bases t0 + u, u < launch size
+    Jac* scratch; Fq* pz;          // [launch size][TS] multiples before normalisation / prefix products of their Z
+    Aff* table;                    // [nbases][TS] (out)
+    CPG_HD void operator()(uint64_t u) const {
+        const uint64_t t = t0 + u;
+        const Aff P = bases[(t / count) * row_stride + first + t % count];
+        Jac* m = scratch + u * TS; Fq* z = pz + u * TS; Aff* out = table + t * TS;
+        Jac acc = to_jac(P);
+        Fq prod = fq_one();
+        for (uint32_t d = 0; d < TS; d++) {                 // m[d] = (d + 1) P; infinities (P = O, small-order P) are skipped in the product
+            m[d] = acc;
+            if (!is_inf(acc)) prod = mul(prod, acc.Z);
+            z[d] = prod;
+            acc = jac_add_mixed(acc, P);
+        }
+        Fq inv = fq_inv(prod);                              // prod != 0: a product of non-zero Z
+        for (uint32_t d = TS; d-- > 0;) {
+            Jac q = m[d];
+            if (is_inf(q)) { out[d] = aff_inf(); continue; }
+            Fq zi = d ? mul(inv, z[d - 1]) : inv;            // z[d-1] = product of the non-zero Z before d
+            inv = mul(inv, q.Z);
+            Fq zi2 = sqr(zi);
+            Aff r; r.x = mul(q.X, zi2); r.y = mul(q.Y, mul(zi2, zi));
+            out[d] = r;
+        }
+    }
+};
+struct VarTableMsmWindow {         // sum_i +-tab[base i of msm m][|d_w| - 1] for one (msm, window); lane = msm as in FixedMsmWindow
+    static constexpr const char* kName = "VarTableMsmWindow";
+    uint32_t nb, TS, W; Recode rc; uint32_t B;
+    const Aff* table; const uint32_t* tab_off;   // tab_off[m]: first base (in bases, not entries) of msm m's nb consecutive tables
+    const uint32_t* scalars;       // [B][nb][8]
+    Xyzz* partial;                 // [B*W]
+    CPG_HD void operator()(uint64_t t) const {
+        uint32_t lane = (uint32_t)(t % 32), w = (uint32_t)((t / 32) % W);
+        uint64_t m = (t / (32ull * W)) * 32 + lane;
+        if (m >= B) return;
+        const uint32_t* ks = scalars + m * nb * 8;
+        const Aff* tab = table + (uint64_t)tab_off[m] * TS;
+        Xyzz acc = xyzz_inf();
+        uint32_t kp[8];
+        for (uint32_t i = 0; i < nb; i++) {
+            const uint32_t* k = ks + 8 * (uint64_t)i;
+            if ((k[0] | k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) == 0) continue;
+            recode_add(rc, k, kp);
+            int d = recode_digit(rc, kp, w);
+            if (!d) continue;
+            uint32_t a = (uint32_t)(d < 0 ? -d : d);
+            acc = xyzz_add_mixed(acc, cneg(tab[(uint64_t)i * TS + (a - 1)], d < 0));
+        }
+        partial[m * W + w] = acc;
     }
 };
 

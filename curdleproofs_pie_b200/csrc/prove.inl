@@ -462,31 +462,42 @@ struct ProveCombine {
 };
 
 // base offset (in points) of variable-base instance t = v*B + b: proof b's row [R|S|T|U], vector set[v]
+// (tables = 1: offset, in bases, into the lane's [B][2 ell] table block T | U instead)
 struct VarOffsets {
     static constexpr const char* kName = "VarOffsets";
-    uint64_t B; uint32_t ell; uint32_t set[P_MAX_VAR]; uint32_t* off;
-    CPG_HD void operator()(uint64_t t) const { uint64_t v = t / B, b = t % B; off[t] = (uint32_t)(b * 4 * ell + set[v] * ell); }
+    uint64_t B; uint32_t ell; uint32_t set[P_MAX_VAR]; uint32_t* off; int tables;
+    CPG_HD void operator()(uint64_t t) const {
+        uint64_t v = t / B, b = t % B;
+        off[t] = tables ? (uint32_t)(b * 2 * ell + (set[v] - 2) * ell) : (uint32_t)(b * 4 * ell + set[v] * ell);
+    }
 };
 
 // One lane = the device buffers of a contiguous sub-batch.  A batch is split over `nlanes` lanes whose
 // rounds are issued alternately on separate streams, so the latency-bound per-proof kernels of one lane
 // (ProveStep: one thread per proof, 32 warps for 4096 proofs) run under the MSM kernels of the other.
+constexpr size_t TAB_CHUNK = 148 * 3 * 128 * 2;   // bases per VarTableBuild launch (bounds the scratch): two full waves of 3 blocks x 148 SMs
 struct ProverLane {
     size_t cap = 0, B = 0;
     uint8_t *d_in48 = nullptr, *d_tu48 = nullptr, *d_k = nullptr, *d_rand = nullptr, *d_outs = nullptr, *d_fs = nullptr, *d_vs = nullptr, *d_proof = nullptr, *d_err = nullptr;
     uint32_t *d_perm = nullptr, *d_off = nullptr; Aff* d_bases = nullptr; PState* d_st = nullptr; HFr* d_vec = nullptr; Jac *d_fix = nullptr, *d_var = nullptr;
+    Aff* d_tab = nullptr; uint32_t tab_ts = 0;   // multiples 1..tab_ts of every T_i, U_i: [B][2 ell][tab_ts]
+    Jac* d_tab_jac = nullptr; Fq* d_tab_pz = nullptr;   // build scratch for TAB_CHUNK bases at a time
 #ifndef CPG_HOST_EMU
     cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
 #endif
-    std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_off, d_bases, d_st, d_vec, d_fix, d_var}; }
+    std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_off, d_bases, d_st, d_vec, d_fix, d_var, d_tab, d_tab_jac, d_tab_pz}; }
     void release() {
         for (void* q : all()) cpg_free(q);
-        d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = d_off = nullptr; d_bases = nullptr; d_st = nullptr; d_vec = nullptr; d_fix = d_var = nullptr;
+        d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = d_off = nullptr; d_bases = nullptr; d_st = nullptr; d_vec = nullptr; d_fix = d_var = nullptr; d_tab = nullptr; d_tab_jac = nullptr; d_tab_pz = nullptr;
         cap = 0;
     }
-    int reserve(const PShape& sh, size_t proof_len, size_t Bn, uint32_t NOUT) {
-        if (Bn <= cap) return 0;
+    int reserve(const PShape& sh, size_t proof_len, size_t Bn, uint32_t NOUT, uint32_t ts) {
+        if (Bn <= cap && ts == tab_ts) return 0;
         release();
+        tab_ts = ts;
+        d_tab = (Aff*)cpg_malloc(sizeof(Aff) * (Bn * 2 * sh.ell * (size_t)ts + 1));
+        d_tab_jac = (Jac*)cpg_malloc(sizeof(Jac) * (TAB_CHUNK * (size_t)ts + 1));
+        d_tab_pz = (Fq*)cpg_malloc(sizeof(Fq) * (TAB_CHUNK * (size_t)ts + 1));
         const size_t ell = sh.ell, n = sh.n;
         d_in48 = (uint8_t*)cpg_malloc(Bn * 2 * ell * 48);     d_tu48 = (uint8_t*)cpg_malloc(Bn * 2 * ell * 48);
         d_k = (uint8_t*)cpg_malloc(Bn * 32);                  d_rand = (uint8_t*)cpg_malloc(Bn * sh.NR * 32);
@@ -511,6 +522,7 @@ struct Prover {
     Aff* d_crs = nullptr; uint8_t* d_crs48 = nullptr;
     void* table = nullptr;        // fixed-base table over vec_G | vec_H | H | G_t | G_u
     int var_window = 0;
+    int table_window = 6;         // per-base tables of 2^(c-1) multiples for the T / U MSMs (0: bucket method for those too)
     int nlanes = 2, lastK = 1;
     size_t lane_min = 256;        // proofs per lane below which a batch is not split
     size_t lastB = 0;
@@ -546,7 +558,15 @@ int prove_lane_prologue(Prover& pr, ProverLane& p) {
         for (size_t b = 0; b < B; b++) memcpy(p.d_bases + b * 4 * (size_t)ell, tmp + b * 2 * (size_t)ell, sizeof(Aff) * 2 * (size_t)ell);
 #endif
     }
-    return launch(ProveShuffle{ell, p.d_bases, p.d_perm, (const uint32_t*)p.d_k, p.d_tu48}, B * 2 * (size_t)ell);
+    if (int rc = launch(ProveShuffle{ell, p.d_bases, p.d_perm, (const uint32_t*)p.d_k, p.d_tu48}, B * 2 * (size_t)ell)) return rc;
+    if (p.tab_ts) {                                     // multiples of every T_i, U_i (they enter 8 small MSMs each)
+        const size_t nbases = B * 2 * (size_t)ell;
+        for (size_t t0 = 0; t0 < nbases; t0 += TAB_CHUNK) {
+            size_t cnt = nbases - t0 < TAB_CHUNK ? nbases - t0 : TAB_CHUNK;
+            if (int rc = launch_occ(VarTableBuild{p.tab_ts, p.d_bases, 4 * (uint64_t)ell, 2 * (uint64_t)ell, 2 * (uint64_t)ell, t0, p.d_tab_jac, p.d_tab_pz, p.d_tab}, cnt)) return rc;
+        }
+    }
+    return 0;
 }
 int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
     const PShape sh = pr.sh;
@@ -589,8 +609,21 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
         if (pl.nvar) {                                  // variable-base parts: ONE batched MSM over all B*nvar instances
             VarOffsets vo; vo.B = B; vo.ell = ell; vo.off = p.d_off;
             for (uint32_t v = 0; v < P_MAX_VAR; v++) vo.set[v] = v < pl.nvar ? pl.var_set[v] : 0;
+            bool tu_only = p.tab_ts != 0;               // every variable part of the round is over T or U: table look-ups
+            for (uint32_t v = 0; v < pl.nvar; v++) tu_only = tu_only && pl.var_set[v] >= 2;
+            vo.tables = tu_only ? 1 : 0;
             if (int rc = launch(vo, B * pl.nvar)) return rc;
-            if (int rc = cpg_g1_msm_batched_off(p.d_bases, p.d_off, p.d_vs, B * pl.nvar, ell, pr.var_window, p.d_var)) return rc;
+            if (tu_only) {
+                const uint32_t c = (uint32_t)pr.table_window;
+                Recode rc_ = make_recode(c);
+                const uint64_t M = B * pl.nvar;
+                Scratch sc;
+                Xyzz* partial = sc.get<Xyzz>(M * rc_.W);
+                if (!partial) return fail("cpg_prove_batch: scratch allocation failed");
+                if (int rc = launch<128, 3>(VarTableMsmWindow{ell, p.tab_ts, rc_.W, rc_, (uint32_t)M, p.d_tab, p.d_off, (const uint32_t*)p.d_vs, partial}, ((M + 31) / 32) * 32 * rc_.W)) return rc;
+                MsmShape hs; memset(&hs, 0, sizeof hs); hs.W = rc_.W; hs.c = c;
+                if (int rc = launch_occ(Horner{hs, partial, p.d_var}, M)) return rc;
+            } else if (int rc = cpg_g1_msm_batched_off(p.d_bases, p.d_off, p.d_vs, B * pl.nvar, ell, pr.var_window, p.d_var)) return rc;
         }
         ProveCombine pc;
         pc.nout = pl.nout; pc.NOUT = O.NOUT; pc.B = B; pc.fixed = p.d_fix; pc.var = p.d_var; pc.outs48 = p.d_outs;
@@ -697,6 +730,12 @@ int cpg_prove_replay_device(void* handle) {
     return prove_device_all(p, p.lastK);
 }
 int cpg_prover_set_window(void* handle, int w) { if (!handle) return 1; ((Prover*)handle)->var_window = w; return 0; }
+int cpg_prover_set_table_window(void* handle, int window) {
+    if (!handle) return fail("cpg_prover_set_table_window: null prover");
+    if (window < 0 || window > 10) return fail("cpg_prover_set_table_window: 0 (off) or 2..10");
+    ((Prover*)handle)->table_window = window == 1 ? 0 : window;
+    return 0;
+}
 int cpg_prover_set_lanes(void* handle, int nlanes, size_t min_proofs_per_lane) {
     if (!handle) return fail("cpg_prover_set_lanes: null prover");
     if (nlanes < 1 || nlanes > P_MAX_LANES) return fail("cpg_prover_set_lanes: 1..4 lanes");
@@ -727,7 +766,9 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
     for (int i = 0; i < k; i++) {
         ProverLane& L = p.lanes[i];
         const size_t f = first[i], c = count[i];
-        if (int rc = L.reserve(sh, p.proof_len, c, O.NOUT)) return rc;
+        // per-base tables pay off for the many small MSMs of Whisk-size proofs; one thread walks all ell terms of a
+        // (msm, window), so large shuffles keep the bucket method
+        if (int rc = L.reserve(sh, p.proof_len, c, O.NOUT, (p.table_window > 0 && ell <= 2048) ? 1u << (p.table_window - 1) : 0)) return rc;
         L.B = c;
         if (int rc = cpg_h2d(L.d_in48, inputs + f * 2 * (size_t)ell * 48, c * 2 * (size_t)ell * 48)) return rc;
         if (int rc = cpg_h2d(L.d_perm, perms + f * (size_t)ell, c * (size_t)ell * 4)) return rc;

@@ -139,6 +139,9 @@ class BatchProver:
     def set_window(self, c):
         self.lib.check(self.lib.c.cpg_prover_set_window(self.handle, int(c)), "cpg_prover_set_window")
 
+    def set_table_window(self, c):
+        self.lib.check(self.lib.c.cpg_prover_set_table_window(self.handle, int(c)), "cpg_prover_set_table_window")
+
     def set_lanes(self, k, min_proofs_per_lane=0):
         self.lib.check(self.lib.c.cpg_prover_set_lanes(self.handle, int(k), int(min_proofs_per_lane)), "cpg_prover_set_lanes")
 

@@ -183,6 +183,10 @@ int cpg_prover_free(void* prover);
 size_t cpg_prover_proof_bytes(const void* prover);
 size_t cpg_prover_rand_scalars(const void* prover);
 int cpg_prover_set_window(void* prover, int var_window);
+/* The post-shuffle trackers T_i, U_i each enter 8 of a proof's small MSMs: with window > 0 (default 6) the
+ * prover builds, per batch, a table of the 2^(window-1) multiples of each of them and evaluates those MSMs
+ * as table look-ups + Horner instead of the bucket method; 0 = bucket method for every variable-base MSM */
+int cpg_prover_set_table_window(void* prover, int window);
 /* sub-batches ("lanes", 1..4, default 2) whose rounds are issued alternately on separate streams: the
  * one-thread-per-proof transcript kernels of one lane run under the MSM kernels of the other */
 int cpg_prover_set_lanes(void* prover, int nlanes, size_t min_proofs_per_lane /* 0 = 256: smaller batches are not split */);

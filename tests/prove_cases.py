@@ -25,12 +25,14 @@ def replay_rng(case, prover):
     return perm, k, rand
 
 
-def check_prove(lib, name, copies=1, fixed_window=0, window=0, lanes=None):
+def check_prove(lib, name, copies=1, fixed_window=0, window=0, lanes=None, table_window=None):
     case = sc.load_case(name)
     ell = case["N"] - 4
     prover = whisk.BatchProver(bytes.fromhex(case["crs"]), ell, fixed_window=fixed_window, lib=lib)
     if lanes:
         prover.set_lanes(*lanes)
+    if table_window is not None:
+        prover.set_table_window(table_window)
     if window:
         prover.set_window(window)
     perm, k, rand = replay_rng(case, prover)

@@ -59,6 +59,7 @@ def test_msm_empty(gpu_lib):
 def test_fixed_base(gpu_lib, cref):
     pc.case_fixed(gpu_lib, cref, 8, 131, 8)
     pc.case_fixed(gpu_lib, cref, 3, 5, 4)
+    pc.case_fixed(gpu_lib, cref, 2, 1300, 5)      # few MSMs over many bases: the bases are split over threads (one large proof)
 
 
 def test_fr(gpu_lib):
@@ -170,6 +171,11 @@ def test_prove_then_verify_full_size(gpu_lib):
     prc.check_prove_then_verify(gpu_lib, "shuffle_N128_seed4096.json", B=96)
 
 
+@pytest.mark.parametrize("table_window", [0, 4, 7])
+def test_prove_tracker_msm_table_windows(gpu_lib, table_window):
+    prc.check_prove(gpu_lib, "shuffle_N128_seed4096.json", copies=3, table_window=table_window)
+
+
 def test_prove_sub_batches_on_stream_lanes(gpu_lib):
     prc.check_prove(gpu_lib, "shuffle_N64_seed2024.json", copies=7, lanes=(3, 2))
     prc.check_prove_then_verify(gpu_lib, "shuffle_N128_seed4096.json", B=96, lanes=(4, 16))
@@ -187,3 +193,8 @@ import large_cases as lc  # noqa: E402
 
 def test_large_shuffle_N1024_bytes_and_verdicts_equal_reference(gpu_lib):
     lc.check_large(gpu_lib, "large_N1024_seed6024.json", fixed_window=8)
+
+
+def test_large_shuffle_N16384_config5_single_gpu(gpu_lib):
+    """BASELINE config 5 on one GPU: 7808-byte proof, digests of the unmodified reference's outputs"""
+    lc.check_large(gpu_lib, "large_N16384_seed21384.json", fixed_window=8)

@@ -19,3 +19,10 @@ def test_prove_sub_batches_on_stream_lanes(seam_lib):
     """the batch split over 3 lanes of unequal size (5 = 1 + 2 + 2): bytes still equal the reference's"""
     pc.check_prove(seam_lib, "shuffle_N8_seed1234.json", copies=5, fixed_window=4, lanes=(3, 1))
     pc.check_prove_then_verify(seam_lib, "shuffle_N8_seed1234.json", B=4, fixed_window=4, lanes=(2, 2))
+
+
+def test_prove_tracker_msms_bucket_method_and_small_tables(seam_lib):
+    """the T / U MSMs either through per-base tables of multiples (default, window 6) or through the bucket
+    method (0); a 3-bit table exercises the top-digit edge of the signed recoding"""
+    pc.check_prove(seam_lib, "shuffle_N8_seed1234.json", fixed_window=4, table_window=0)
+    pc.check_prove(seam_lib, "shuffle_N16_seed77.json", fixed_window=5, table_window=3)
