@@ -425,14 +425,14 @@ struct ProveShuffle {
     uint32_t ell;
     Aff* bases;                   // [B][4 ell]  R | S | T | U  (T, U written here)
     const uint32_t* perm;         // [B][ell]
-    const uint32_t* k;            // [B][8]
+    const uint32_t* k;            // [B][8]  k1 | k2 with k = k1 + k2 lambda (glv_split)
     uint8_t* tu48;                // [B][2 ell][48]
     CPG_HD void operator()(uint64_t t) const {
         uint64_t b = t / (2 * ell); uint32_t j = (uint32_t)(t % (2 * ell));
         Aff* row = bases + b * 4 * (uint64_t)ell;
         const uint32_t* pm = perm + b * (uint64_t)ell;
         Aff src = j < ell ? row[pm[j]] : row[ell + pm[j - ell]];
-        Aff out = jac_to_aff(jac_mul(to_jac(src), k + 8 * b));
+        Aff out = jac_to_aff(jac_mul_glv(to_jac(src), k + 8 * b));
         row[2 * (uint64_t)ell + j] = out;
         aff_compress(out, tu48 + 48 * t);
     }
@@ -475,26 +475,50 @@ struct VarOffsets {
 // One lane = the device buffers of a contiguous sub-batch.  A batch is split over `nlanes` lanes whose
 // rounds are issued alternately on separate streams, so the latency-bound per-proof kernels of one lane
 // (ProveStep: one thread per proof, 32 warps for 4096 proofs) run under the MSM kernels of the other.
+// k = k1 + k2 lambda as integers, lambda = 0xac45a4010001a40200000000ffffffff (g1.cuh::jac_mul_glv); out = k1[4] | k2[4]
+// returns false (and splits 0) when k is not a canonical scalar (k >= r): k2 would not fit 128 bits
+bool glv_split(const uint8_t* k32, uint32_t* out) {
+    uint64_t n[4];
+    memcpy(n, k32, 32);                                  // little-endian host
+    static const uint64_t R[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+    bool lt = false;
+    for (int i = 3; i >= 0; i--) { if (n[i] != R[i]) { lt = n[i] < R[i]; break; } }
+    if (!lt) { memset(out, 0, 32); return false; }
+    const unsigned __int128 lam = ((unsigned __int128)0xac45a4010001a402ULL << 64) | 0x00000000ffffffffULL;
+    unsigned __int128 rem = 0, q = 0;
+    for (int i = 255; i >= 0; i--) {
+        const bool top = (rem >> 127) != 0;              // 2 rem + bit may pass 2^128: the subtraction below is exact mod 2^128
+        rem = (rem << 1) | ((n[i >> 6] >> (i & 63)) & 1);
+        const bool ge = top || rem >= lam;
+        if (ge) rem -= lam;
+        q = (q << 1) | (ge ? 1 : 0);
+    }
+    for (int i = 0; i < 4; i++) { out[i] = (uint32_t)(rem >> (32 * i)); out[4 + i] = (uint32_t)(q >> (32 * i)); }
+    return true;
+}
+
 constexpr size_t TAB_CHUNK = 148 * 3 * 128 * 2;   // bases per VarTableBuild launch (bounds the scratch): two full waves of 3 blocks x 148 SMs
 struct ProverLane {
     size_t cap = 0, B = 0;
     uint8_t *d_in48 = nullptr, *d_tu48 = nullptr, *d_k = nullptr, *d_rand = nullptr, *d_outs = nullptr, *d_fs = nullptr, *d_vs = nullptr, *d_proof = nullptr, *d_err = nullptr;
     uint32_t *d_perm = nullptr, *d_off = nullptr; Aff* d_bases = nullptr; PState* d_st = nullptr; HFr* d_vec = nullptr; Jac *d_fix = nullptr, *d_var = nullptr;
+    uint32_t* d_k12 = nullptr;    // [B][8] GLV halves of k
     Aff* d_tab = nullptr; uint32_t tab_ts = 0;   // multiples 1..tab_ts of every T_i, U_i: [B][2 ell][tab_ts]
     Jac* d_tab_jac = nullptr; Fq* d_tab_pz = nullptr;   // build scratch for TAB_CHUNK bases at a time
 #ifndef CPG_HOST_EMU
     cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
 #endif
-    std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_off, d_bases, d_st, d_vec, d_fix, d_var, d_tab, d_tab_jac, d_tab_pz}; }
+    std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_off, d_bases, d_st, d_vec, d_fix, d_var, d_tab, d_tab_jac, d_tab_pz, d_k12}; }
     void release() {
         for (void* q : all()) cpg_free(q);
-        d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = d_off = nullptr; d_bases = nullptr; d_st = nullptr; d_vec = nullptr; d_fix = d_var = nullptr; d_tab = nullptr; d_tab_jac = nullptr; d_tab_pz = nullptr;
+        d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = d_off = nullptr; d_bases = nullptr; d_st = nullptr; d_vec = nullptr; d_fix = d_var = nullptr; d_tab = nullptr; d_tab_jac = nullptr; d_tab_pz = nullptr; d_k12 = nullptr;
         cap = 0;
     }
     int reserve(const PShape& sh, size_t proof_len, size_t Bn, uint32_t NOUT, uint32_t ts) {
         if (Bn <= cap && ts == tab_ts) return 0;
         release();
         tab_ts = ts;
+        d_k12 = (uint32_t*)cpg_malloc(Bn * 32);
         d_tab = (Aff*)cpg_malloc(sizeof(Aff) * (Bn * 2 * sh.ell * (size_t)ts + 1));
         d_tab_jac = (Jac*)cpg_malloc(sizeof(Jac) * (TAB_CHUNK * (size_t)ts + 1));
         d_tab_pz = (Fq*)cpg_malloc(sizeof(Fq) * (TAB_CHUNK * (size_t)ts + 1));
@@ -558,7 +582,7 @@ int prove_lane_prologue(Prover& pr, ProverLane& p) {
         for (size_t b = 0; b < B; b++) memcpy(p.d_bases + b * 4 * (size_t)ell, tmp + b * 2 * (size_t)ell, sizeof(Aff) * 2 * (size_t)ell);
 #endif
     }
-    if (int rc = launch(ProveShuffle{ell, p.d_bases, p.d_perm, (const uint32_t*)p.d_k, p.d_tu48}, B * 2 * (size_t)ell)) return rc;
+    if (int rc = launch(ProveShuffle{ell, p.d_bases, p.d_perm, p.d_k12, p.d_tu48}, B * 2 * (size_t)ell)) return rc;
     if (p.tab_ts) {                                     // multiples of every T_i, U_i (they enter 8 small MSMs each)
         const size_t nbases = B * 2 * (size_t)ell;
         for (size_t t0 = 0; t0 < nbases; t0 += TAB_CHUNK) {
@@ -763,6 +787,9 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
     const uint32_t ell = sh.ell, lg = sh.lg;
     size_t first[P_MAX_LANES], count[P_MAX_LANES];
     const int k = p.split(B, first, count);
+    std::vector<uint32_t> k12(B * 8);
+    std::vector<uint8_t> bad_k(B, 0);
+    for (size_t b = 0; b < B; b++) bad_k[b] = glv_split(ks + 32 * b, k12.data() + 8 * b) ? 0 : 1;
     for (int i = 0; i < k; i++) {
         ProverLane& L = p.lanes[i];
         const size_t f = first[i], c = count[i];
@@ -773,6 +800,7 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
         if (int rc = cpg_h2d(L.d_in48, inputs + f * 2 * (size_t)ell * 48, c * 2 * (size_t)ell * 48)) return rc;
         if (int rc = cpg_h2d(L.d_perm, perms + f * (size_t)ell, c * (size_t)ell * 4)) return rc;
         if (int rc = cpg_h2d(L.d_k, ks + f * 32, c * 32)) return rc;
+        if (int rc = cpg_h2d(L.d_k12, k12.data() + f * 8, c * 32)) return rc;
         if (int rc = cpg_h2d(L.d_rand, rand + f * (size_t)sh.NR * 32, c * (size_t)sh.NR * 32)) return rc;
     }
     p.lastB = B; p.lastK = k;
@@ -791,7 +819,7 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
         uint8_t* w = out_proofs + b * (p.proof_len + 48);
         memcpy(w, outs.data() + (b * O.NOUT + O.M) * 48, 48);
         memcpy(w + 48, proofs.data() + b * p.proof_len, p.proof_len);
-        uint8_t bad = 0;
+        uint8_t bad = bad_k[b];
         for (size_t i = 0; i < 2 * (size_t)ell; i++) bad |= err[b * 2 * ell + i];
         if (status) status[b] = bad ? 1 : 0;
     }

@@ -177,7 +177,7 @@ int cpg_verify_replay_device(void* verifier, uint8_t* verdicts_or_null);
  *               m_bl(4) a_bl(2) c_bl(4) ipa_r(n) ipa_z(n-2) r_t r_u r_a r_b r_k msm_r(n), canonical LE
  *   out_tu    : [B][2*ell*48]  vec_T | vec_U (post-shuffle tracker halves)
  *   out_proofs: [B][cpg_prover_proof_bytes]  M | proof  (WhiskShuffleProof.to_bytes, :57-61)
- *   status    : [B] 0 ok, 1 malformed input point encoding */
+ *   status    : [B] 0 ok, 1 malformed input (a point encoding, or k >= r) */
 void* cpg_prover_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window);
 int cpg_prover_free(void* prover);
 size_t cpg_prover_proof_bytes(const void* prover);

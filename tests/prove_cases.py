@@ -71,3 +71,21 @@ def check_prove_then_verify(lib, name, B=3, fixed_window=0, lanes=None):
     assert ver.verify(inputs, proofs) == [True] * B
     assert ver.verify(inputs, proofs[1:] + proofs[:1]) == [False] * B
     ver.close()
+
+
+def check_rejects_non_canonical_k(lib, name, fixed_window=0):
+    """k >= r is not a Scalar (Scalar.from_le_bytes raises in the reference): that lane is flagged, the others prove"""
+    import pytest
+
+    case = sc.load_case(name)
+    ell = case["N"] - 4
+    prover = whisk.BatchProver(bytes.fromhex(case["crs"]), ell, fixed_window=fixed_window, lib=lib)
+    perm, k, rand = replay_rng(case, prover)
+    pre = b"".join(bytes.fromhex(h) for h in case["vec_R"] + case["vec_S"])
+    ks = k.to_bytes(32, "little") + rt.R_ORDER.to_bytes(32, "little") + (2**256 - 1).to_bytes(32, "little")
+    tu, pr, st = prover.prove_raw(pre * 3, perm * 3, ks, rand * 3, 3)
+    assert list(st) == [0, 1, 1]
+    assert pr[:prover.proof_len] == bytes.fromhex(case["M"]) + bytes.fromhex(case["proof"])
+    with pytest.raises(ValueError):
+        prover.prove([pre], [perm], [rt.R_ORDER], [rand])
+    prover.close()

@@ -176,6 +176,10 @@ def test_prove_tracker_msm_table_windows(gpu_lib, table_window):
     prc.check_prove(gpu_lib, "shuffle_N128_seed4096.json", copies=3, table_window=table_window)
 
 
+def test_prove_rejects_non_canonical_k(gpu_lib):
+    prc.check_rejects_non_canonical_k(gpu_lib, "shuffle_N16_seed77.json")
+
+
 def test_prove_sub_batches_on_stream_lanes(gpu_lib):
     prc.check_prove(gpu_lib, "shuffle_N64_seed2024.json", copies=7, lanes=(3, 2))
     prc.check_prove_then_verify(gpu_lib, "shuffle_N128_seed4096.json", B=96, lanes=(4, 16))

@@ -26,3 +26,7 @@ def test_prove_tracker_msms_bucket_method_and_small_tables(seam_lib):
     method (0); a 3-bit table exercises the top-digit edge of the signed recoding"""
     pc.check_prove(seam_lib, "shuffle_N8_seed1234.json", fixed_window=4, table_window=0)
     pc.check_prove(seam_lib, "shuffle_N16_seed77.json", fixed_window=5, table_window=3)
+
+
+def test_prove_rejects_non_canonical_k(seam_lib):
+    pc.check_rejects_non_canonical_k(seam_lib, "shuffle_N8_seed1234.json", fixed_window=4)
