@@ -688,7 +688,8 @@ def run_ours(args, rank, world, dist):
 
     lib = rt.get_lib()
     assert lib.backend == "cuda-sm_100a", "bench must run on the CUDA library, got " + lib.backend
-    B, n, c = args.batch, args.n, args.window
+    B, n = args.batch, args.n
+    c = args.window or int(lib.c.cpg_msm_pick_window_batched(B, n))
     rng = random.Random(1000 + rank)
     model = msm_model(n, c)
 
@@ -735,6 +736,17 @@ def run_ours(args, rank, world, dist):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    if rank == 0 and n <= 8192:
+        # parity on this very instance: the last MSM of the batch against the oracle's C Pippenger
+        from oracle import cref_binding
+
+        cref = cref_binding.load()
+        enc = lib.download(comp_dev, n * 48, offset=(B - 1) * n * 48)
+        blobs = [cref.decompress(enc[48 * i:48 * i + 48], False) for i in range(n)]
+        ks = [int.from_bytes(scal_bytes[32 * ((B - 1) * n + i):32 * ((B - 1) * n + i) + 32], "little") for i in range(n)]
+        want = cref.compress(cref.msm(blobs, ks))
+        got = lib.compress_jac(out, B)[48 * (B - 1):48 * B]
+        assert got == want, "batched MSM differs from the oracle"
 
     # ---- timed region: K steps, device events on the launching stream, per-kernel events live ----
     sampler = ClockSampler(lib.device) if rank == 0 else None
@@ -888,8 +900,8 @@ def main():
     ap.add_argument("--workload", default="verify", choices=["verify", "prove", "msm", "msm_large"])
     ap.add_argument("--prove-window", type=int, default=0, help="bucket window of the prover's variable-base MSMs (0 = model)")
     ap.add_argument("--table-window", type=int, default=6, help="prover: window of the per-base tables of T_i / U_i multiples (0 = bucket method)")
-    ap.add_argument("--prove-lanes", type=int, default=2, help="sub-batches of the prover issued alternately on separate streams")
-    ap.add_argument("--fixed-window", type=int, default=0, help="window of the CRS fixed-base tables (0 = library default 12; 16 = 6.6 GB table)")
+    ap.add_argument("--prove-lanes", type=int, default=3, help="sub-batches of the prover issued alternately on separate streams")
+    ap.add_argument("--fixed-window", type=int, default=16, help="window of the CRS fixed-base tables (16 = 6.6 GB table, built once per CRS; 0 = library default 12, 540 MB)")
     ap.add_argument("--prove-batch", type=int, default=4096, help="proofs in the prove side-measurement of the default (verify) run; 0 = skip")
     ap.add_argument("--cpu-sample-prove", type=int, default=4, help="proofs in the bounded CPU sample")
     ap.add_argument("--batch", type=int, default=8192, help="proofs (or MSMs) per GPU per step")
@@ -908,8 +920,6 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.workload == "msm" and not args.window:
-        args.window = 4
     if args.impl == "reference":
         line = (run_reference_verify if args.workload == "verify" else run_reference)(args, rank, world)
         if line is not None:
