@@ -166,7 +166,9 @@ def run_ours_verify(args, rank, world, dist):
     B, ell, n = args.batch, 124, 128
     NV, NF = 4 * ell + 1 + 18 + 10 * 7 + 1, n + 3
     c = args.window or pick_window(NV)
-    ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), ell, fixed_window=args.fixed_window, host_threads=args.host_threads)
+    # host threads stage the wire bytes (and run the transcript with --transcript host): share the cores between the ranks
+    host_threads = args.host_threads or max(1, (os.cpu_count() or 1) // world)
+    ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), ell, fixed_window=args.fixed_window, host_threads=host_threads)
     ver.set_window(c)
     ver.set_transcript(args.transcript == "device")
     ver.set_streams(args.streams)
@@ -304,7 +306,7 @@ def run_ours_verify(args, rank, world, dist):
         "e2e": {"value": total * args.steps / (ms_e2e * 1e-3), "unit": "verifications/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": B * (NV * 48 + 7 * 32 + (0 if args.transcript == "device" else 64 + NV * 32 + NF * 32 + 1)),
                 "d2h_bytes_per_step": B * (1 + (0 if args.transcript == "device" else 96 + NV + 1)),
-                "host_threads": args.host_threads or (os.cpu_count() or 1)},
+                "host_threads": host_threads},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
 
@@ -536,15 +538,24 @@ def run_ours_prove(args, rank, world, dist):
     # whose count is not modelled here, so it carries no roofline entry and the whole-step figure is a lower bound.
     ell_, lg_ = 124, 7
     var = msm_model(1, r["window"])
-    var_terms, var_inst = 4 * ell_ + 4 * lg_ * (ell_ // 2), 4 + 4 * lg_
+    tw = args.table_window
+    tu_terms, tu_inst = 2 * ell_ + 4 * lg_ * (ell_ // 2), 2 + 4 * lg_          # B_t, B_u + L/R of T and U per SameMSM round
+    rs_terms, rs_inst = 2 * ell_, 2                                          # R', S'
+    bucket_terms, bucket_inst = (rs_terms, rs_inst) if tw else (rs_terms + tu_terms, rs_inst + tu_inst)
     DEC_MAC = 378 * SQR_MAC + 86 * MAC_PER_MODMUL
+    INV_MAC = 377 * SQR_MAC + 83 * MAC_PER_MODMUL
     alg_mac = {
-        "BucketAccumulate": B * var_terms * var["W"] * 10 * MAC_PER_MODMUL,
-        "WindowReduce": B * var_inst * var["window_reduce"] * MAC_PER_MODMUL,
-        "Horner": B * var_inst * var["horner"] * MAC_PER_MODMUL,
-        "ProveShuffle": B * 2 * ell_ * (2900 * MAC_PER_MODMUL + DEC_MAC),
+        "BucketAccumulate": B * bucket_terms * var["W"] * 10 * MAC_PER_MODMUL,
+        "WindowReduce": B * bucket_inst * var["window_reduce"] * MAC_PER_MODMUL,
+        # GLV shuffle: 128 doublings (2M+5S) + ~62 Jacobian additions (11M+5S) + table + phi, then one inversion to affine
+        "ProveShuffle": B * 2 * ell_ * (132 * (2 * MAC_PER_MODMUL + 5 * SQR_MAC) + 70 * (11 * MAC_PER_MODMUL + 5 * SQR_MAC) + 40 * MAC_PER_MODMUL + INV_MAC),
         "Decompress": B * 2 * ell_ * DEC_MAC,
     }
+    if tw:
+        Wt, TS = (256 + tw - 1) // tw, 1 << (tw - 1)
+        alg_mac["VarTableMsmWindow"] = B * tu_terms * Wt * 10 * MAC_PER_MODMUL
+        # per entry: mixed Jacobian addition (7M+4S), prefix product, 2 back-substitution products, 1S+3M to affine; one inversion per base
+        alg_mac["VarTableBuild"] = B * 2 * ell_ * (TS * (13 * MAC_PER_MODMUL + 5 * SQR_MAC) + INV_MAC)
     kernels = {}
     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
         ms_step = v["ms"] / args.steps
@@ -554,9 +565,11 @@ def run_ours_prove(args, rank, world, dist):
             ent["frac"] = alg_mac[k] / (ms_step * 1e-3) / peak_mac if peak_mac else None
         kernels[k] = ent
     total_kernel_ms = sum(v["ms"] for v in prof.values())
-    ba = prof.get("BucketAccumulate", {"ms": 0.0, "launches": 1})
+    modelled = [k for k in prof if k in alg_mac]
+    dom = max(modelled, key=lambda k: prof[k]["ms"]) if modelled else "BucketAccumulate"
+    ba = prof.get(dom, {"ms": 0.0, "launches": 1})
     ba_launch_ms = ba["ms"] / max(1, ba["launches"])
-    ba_mac_launch = alg_mac["BucketAccumulate"] * args.steps / max(1, ba["launches"])
+    ba_mac_launch = alg_mac.get(dom, 0) * args.steps / max(1, ba["launches"])
     cpu = cpu_prove_rate(case, sample=args.cpu_sample_prove, procs=1)
     total = B * world
     return {
@@ -570,7 +583,7 @@ def run_ours_prove(args, rank, world, dist):
         "e2e": {"value": total * args.steps / (ms_e2e * 1e-3), "unit": "proofs/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
         "gpu_launches": r["launches"], "clocks": clocks,
-        "roofline": {"bound": "int_pipe", "kernel": "BucketAccumulate", "achieved": ba_mac_launch / (ba_launch_ms * 1e-3) / 1e9 if ba_launch_ms else 0.0,
+        "roofline": {"bound": "int_pipe", "kernel": dom, "achieved": ba_mac_launch / (ba_launch_ms * 1e-3) / 1e9 if ba_launch_ms else 0.0,
                      "peak": peak_mac / 1e9, "unit": "GMAC/s", "frac": (ba_mac_launch / (ba_launch_ms * 1e-3) / peak_mac) if ba_launch_ms and peak_mac else None,
                      "traffic": None, "kernel_ms_per_launch": ba_launch_ms, "algorithmic_mac_per_launch": ba_mac_launch,
                      "kernel_share_of_step": ba["ms"] / total_kernel_ms if total_kernel_ms else None,
