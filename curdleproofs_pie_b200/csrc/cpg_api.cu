@@ -824,3 +824,4 @@ int cpg_bench_int_pipe(int, uint64_t, double* per_second, float* ms) {
 
 #include "verify.inl"
 #include "prove.inl"
+#include "pyrandom.inl"

@@ -90,6 +90,7 @@ _SIGS = {
     "cpg_prover_proof_bytes": (_c.c_size_t, [_c.c_void_p]),
     "cpg_prover_rand_scalars": (_c.c_size_t, [_c.c_void_p]),
     "cpg_prover_set_window": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "cpg_pyrandom_draw_shuffles": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "cpg_prover_set_table_window": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "cpg_prover_set_lanes": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_size_t]),
     "cpg_prove_replay_device": (_c.c_int, [_c.c_void_p]),

@@ -151,6 +151,49 @@ class BatchProver:
         order = _rt.R_ORDER
         return b"".join(rng.randint(1, order - 1).to_bytes(32, "little") for _ in range(self.n_rand))
 
+    def draw_batch(self, rng, B):
+        """(perms, ks, rand) for B proofs - flat u32 array, B*32 bytes, B*n_rand*32 bytes - drawn from `rng` in the
+        reference's order (shuffle, k, blinders per proof).  A CPython Mersenne Twister (the `random` module or a
+        random.Random) is continued in C (cpg_pyrandom_draw_shuffles) and left where Python would have left it;
+        any other generator is driven call by call."""
+        import array
+        import random as _random
+
+        is_mt = rng is _random or type(rng) is _random.Random
+        if is_mt:
+            version, words, gauss = rng.getstate()
+            if version == 3 and len(words) == 625:
+                st = (ctypes.c_uint32 * 625)(*words)
+                perms = (ctypes.c_uint32 * (B * self.ell))()
+                ks = ctypes.create_string_buffer(max(1, B * 32))
+                rand = ctypes.create_string_buffer(max(1, B * self.n_rand * 32))
+                self.lib.check(self.lib.c.cpg_pyrandom_draw_shuffles(st, self.ell, self.n_rand, B, perms, ks, rand), "cpg_pyrandom_draw_shuffles")
+                rng.setstate((version, tuple(st), gauss))
+                return perms, ks.raw[:B * 32], rand.raw[:B * self.n_rand * 32]
+        perms, ks, rands = array.array("I"), bytearray(), bytearray()
+        for _ in range(B):
+            perm = list(range(self.ell))
+            rng.shuffle(perm)
+            perms.extend(perm)
+            ks += rng.randint(1, _rt.R_ORDER - 1).to_bytes(32, "little")
+            rands += self.draw_randomness(rng)
+        return (ctypes.c_uint32 * len(perms)).from_buffer(perms), bytes(ks), bytes(rands)
+
+    def prove_drawn(self, pre_inputs, rng):
+        """Proves len(pre_inputs) shuffles with randomness drawn from `rng` as the reference draws it.
+        Returns [(vec_T|vec_U bytes, M|proof bytes)]."""
+        B = len(pre_inputs)
+        perms, ks, rand = self.draw_batch(rng, B)
+        out_tu = ctypes.create_string_buffer(max(1, B * 2 * self.ell * 48))
+        out_pr = ctypes.create_string_buffer(max(1, B * self.proof_len))
+        status = ctypes.create_string_buffer(max(1, B))
+        self.lib.check(self.lib.c.cpg_prove_batch(self.handle, b"".join(pre_inputs), perms, ks, rand, B, out_tu, out_pr, status), "cpg_prove_batch")
+        if any(status.raw[:B]):
+            raise ValueError("serialised data seems to be invalid (lanes %s)" % [i for i, s in enumerate(status.raw[:B]) if s])
+        w = 2 * self.ell * 48
+        tu, pr = out_tu.raw, out_pr.raw
+        return [(tu[i * w:(i + 1) * w], pr[i * self.proof_len:(i + 1) * self.proof_len]) for i in range(B)]
+
     def prove_raw(self, inputs, perms, ks, rand, B):
         import array
 
@@ -199,16 +242,9 @@ def GenerateWhiskShuffleProofBatch(crs, pre_shuffle_trackers_per_proof, rng=None
     else:
         crs_bytes, ell, nbl = crs.to_bytes(), len(crs.vec_G), len(crs.vec_H)
     prover = BatchProver(crs_bytes, ell, nbl)
-    inputs, perms, ks, rands = [], [], [], []
-    for trackers in pre_shuffle_trackers_per_proof:
-        perm = list(range(ell))
-        rng.shuffle(perm)
-        k = rng.randint(1, _rt.R_ORDER - 1)
-        halves = trackers_to_input(trackers, [])
-        inputs.append(halves)
-        perms.append(perm); ks.append(k); rands.append(prover.draw_randomness(rng))
+    inputs = [trackers_to_input(trackers, []) for trackers in pre_shuffle_trackers_per_proof]
     out = []
-    for tu, proof in prover.prove(inputs, perms, ks, rands):
+    for tu, proof in prover.prove_drawn(inputs, rng):
         T, U = tu[:48 * ell], tu[48 * ell:]
         post = [(T[48 * i:48 * i + 48], U[48 * i:48 * i + 48]) for i in range(ell)]
         out.append((post, proof))

@@ -194,6 +194,15 @@ int cpg_prove_replay_device(void* prover);   /* device side of the last batch ag
 int cpg_prove_batch(void* prover, const uint8_t* inputs, const uint32_t* perms, const uint8_t* ks, const uint8_t* rand,
                     size_t B, uint8_t* out_tu, uint8_t* out_proofs, uint8_t* status);
 
+/* ---- the prover's randomness, drawn as the reference draws it ----------------------
+ * The reference takes the permutation (random.shuffle, cp/whisk_interface.py:114), k (:116) and every
+ * blinder (random_scalar, cp/util.py:21-24) from Python's `random`.  This continues that very stream in C:
+ * state625 = the 625 words of random.getstate()[1], advanced in place (random.setstate resumes from it).
+ * For each of the B proofs: perm[ell], k, then n_rand = cpg_prover_rand_scalars blinders - exactly the
+ * inputs of cpg_prove_batch.  Host-only; needs no device. */
+int cpg_pyrandom_draw_shuffles(uint32_t* state625, size_t ell, size_t n_rand, size_t B,
+                               uint32_t* perms, uint8_t* ks, uint8_t* rand);
+
 /* ---- roofline support: saturating integer-pipe microbenchmark ---------------------------------
  * Runs `iters` dependent-chain steps of 32x32->64 multiply-accumulates on every SM and reports
  * the achieved rate: kind 0 = 32x32->64 MAC/s of data-dependent IMAD.WIDE.U32 chains (THE roofline

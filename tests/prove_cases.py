@@ -89,3 +89,26 @@ def check_rejects_non_canonical_k(lib, name, fixed_window=0):
     with pytest.raises(ValueError):
         prover.prove([pre], [perm], [rt.R_ORDER], [rand])
     prover.close()
+
+
+def check_prove_drawn(lib, name, B=3, fixed_window=0):
+    """prove_drawn (randomness continued in C from the caller's `random` state) == prove() on values drawn by
+    Python from a twin generator; the proofs verify"""
+    case = sc.load_case(name)
+    ell = case["N"] - 4
+    crs = bytes.fromhex(case["crs"])
+    prover = whisk.BatchProver(crs, ell, fixed_window=fixed_window, lib=lib)
+    pre = b"".join(bytes.fromhex(h) for h in case["vec_R"] + case["vec_S"])
+    a, b = random.Random(31337), random.Random(31337)
+    got = prover.prove_drawn([pre] * B, a)
+    perms, ks, rands = [], [], []
+    for _ in range(B):
+        p = list(range(ell)); b.shuffle(p)
+        perms.append(p); ks.append(b.randint(1, rt.R_ORDER - 1)); rands.append(prover.draw_randomness(b))
+    want = prover.prove([pre] * B, perms, ks, rands)
+    assert got == want
+    assert a.random() == b.random()
+    prover.close()
+    ver = whisk.BatchVerifier(crs, ell, fixed_window=fixed_window, lib=lib)
+    assert ver.verify([pre + tu for tu, _ in got], [pr for _, pr in got]) == [True] * B
+    ver.close()

@@ -176,6 +176,10 @@ def test_prove_tracker_msm_table_windows(gpu_lib, table_window):
     prc.check_prove(gpu_lib, "shuffle_N128_seed4096.json", copies=3, table_window=table_window)
 
 
+def test_prove_with_randomness_continued_in_c(gpu_lib):
+    prc.check_prove_drawn(gpu_lib, "shuffle_N128_seed4096.json", B=5)
+
+
 def test_prove_rejects_non_canonical_k(gpu_lib):
     prc.check_rejects_non_canonical_k(gpu_lib, "shuffle_N16_seed77.json")
 

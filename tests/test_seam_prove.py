@@ -30,3 +30,7 @@ def test_prove_tracker_msms_bucket_method_and_small_tables(seam_lib):
 
 def test_prove_rejects_non_canonical_k(seam_lib):
     pc.check_rejects_non_canonical_k(seam_lib, "shuffle_N8_seed1234.json", fixed_window=4)
+
+
+def test_prove_with_randomness_continued_in_c(seam_lib):
+    pc.check_prove_drawn(seam_lib, "shuffle_N8_seed1234.json", B=2, fixed_window=4)
