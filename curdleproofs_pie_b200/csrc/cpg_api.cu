@@ -76,6 +76,75 @@ __global__ void __launch_bounds__(SORT_BLOCK) k_sort_digits_smem(SortDigits f, u
     }
 }
 
+// ---- HornerJac for FEW MSMs: the 255 dependent doublings of one MSM's Horner pass on one thread are
+// 1.8 ms of pure latency (7 dependent Fq products per doubling, 0.9 us each).  Here a warp owns an MSM and
+// four of its lanes each take ONE of the independent products of a stage; the results travel by shuffle:
+//   doubling (dbl-2009-l, a = 0):  {X^2, Y^2, Y Z} -> {B^2, (X+B)^2, (3A)^2} -> {E (D - X3)}      3 stages, not 7
+//   addition (add-2007-bl):        4 -> 4 -> 2 -> 4 -> 2 products                                   5 stages, not 16
+// Every lane keeps the whole accumulator, so control flow (identity / equal-point cases) stays warp-uniform.
+__device__ __forceinline__ Fq warp_bcast(const Fq& v, int src) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = __shfl_sync(0xffffffffu, v.l[i], src);
+    return r;
+}
+__device__ __forceinline__ Fq pick4(int lane, const Fq& a, const Fq& b, const Fq& c, const Fq& d) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = lane == 0 ? a.l[i] : lane == 1 ? b.l[i] : lane == 2 ? c.l[i] : d.l[i];
+    return r;
+}
+__device__ Jac coop_dbl(const Jac& p, int lane) {
+    if (is_inf(p)) return p;
+    Fq r1 = mul(pick4(lane, p.X, p.Y, p.Y, p.X), pick4(lane, p.X, p.Y, p.Z, p.X));        // A = X^2 | B = Y^2 | Y Z
+    Fq A = warp_bcast(r1, 0), B = warp_bcast(r1, 1), YZ = warp_bcast(r1, 2);
+    Fq E = add(dbl(A), A), t = add(p.X, B);
+    Fq o2 = pick4(lane, B, t, E, B);
+    Fq r2 = mul(o2, o2);                                                                    // C = B^2 | t^2 | F = E^2
+    Fq C = warp_bcast(r2, 0), T2 = warp_bcast(r2, 1), F = warp_bcast(r2, 2);
+    Fq D = dbl(sub(sub(T2, A), C));
+    Jac r;
+    r.X = sub(F, dbl(D));
+    r.Z = dbl(YZ);
+    Fq m = warp_bcast(mul(E, sub(D, r.X)), 0);
+    r.Y = sub(m, dbl(dbl(dbl(C))));
+    return r;
+}
+__device__ Jac coop_add(const Jac& p, const Jac& q, int lane) {
+    if (is_inf(p)) return q;
+    if (is_inf(q)) return p;
+    Fq r1 = mul(pick4(lane, p.Z, q.Z, p.Y, q.Y), pick4(lane, p.Z, q.Z, q.Z, p.Z));        // Z1Z1 | Z2Z2 | Y1 Z2 | Y2 Z1
+    Fq Z1Z1 = warp_bcast(r1, 0), Z2Z2 = warp_bcast(r1, 1), Y1Z2 = warp_bcast(r1, 2), Y2Z1 = warp_bcast(r1, 3);
+    Fq r2 = mul(pick4(lane, p.X, q.X, Y1Z2, Y2Z1), pick4(lane, Z2Z2, Z1Z1, Z2Z2, Z1Z1));  // U1 | U2 | S1 | S2
+    Fq U1 = warp_bcast(r2, 0), U2 = warp_bcast(r2, 1), S1 = warp_bcast(r2, 2), S2 = warp_bcast(r2, 3);
+    Fq H = sub(U2, U1), rr = sub(S2, S1);
+    if (H.is_zero()) return rr.is_zero() ? coop_dbl(p, lane) : jac_inf();
+    rr = dbl(rr);
+    Fq o3 = pick4(lane, dbl(H), add(p.Z, q.Z), H, H);
+    Fq r3 = mul(o3, o3);                                                                    // I = (2H)^2 | (Z1+Z2)^2
+    Fq I = warp_bcast(r3, 0), ZS = warp_bcast(r3, 1);
+    Fq r4 = mul(pick4(lane, H, U1, rr, sub(sub(ZS, Z1Z1), Z2Z2)), pick4(lane, I, I, rr, H)); // J | V | rr^2 | Z3
+    Fq J = warp_bcast(r4, 0), V = warp_bcast(r4, 1), RR2 = warp_bcast(r4, 2);
+    Jac r;
+    r.Z = warp_bcast(r4, 3);
+    r.X = sub(sub(RR2, J), dbl(V));
+    Fq r5 = mul(pick4(lane, rr, S1, rr, rr), pick4(lane, sub(V, r.X), J, rr, rr));          // rr (V - X3) | S1 J
+    r.Y = sub(warp_bcast(r5, 0), dbl(warp_bcast(r5, 1)));
+    return r;
+}
+__global__ void __launch_bounds__(32) k_horner_jac_coop(HornerJac f, uint64_t n_msm) {
+    const uint64_t m = blockIdx.x;
+    if (m >= n_msm) return;
+    const int lane = threadIdx.x;
+    const Jac* ws = f.wsum + m * (uint64_t)f.W;
+    Jac acc = ws[f.W - 1];
+    for (uint32_t w = f.W - 1; w-- > 0;) {
+        for (uint32_t j = 0; j < f.c; j++) acc = coop_dbl(acc, lane);
+        acc = coop_add(acc, ws[w], lane);
+    }
+    if (lane == 0) f.out[m] = acc;
+}
+
 // ---- optional per-kernel timing (cpg_profile_*): one CUDA event pair per launch on the launching
 // stream, resolved lazily.  Off by default; bench.py turns it on to time the dominant kernel live.
 struct ProfRec { const char* name; cudaEvent_t a, b; uint64_t threads; };
@@ -127,6 +196,16 @@ int launch_sort_digits(const SortDigits& f, uint64_t n) {
     g_launches++;
     return ck(cudaGetLastError(), "kernel launch");
 }
+int launch_horner_jac(const HornerJac& f, uint64_t n) {
+    if (!n) return 0;
+    if (n > 4096) return launch_occ(f, n);                 // many MSMs: throughput-bound, one thread each
+    ProfRec rec{"HornerJacCoop", nullptr, nullptr, n * 32};
+    if (g_prof_on) { cudaEventCreate(&rec.a); cudaEventCreate(&rec.b); cudaEventRecord(rec.a, cur()); }
+    k_horner_jac_coop<<<(unsigned)n, 32, 0, cur()>>>(f, n);
+    if (g_prof_on) { cudaEventRecord(rec.b, cur()); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back(rec); }
+    g_launches++;
+    return ck(cudaGetLastError(), "kernel launch");
+}
 void* scratch_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocAsync(&p, bytes ? bytes : 1, cur()) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -145,6 +224,7 @@ int launch(const F& f, uint64_t n) {
 template <class F>
 int launch_occ(const F& f, uint64_t n) { return launch(f, n); }
 int launch_sort_digits(const SortDigits& f, uint64_t n) { return launch(f, n); }
+int launch_horner_jac(const HornerJac& f, uint64_t n) { return launch(f, n); }
 void* scratch_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void scratch_free(void* p) { free(p); }
 #endif
@@ -565,7 +645,7 @@ int cpg_g1_msm_window_sums(const void* d_bases, const uint8_t* d_scalars, size_t
 int cpg_g1_msm_combine_windows(const void* d_wsums_jac, int window, void* d_out_jac) {
     NEED_INIT();
     if (window <= 0) return fail("cpg_g1_msm_combine_windows: bad window");
-    return launch(HornerJac{windows_for((uint32_t)window), (uint32_t)window, (const Jac*)d_wsums_jac, (Jac*)d_out_jac}, 1);
+    return launch_horner_jac(HornerJac{windows_for((uint32_t)window), (uint32_t)window, (const Jac*)d_wsums_jac, (Jac*)d_out_jac}, 1);
 }
 // wn = 0: all windows and the final Horner; wn > 0: only windows [w0, w0+wn), output = their sums (B must be 1)
 static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint32_t* d_base_off, const uint8_t* d_scalars,
@@ -667,7 +747,7 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
         for (int k = 0; k < 16; k++) fin.lg_ch[k] = k < (int)nlev ? lg_ch[k] : 0;
         if (int r = launch(fin, BW)) return r;
         if (!slice) {
-            if (int r = launch(HornerJac{s.W, s.c, wsum, (Jac*)d_out + b0}, nb)) return r;
+            if (int r = launch_horner_jac(HornerJac{s.W, s.c, wsum, (Jac*)d_out + b0}, nb)) return r;
         }
     }
     return 0;
