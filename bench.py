@@ -42,6 +42,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "dropin")]
 
 R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+# DRAM bytes per unit from the committed `ncu --set full` capture (profiles/r01_ncu_full_v10_key_metrics.txt:
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch over 4096 proofs), scaled to the launch the bench times
+NCU_DRAM_BYTES = {"Decompress": (120.727e6 + 329.198e6) / (4096 * 586),           # per point (algorithmic: 48 in + 96 + 1 out)
+                  "BucketAccumulate": (654.527e6 + 1826.430e6) / (4096 * 586 * 37)}  # per (term, window) at c = 7, one MSM per proof
 MAC_PER_MODMUL = 300     # 12-limb Montgomery product: 2*12^2 + 12
 SQR_MAC = 222            # dedicated Montgomery squaring: 78 product + 144 reduction MACs
 
@@ -275,7 +279,9 @@ def run_ours_verify(args, rank, world, dist):
     mac_step = sum(alg_mac.values()) + (per_proof * model["horner"] + ngroups * gmodel["horner"] + B * 2 * 2900) * MAC_PER_MODMUL
     roofline = {
         "bound": "int_pipe", "kernel": dom, "achieved": achieved / 1e9, "peak": peak_mac / 1e9, "unit": "GMAC/s",
-        "frac": achieved / peak_mac if peak_mac else None, "traffic": None,
+        "frac": achieved / peak_mac if peak_mac else None,
+        "traffic": (NCU_DRAM_BYTES["Decompress"] * B * (NV - 1) * args.steps / max(1, prof[dom]["launches"])) if dom == "Decompress" else None,
+        "traffic_note": "bytes per launch = the committed ncu capture's DRAM bytes per point (187 B read + written; 145 B algorithmic) x the points of one launch: ~13 GB/s against 6.5 TB/s, HBM is idle",
         "peak_source": "data-dependent IMAD.WIDE.U32 chains measured in this run (32 lanes/clk/SM; MEASURED_PEAKS.json has no integer-pipe entry)",
         "kernel_ms_per_launch": dom_launch_ms, "kernel_share_of_step": dom_ms * args.steps / total_kernel_ms if total_kernel_ms else None,
         "algorithmic_mac_per_launch": dom_mac_launch, "mac_per_modmul": MAC_PER_MODMUL, "mac_per_modsqr": SQR_MAC,
