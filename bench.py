@@ -625,7 +625,9 @@ def run_ours_msm_large(args, rank, world, dist):
         cnt = min(nuniq, n - have)
         lib.check(lib.c.cpg_d2d(bases.ptr + have * rt.AFF, uaff.ptr, cnt * rt.AFF))
         have += cnt
-    sc_bytes = bytearray(rng.randbytes(32 * n))             # seeded: every rank must hold the same scalars
+    sc_bytes = bytearray()                                  # seeded: every rank must hold the same scalars
+    while len(sc_bytes) < 32 * n:                           # (randbytes is limited to 2^28 bytes per call)
+        sc_bytes += rng.randbytes(min(1 << 24, 32 * n - len(sc_bytes)))
     sc_bytes[31::32] = bytes(b & 0x3F for b in sc_bytes[31::32])      # < 2^254 < r
     scalars = lib.upload(bytes(sc_bytes))
     c = args.window or int(lib.c.cpg_msm_pick_window(n))
