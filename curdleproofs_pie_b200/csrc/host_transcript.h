@@ -26,6 +26,17 @@
 #define CPGH_SEL(name) H_##name
 #endif
 
+// The per-proof kernels (transcript + Fr algebra, one thread per proof) were 213 k (ProveStep) and 150 k
+// (VerifyPhase2) SASS instructions with everything inlined.  The Keccak permutation, the Fr product and the Fr
+// inversion are real functions (operands and results in registers): same speed, a quarter of the code and of the
+// nvcc time.  The STROBE absorb loop stays inline: as a function its byte accesses lose their address space
+// (generic LD/ST instead of LDL/LDG) and the transcript kernels slow down by 15 %.
+#if defined(__CUDACC__)
+#define CPGH_CALL __host__ __device__ __noinline__
+#else
+#define CPGH_CALL inline
+#endif
+
 namespace cpgh {
 
 typedef unsigned __int128 u128;
@@ -42,7 +53,7 @@ static const uint64_t H_KECCAK_RC[24] = CPGH_KECCAK_RC_INIT;
 static __device__ __constant__ uint64_t D_KECCAK_RC[24] = CPGH_KECCAK_RC_INIT;
 #endif
 
-CPG_HD void keccak_f1600(uint64_t* A) {
+CPGH_CALL void keccak_f1600(uint64_t* A) {
     for (int r = 0; r < 24; r++) {
         uint64_t C0 = A[0] ^ A[5] ^ A[10] ^ A[15] ^ A[20], C1 = A[1] ^ A[6] ^ A[11] ^ A[16] ^ A[21];
         uint64_t C2 = A[2] ^ A[7] ^ A[12] ^ A[17] ^ A[22], C3 = A[3] ^ A[8] ^ A[13] ^ A[18] ^ A[23];
@@ -127,13 +138,36 @@ struct Strobe128 {
 // ------------------------------------------------------------------------- Fr (host) ---
 // 4 x u64 Montgomery arithmetic mod r; values are kept in Montgomery form inside `HFr` (host Fr).
 struct HFr { uint64_t l[4]; };
+// 32-byte scalars / coefficient rows live at 8-byte-aligned offsets of every buffer of this library (rows start at
+// multiples of 32, wire scalars at multiples of 16).  A plain memcpy / memset on a uint8_t* compiles to BYTE loads and
+// stores in device code (40 k byte stores per proof and round when zeroing the coefficient rows), so 32-byte items move
+// as four u64 whenever the pointer allows it, and rows are zeroed 8 bytes at a time.
+CPG_HD void copy32(void* dst, const void* src) {
+    if ((((uintptr_t)dst | (uintptr_t)src) & 7) == 0) {
+        uint64_t* d = (uint64_t*)dst; const uint64_t* s = (const uint64_t*)src;
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+    } else {
+        memcpy(dst, src, 32);
+    }
+}
+CPG_HD void zero_bytes(uint8_t* p, size_t n) {
+    if ((((uintptr_t)p | n) & 7) == 0) {
+        uint64_t* q = (uint64_t*)p;
+        for (size_t i = 0; i < n / 8; i++) q[i] = 0;
+    } else {
+        memset(p, 0, n);
+    }
+}
 #define CPGH_FR_MOD_INIT {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL}
 #define CPGH_FR_R1_INIT {0x00000001fffffffeULL, 0x5884b7fa00034802ULL, 0x998c4fefecbc4ff5ULL, 0x1824b159acc5056fULL}  /* 2^256 mod r */
 #define CPGH_FR_R2_INIT {0xc999e990f3f29c6dULL, 0x2b6cedcb87925c23ULL, 0x05d314967254398fULL, 0x0748d9d99f59ff11ULL}  /* 2^512 mod r */
 static const uint64_t H_FR_MOD[4] = CPGH_FR_MOD_INIT;
 static const uint64_t H_FR_R1[4] = CPGH_FR_R1_INIT;
 static const uint64_t H_FR_R2[4] = CPGH_FR_R2_INIT;
+#define CPGH_FR_R3_INIT {0xc62c1807439b73afULL, 0x1b3e0d188cf06990ULL, 0x73d13c71c7b5f418ULL, 0x6e2a5bb9c8db33e9ULL}  /* 2^768 mod r */
+static const uint64_t H_FR_R3[4] = CPGH_FR_R3_INIT;
 #if defined(__CUDACC__)
+static __device__ __constant__ uint64_t D_FR_R3[4] = CPGH_FR_R3_INIT;
 static __device__ __constant__ uint64_t D_FR_MOD[4] = CPGH_FR_MOD_INIT;
 static __device__ __constant__ uint64_t D_FR_R1[4] = CPGH_FR_R1_INIT;
 static __device__ __constant__ uint64_t D_FR_R2[4] = CPGH_FR_R2_INIT;
@@ -163,7 +197,7 @@ CPG_HD HFr fr_sub(const HFr& a, const HFr& b) {
     if (br) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)r.l[i] + FR_MOD[i]; r.l[i] = (uint64_t)c; c >>= 64; } }
     return r;
 }
-CPG_HD HFr fr_mul(const HFr& a, const HFr& b) {
+CPGH_CALL HFr fr_mul(HFr a, HFr b) {
     uint64_t t[5] = {0, 0, 0, 0, 0};
     for (int i = 0; i < 4; i++) {
         u128 c = 0;
@@ -186,7 +220,7 @@ CPG_HD HFr fr_neg(const HFr& a) { return fr_sub(fr_zero(), a); }
 CPG_HD HFr fr_from_u64(uint64_t v) { HFr r = {{v, 0, 0, 0}}; return fr_mul(r, fr_r2()); }
 // canonical 32-byte little-endian -> HFr; false if >= r
 CPG_HD bool fr_from_bytes(HFr* out, const uint8_t* b) {
-    HFr r; memcpy(r.l, b, 32);
+    HFr r; copy32(r.l, b);
     if (fr_geq_mod(r.l)) return false;
     *out = fr_mul(r, fr_r2());
     return true;
@@ -194,21 +228,54 @@ CPG_HD bool fr_from_bytes(HFr* out, const uint8_t* b) {
 CPG_HD void fr_to_bytes(uint8_t* b, const HFr& a) {
     HFr one = {{1, 0, 0, 0}};
     HFr r = fr_mul(a, one);
-    memcpy(b, r.l, 32);
+    copy32(b, r.l);
 }
 CPG_HD HFr fr_pow_u64(HFr a, uint64_t e) {
     HFr r = fr_one();
     while (e) { if (e & 1) r = fr_mul(r, a); a = fr_mul(a, a); e >>= 1; }
     return r;
 }
-CPG_HD HFr fr_inv(const HFr& a) {   // a^(r-2); 0 -> 0
-    uint64_t e[4] = {FR_MOD[0] - 2, FR_MOD[1], FR_MOD[2], FR_MOD[3]};
-    HFr r = fr_one();
-    for (int i = 255; i >= 0; i--) {
-        r = fr_mul(r, r);
-        if ((e[i >> 6] >> (i & 63)) & 1) r = fr_mul(r, a);
+// Inverse by the binary extended Euclidean algorithm (HAC 14.61) on the plain integers: ~600 iterations of
+// shifts / subtractions on 4 limbs instead of the 420 Montgomery products of a^(r-2) - the per-round challenge
+// inversions were half of the prover's per-proof Fr work.  0 -> 0.
+//   input A = a R (Montgomery form);  binv(A) = a^-1 R^-1;  mont(binv(A), R^3) = a^-1 R.
+CPG_HD bool fr_u256_geq(const uint64_t* a, const uint64_t* b) {
+    for (int i = 3; i >= 0; i--) { if (a[i] != b[i]) return a[i] > b[i]; }
+    return true;
+}
+CPG_HD void fr_u256_sub(uint64_t* a, const uint64_t* b) {            // a -= b (a >= b)
+    u128 br = 0;
+    for (int i = 0; i < 4; i++) { u128 d = (u128)a[i] - b[i] - (uint64_t)br; a[i] = (uint64_t)d; br = (d >> 64) & 1; }
+}
+CPG_HD void fr_u256_shr1(uint64_t* a) {
+    for (int i = 0; i < 3; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 63);
+    a[3] >>= 1;
+}
+CPG_HD void fr_halve_mod(uint64_t* x) {                              // x / 2 mod r, x < r: (x or x + r) >> 1, x + r < 2^256
+    if (x[0] & 1) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)x[i] + FR_MOD[i]; x[i] = (uint64_t)c; c >>= 64; } }
+    fr_u256_shr1(x);
+}
+CPG_HD void fr_sub_into_mod(uint64_t* x, const uint64_t* y) {        // x = x - y mod r, both < r
+    u128 br = 0;
+    for (int i = 0; i < 4; i++) { u128 d = (u128)x[i] - y[i] - (uint64_t)br; x[i] = (uint64_t)d; br = (d >> 64) & 1; }
+    if (br) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)x[i] + FR_MOD[i]; x[i] = (uint64_t)c; c >>= 64; } }
+}
+CPGH_CALL HFr fr_inv(HFr a) {
+    if (fr_is_zero(a)) return a;
+    uint64_t u[4], v[4], x1[4] = {1, 0, 0, 0}, x2[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) { u[i] = a.l[i]; v[i] = FR_MOD[i]; }
+    for (;;) {                                                       // gcd(u, v) = 1 (r prime): ends with u = 1 or v = 1
+        const bool u1 = u[0] == 1 && (u[1] | u[2] | u[3]) == 0, v1 = v[0] == 1 && (v[1] | v[2] | v[3]) == 0;
+        if (u1 || v1) {
+            HFr t, r3;
+            for (int i = 0; i < 4; i++) { t.l[i] = u1 ? x1[i] : x2[i]; r3.l[i] = CPGH_SEL(FR_R3)[i]; }
+            return fr_mul(t, r3);
+        }
+        if (!(u[0] & 1)) { fr_u256_shr1(u); fr_halve_mod(x1); }
+        else if (!(v[0] & 1)) { fr_u256_shr1(v); fr_halve_mod(x2); }
+        else if (fr_u256_geq(u, v)) { fr_u256_sub(u, v); fr_sub_into_mod(x1, x2); }
+        else { fr_u256_sub(v, u); fr_sub_into_mod(x2, x1); }
     }
-    return r;
 }
 // in-place batch inversion (Montgomery's trick); zeros stay zero
 CPG_HD void fr_batch_inv(HFr* v, size_t n, HFr* scratch) {

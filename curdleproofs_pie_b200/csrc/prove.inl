@@ -78,8 +78,8 @@ CPG_HD HFr prand(const PBuffers& pb, const PShape& sh, size_t b, uint32_t i) {
     HFr v; cpgh::fr_from_bytes(&v, pb.rand + (b * sh.NR + i) * 32); return v;
 }
 CPG_HD void zero_rows(const PShape& sh, const PBuffers& pb, size_t b, uint32_t nfix, uint32_t nvar) {
-    for (uint32_t o = 0; o < nfix; o++) memset(frow(sh, pb, b, o), 0, (size_t)sh.NF * 32);
-    for (uint32_t o = 0; o < nvar; o++) memset(vrow(sh, pb, b, o), 0, (size_t)sh.ell * 32);
+    for (uint32_t o = 0; o < nfix; o++) cpgh::zero_bytes(frow(sh, pb, b, o), (size_t)sh.NF * 32);
+    for (uint32_t o = 0; o < nvar; o++) cpgh::zero_bytes(vrow(sh, pb, b, o), (size_t)sh.ell * 32);
 }
 CPG_HD HFr ip(const FrVec& a, const FrVec& b, uint32_t n) {
     HFr acc = cpgh::fr_zero();
@@ -292,7 +292,7 @@ CPG_HD void prove_step(const PShape& sh, const POut& O, const PBuffers& pb, uint
         uint8_t *vR = vrow(sh, pb, b, 0), *vS = vrow(sh, pb, b, 1);
         for (uint32_t i = 0; i < ell; i++) {
             fr_to_bytes(vR + 32 * (size_t)i, a[i]);
-            memcpy(vS + 32 * (size_t)i, vR + 32 * (size_t)i, 32);
+            cpgh::copy32(vS + 32 * (size_t)i, vR + 32 * (size_t)i);
         }
         const size_t iH = n, iGt = n + 1, iGu = n + 2;
         fr_to_bytes(frow(sh, pb, b, 2) + 32 * iGt, s.r_t);      // cm_T = (G_t r_t, R' k + H r_t)
@@ -325,7 +325,7 @@ CPG_HD void prove_step(const PShape& sh, const POut& O, const PBuffers& pb, uint
         fr_to_bytes(fAp + 32 * (size_t)(n + 2), s.r_u);          // + cm_U.T_1 = G_u r_u
         for (uint32_t L = 0; L < n; L++) fr_to_bytes(fBa + 32 * (size_t)gwb_index(sh, L), w2[L]);
         uint8_t *vT = vrow(sh, pb, b, 0), *vU = vrow(sh, pb, b, 1);
-        for (uint32_t i = 0; i < ell; i++) { fr_to_bytes(vT + 32 * (size_t)i, w2[i]); memcpy(vU + 32 * (size_t)i, vT + 32 * (size_t)i, 32); }
+        for (uint32_t i = 0; i < ell; i++) { fr_to_bytes(vT + 32 * (size_t)i, w2[i]); cpgh::copy32(vU + 32 * (size_t)i, vT + 32 * (size_t)i); }
         fr_to_bytes(fBt + 32 * (size_t)n, w2[ell + 2]);          // T_wb = vec_T | 0 0 H 0
         fr_to_bytes(fBu + 32 * (size_t)n, w2[ell + 3]);          // U_wb = vec_U | 0 0 0 H
         s.tr = tr;
@@ -376,7 +376,7 @@ CPG_HD void prove_step(const PShape& sh, const POut& O, const PBuffers& pb, uint
             if (L < ell) {
                 uint8_t* vT = right ? vLT : vRT;
                 fr_to_bytes(vT + 32 * (size_t)L, coef);
-                memcpy((right ? vLU : vRU) + 32 * (size_t)L, vT + 32 * (size_t)L, 32);
+                cpgh::copy32((right ? vLU : vRU) + 32 * (size_t)L, vT + 32 * (size_t)L);
             } else if (L == ell + 2) {
                 fr_to_bytes((right ? fLT : fRT) + 32 * (size_t)n, coef);          // H inside T_wb
             } else if (L == ell + 3) {

@@ -126,8 +126,8 @@ CPG_HD void verify_phase2(const VShape& sh, const Layout& L, const VBuffers& vb,
     const uint32_t ell = sh.ell, n = sh.n, lg = sh.lg, NV = sh.NV, NF = sh.NF, NI = sh.NI;
     uint8_t* vrow = vb.vs + b * (size_t)NV * 32;
     uint8_t* frow = vb.fs + b * (size_t)NF * 32;
-    memset(vrow, 0, (size_t)NV * 32);
-    memset(frow, 0, (size_t)NF * 32);
+    zero_bytes(vrow, (size_t)NV * 32);
+    zero_bytes(frow, (size_t)NF * 32);
     bool rej = s.bad || vb.t0[b];
     const uint8_t* e = vb.err + b * (size_t)NV;
     for (uint32_t i = 0; i + 1 < NV && !rej; i++) if (e[i]) rej = true;   // any malformed point encoding
@@ -335,10 +335,10 @@ struct GroupSumFixed {            // thread = (group, i < NF): sum of the G proo
         HFr acc = cpgh::fr_zero();
         for (uint32_t k = 0; k < G; k++) {
             HFr v;                                                       // canonical integers < r: add mod r as they are
-            memcpy(v.l, fs + ((g * G + k) * (uint64_t)NF + i) * 32, 32);
+            cpgh::copy32(v.l, fs + ((g * G + k) * (uint64_t)NF + i) * 32);
             acc = cpgh::fr_add(acc, v);
         }
-        memcpy(out + t * 32, acc.l, 32);
+        cpgh::copy32(out + t * 32, acc.l);
     }
 };
 struct GroupTest {                // thread = group: provisional verdict of its G proofs
