@@ -31,8 +31,9 @@ def test_msm_both_pipelines(seam_lib, cref, B, n, window, shared, path):
     seam_lib.check(seam_lib.c.cpg_msm_force_path(path))
     try:
         pc.case_msm(seam_lib, cref, B, n, window, shared)
-        if path == 1:
-            pc.case_msm(seam_lib, cref, 4, 12, 4, shared=False, edge=True)
+        # zero scalars, k = r - 1, identity bases, P and -P / the same base twice in one bucket
+        pc.case_msm(seam_lib, cref, 4, 12, 4, shared=False, edge=True)
+        pc.case_msm(seam_lib, cref, 3, 12, 3, shared=True, edge=True)
     finally:
         seam_lib.check(seam_lib.c.cpg_msm_force_path(0))
 
