@@ -92,16 +92,20 @@ CPG_HD void mont_step(uint32_t* x, uint32_t* y, const uint32_t* a, uint32_t bi, 
     cmad_even<N>(y, p + 1, m);          // y += p_odd * m
 }
 
+// 32 x 32 -> 64 as ONE IMAD.WIDE.U32 (a separate a*b and __umulhi(a, b) compile to IMAD + IMAD.HI)
+CPG_HD void mul_wide(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+    uint64_t p = (uint64_t)a * b;
+    lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
+}
+
 // r = a * b / 2^(32N) mod p, all operands < p, result < p.  r may alias a or b.
 template <int N>
 CPG_HD void mont_mul_n(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p, uint32_t inv) {
     uint32_t e[N], o[N];
 #pragma unroll
     for (int j = 0; j < N; j += 2) {
-        e[j] = mul_lo(a[j], b[0]);
-        e[j + 1] = mul_hi(a[j], b[0]);
-        o[j] = mul_lo(a[j + 1], b[0]);
-        o[j + 1] = mul_hi(a[j + 1], b[0]);
+        mul_wide(a[j], b[0], e[j], e[j + 1]);
+        mul_wide(a[j + 1], b[0], o[j], o[j + 1]);
     }
     {
         uint32_t m = mul_lo(e[0], inv);
@@ -218,10 +222,8 @@ CPG_HD void mont_sqr_n(uint32_t* r, const uint32_t* a, const uint32_t* p, uint32
         sqr_row_vec<N, 0>(f, a, d);
 #pragma unroll
         for (int j = 0; j < N; j += 2) {
-            e[j] = mul_lo(f[j], a[0]);
-            e[j + 1] = mul_hi(f[j], a[0]);
-            o[j] = mul_lo(f[j + 1], a[0]);
-            o[j + 1] = mul_hi(f[j + 1], a[0]);
+            mul_wide(f[j], a[0], e[j], e[j + 1]);
+            mul_wide(f[j + 1], a[0], o[j], o[j + 1]);
         }
         uint32_t m = mul_lo(e[0], inv);
         cmad_even<N>(e, p, m);

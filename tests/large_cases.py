@@ -3,12 +3,21 @@ The fixtures (oracle/gen_golden_large.py) hold only the seed and SHA-256 digests
 reference produced; every input point is s_i * G with s_i drawn from Python's `random` in the reference's
 order, so the inputs are rebuilt here on the device and pinned by their digests first."""
 import hashlib
+import json
+import os
 import random
 import time
 
-import shuffle_cases as sc
 from curdleproofs_pie_b200 import runtime as rt
 from curdleproofs_pie_b200 import whisk
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_case(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
 
 
 def sha(b):
@@ -58,7 +67,7 @@ def rebuild_inputs(lib, case, n_rand):
 def check_large(lib, name, fixed_window=8):
     """prove: trackers and proof bytes equal the reference's; verify: the reference's verdicts on the honest
     and the swapped inputs.  Returns the timings."""
-    case = sc.load_case(name)
+    case = load_case(name)
     N = case["N"]
     ell = N - 4
     t0 = time.perf_counter()
