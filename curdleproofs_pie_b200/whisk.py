@@ -15,7 +15,9 @@ from . import runtime as _rt
 class BatchVerifier:
     """Holds the device-resident CRS (fixed-base tables) for one (ell, n_blinders)."""
 
-    def __init__(self, crs_bytes, ell, n_blinders=4, fixed_window=0, host_threads=0, lib=None):
+    def __init__(self, crs_bytes, ell, n_blinders=4, fixed_window=0, host_threads=0, lib=None, group=0):
+        """group: proofs per aggregated check (cpg_verifier_set_group): 0 = adaptive (default: the library re-picks
+        the group size after every batch from the observed rate of failing proofs), 1 = one MSM per proof."""
         self.lib = lib or _rt.get_lib()
         self.ell = int(ell)
         self.n_blinders = int(n_blinders)
@@ -27,6 +29,7 @@ class BatchVerifier:
             raise _rt.CpgError("cpg_verifier_create failed: " + self.lib.last_error())
         self.proof_len = int(self.lib.c.cpg_verifier_proof_bytes(self.handle))
         self.input_len = int(self.lib.c.cpg_verifier_input_bytes(self.handle))
+        self.set_group(group)
 
     def set_window(self, c):
         self.lib.check(self.lib.c.cpg_verifier_set_window(self.handle, int(c)), "cpg_verifier_set_window")
