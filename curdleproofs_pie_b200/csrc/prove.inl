@@ -97,7 +97,7 @@ struct PRand { uint32_t m_bl = 0, a_bl = 4, c_bl = 6, ipa_r = 10, ipa_z, r_t, r_
 // 6+lg A',B_a,B_t,B_u | 7+lg..6+2lg SameMSM | 7+2lg finish (assemble the wire proof).
 CPG_HD void prove_step(const PShape& sh, const POut& O, const PBuffers& pb, uint32_t round, size_t b) {
     using namespace cpgh;
-    const uint32_t ell = sh.ell, n = sh.n, lg = sh.lg, NF = sh.NF;
+    const uint32_t ell = sh.ell, n = sh.n, lg = sh.lg;
     const PRand RO(n);
     PState& s = pb.st[b];
     const uint8_t* outs = pb.outs48 + b * (size_t)O.NOUT * 48;
@@ -786,7 +786,7 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
     Prover& p = *(Prover*)handle;
     const PShape sh = p.sh;
     const POut O(sh.lg);
-    const uint32_t ell = sh.ell, lg = sh.lg;
+    const uint32_t ell = sh.ell;
     size_t first[P_MAX_LANES], count[P_MAX_LANES];
     const int k = p.split(B, first, count);
     std::vector<uint32_t> k12(B * 8);
