@@ -932,7 +932,7 @@ def main():
     ap.add_argument("--group", type=int, default=0, help="cross-proof aggregation: proofs per aggregated MSM (1 = per-proof MSMs, 0 = adaptive); failing groups are re-checked per proof")
     ap.add_argument("--group-window", type=int, default=0, help="window of the aggregated MSM (0 = model)")
     ap.add_argument("--corrupt-every", type=int, default=64, help="one lane in this many carries a corrupted proof or input (0 = none)")
-    ap.add_argument("--streams", type=int, default=2, help="sub-batches in flight on separate CUDA streams")
+    ap.add_argument("--streams", type=int, default=4, help="sub-batches in flight on separate CUDA streams")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads for the transcript (0 = all cores)")
     ap.add_argument("--cpu-sample", type=int, default=400, help="MSMs in the bounded CPU sample (msm workload)")
     ap.add_argument("--cpu-sample-verify", type=int, default=24, help="verifications in the bounded CPU sample")

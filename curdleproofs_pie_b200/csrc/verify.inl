@@ -24,6 +24,7 @@
 // ~2^-250 over the batching weights (the reference's own accumulator has the same soundness error).
 #include "host_transcript.h"
 
+#include <functional>
 #include <thread>
 
 namespace {
@@ -399,7 +400,7 @@ struct Verifier {
 #else
     void* streams[8] = {};
 #endif
-    int nstreams = 2;
+    int nstreams = 4;
 #ifndef CPG_HOST_EMU
     cudaStream_t side_stream = nullptr;
     cudaEvent_t side_ev[2] = {};
@@ -576,8 +577,10 @@ struct Verifier {
     // Transcript on the device: nothing crosses PCIe between the stages.  The batch is cut into
     // sub-batches, each enqueued on its own stream, so the latency-bound kernels of one sub-batch
     // (transcript phases, Horner, sort) run under the integer-pipe-bound kernels of the others.
-    // `upload` = also copy each sub-batch's wire bytes from the pinned staging buffers first.
-    int device_all(size_t B, bool upload) {
+    // `upload` = also copy each sub-batch's wire bytes from the pinned staging buffers first; `stage` (optional)
+    // fills those buffers for proofs [b0, b0 + nb) right before their copy is enqueued, so the host stages
+    // sub-batch k + 1 while the GPU works on sub-batch k.
+    int device_all(size_t B, bool upload, const std::function<void(size_t, size_t)>& stage = nullptr) {
         const Layout L(sh.lg);
         VBuffers vb = device_buffers();
         size_t S = nstreams > 0 ? (size_t)nstreams : 1;
@@ -589,6 +592,7 @@ struct Verifier {
         for (size_t b0 = 0; b0 < B && !rc; b0 += per, si++) {
             size_t nb = B - b0 < per ? B - b0 : per;
             StreamScope scope(S > 1 ? streams[si % S] : nullptr);
+            if (upload && stage) stage(b0, nb);
             if (upload) {
                 rc = cpg_h2d(d_wire + b0 * sh.NV * 48, h_wire + b0 * sh.NV * 48, nb * sh.NV * 48);
                 if (!rc) rc = cpg_h2d(d_psc + b0 * 224, h_psc + b0 * 224, nb * 224);
@@ -719,20 +723,24 @@ int cpg_verify_batch(void* handle, const uint8_t* inputs, const uint8_t* proofs,
     // ---- stage wire points contiguously per proof: R|S|T|U|M|proof points|(slot for D) ----
     uint8_t* wire = v.h_wire;
     uint8_t* psc = v.h_psc;
-    parallel_for(v.threads, B, [&](size_t b) {
-        uint8_t* row = wire + b * (size_t)NV * 48;
-        memcpy(row, inputs + b * in_len, in_len);
-        const uint8_t* pr = proofs + b * v.proof_len;
-        memcpy(row + in_len, pr, 48);                                   // M
-        split_proof(pr + 48, lg, row + (size_t)NI * 48, psc + b * 7 * 32);
-        memset(row + (size_t)(NV - 1) * 48, 0, 48);
-        row[(size_t)(NV - 1) * 48] = 0xc0;                              // D slot: decodes to identity
-    });
+    auto stage = [&](size_t b0, size_t nb) {
+        parallel_for(v.threads, nb, [&](size_t i) {
+            const size_t b = b0 + i;
+            uint8_t* row = wire + b * (size_t)NV * 48;
+            memcpy(row, inputs + b * in_len, in_len);
+            const uint8_t* pr = proofs + b * v.proof_len;
+            memcpy(row + in_len, pr, 48);                                   // M
+            split_proof(pr + 48, lg, row + (size_t)NI * 48, psc + b * 7 * 32);
+            memset(row + (size_t)(NV - 1) * 48, 0, 48);
+            row[(size_t)(NV - 1) * 48] = 0xc0;                              // D slot: decodes to identity
+        });
+    };
     if (v.transcript_on_device) {
         if (int rc = v.fork_streams()) return rc;
-        if (int rc = v.device_all(B, true)) return rc;
+        if (int rc = v.device_all(B, true, stage)) return rc;               // staging of sub-batch k+1 overlaps the GPU work on k
         return cpg_d2h(verdicts, v.d_ok, B);
     }
+    stage(0, B);
 
     // ---- transcript on host threads ----
     if (int rc = cpg_h2d(v.d_wire, wire, (size_t)B * NV * 48)) return rc;

@@ -146,7 +146,8 @@ int cpg_verifier_set_window(void* verifier, int var_window);
 /* where the Fiat-Shamir transcript + coefficient algebra run: 1 = one proof per GPU thread (default;
  * only wire bytes cross PCIe), 0 = on `host_threads` host threads (the reference's placement) */
 int cpg_verifier_set_transcript(void* verifier, int on_device);
-/* sub-batches in flight on separate CUDA streams (1..8, default 2; device transcript only) */
+/* sub-batches in flight on separate CUDA streams (1..8, default 4; device transcript only); the host stages the wire
+ * bytes of sub-batch k + 1 while the GPU works on sub-batch k */
 int cpg_verifier_set_streams(void* verifier, int nstreams);
 /* Cross-proof aggregation: `group` (a power of two, default 1 = off) consecutive proofs
  * are accepted by ONE MSM over their group*NV variable bases and ONE fixed-base MSM over their summed
