@@ -432,6 +432,16 @@ int cpg_d2h(void* h, const void* d, size_t bytes) {
 #endif
     return 0;
 }
+// device -> PINNED host memory on the current stream, no synchronisation (internal: results of one lane / sub-batch
+// leave while the others still compute; the caller synchronises once)
+static int d2h_async(void* h_pinned, const void* d, size_t bytes) {
+#ifndef CPG_HOST_EMU
+    CK(cudaMemcpyAsync(h_pinned, d, bytes, cudaMemcpyDeviceToHost, cur()));
+#else
+    memcpy(h_pinned, d, bytes);
+#endif
+    return 0;
+}
 int cpg_d2d(void* dst, const void* src, size_t bytes) {
     NEED_INIT();
 #ifndef CPG_HOST_EMU

@@ -504,6 +504,8 @@ struct ProverLane {
     size_t cap = 0, B = 0;
     uint8_t *d_in48 = nullptr, *d_tu48 = nullptr, *d_k = nullptr, *d_rand = nullptr, *d_outs = nullptr, *d_fs = nullptr, *d_vs = nullptr, *d_proof = nullptr, *d_err = nullptr;
     uint32_t *d_perm = nullptr, *d_off = nullptr; Aff* d_bases = nullptr; PState* d_st = nullptr; HFr* d_vec = nullptr; Jac *d_fix = nullptr, *d_var = nullptr;
+    uint8_t *h_tu = nullptr, *h_outs = nullptr, *h_proof = nullptr, *h_err = nullptr;   // pinned: results leave per lane
+    uint8_t *h_in = nullptr, *h_rand = nullptr;   // pinned staging of the two large inputs (pageable caller memory copies at a third of the rate)
     uint32_t* d_k12 = nullptr;    // [B][8] GLV halves of k
     Aff* d_tab = nullptr; uint32_t tab_ts = 0;   // multiples 1..tab_ts of every T_i, U_i: [B][2 ell][tab_ts]
     Jac* d_tab_jac = nullptr; Fq* d_tab_pz = nullptr;   // build scratch for TAB_CHUNK bases at a time
@@ -513,6 +515,8 @@ struct ProverLane {
     std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_off, d_bases, d_st, d_vec, d_fix, d_var, d_tab, d_tab_jac, d_tab_pz, d_k12}; }
     void release() {
         for (void* q : all()) cpg_free(q);
+        cpg_host_free(h_tu); cpg_host_free(h_outs); cpg_host_free(h_proof); cpg_host_free(h_err); cpg_host_free(h_in); cpg_host_free(h_rand);
+        h_tu = h_outs = h_proof = h_err = h_in = h_rand = nullptr;
         d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = d_off = nullptr; d_bases = nullptr; d_st = nullptr; d_vec = nullptr; d_fix = d_var = nullptr; d_tab = nullptr; d_tab_jac = nullptr; d_tab_pz = nullptr; d_k12 = nullptr;
         cap = 0;
     }
@@ -534,7 +538,11 @@ struct ProverLane {
         d_bases = (Aff*)cpg_malloc(sizeof(Aff) * Bn * 4 * ell); d_st = (PState*)cpg_malloc(sizeof(PState) * Bn);
         d_vec = (HFr*)cpg_malloc(sizeof(HFr) * Bn * PV_COUNT * n);
         d_fix = (Jac*)cpg_malloc(sizeof(Jac) * Bn * P_MAX_OUT); d_var = (Jac*)cpg_malloc(sizeof(Jac) * Bn * P_MAX_VAR);
+        h_tu = (uint8_t*)cpg_host_alloc(Bn * 2 * ell * 48); h_outs = (uint8_t*)cpg_host_alloc(Bn * NOUT * 48);
+        h_proof = (uint8_t*)cpg_host_alloc(Bn * proof_len);   h_err = (uint8_t*)cpg_host_alloc(Bn * 2 * ell);
+        h_in = (uint8_t*)cpg_host_alloc(Bn * 2 * ell * 48);   h_rand = (uint8_t*)cpg_host_alloc(Bn * sh.NR * 32);
         for (void* q : all()) if (!q) { release(); return fail("cpg_prove_batch: device allocation failed"); }
+        if (!h_tu || !h_outs || !h_proof || !h_err || !h_in || !h_rand) { release(); return fail("cpg_prove_batch: pinned host allocation failed"); }
         cap = Bn;
         return 0;
     }
@@ -666,8 +674,9 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
 }
 // All lanes, rounds issued alternately.  The lane streams fork from the caller's stream and join it again,
 // so events recorded on the caller's stream (cpg_timer_*) bracket the whole batch.
-int prove_device_all(Prover& p, int k) {
+int prove_device_all(Prover& p, int k, bool download = false) {
     const uint32_t rounds = 8 + 2 * p.sh.lg;
+    const POut O(p.sh.lg);
 #ifndef CPG_HOST_EMU
     cudaStream_t caller = cur();
     const bool had = t_stream_set; cudaStream_t prev = t_stream;
@@ -685,6 +694,15 @@ int prove_device_all(Prover& p, int k) {
     for (int i = 0; i < k && !rc; i++) { enter(i); rc = prove_lane_prologue(p, p.lanes[i]); }
     for (uint32_t r = 0; r < rounds && !rc; r++)
         for (int i = 0; i < k && !rc; i++) { enter(i); rc = prove_lane_round(p, p.lanes[i], r); }
+    if (download)                                           // each lane's results leave on its own stream, under the other lanes' last rounds
+        for (int i = 0; i < k && !rc; i++) {
+            ProverLane& L = p.lanes[i];
+            enter(i);
+            rc = d2h_async(L.h_tu, L.d_tu48, L.B * 2 * (size_t)p.sh.ell * 48);
+            if (!rc) rc = d2h_async(L.h_outs, L.d_outs, L.B * (size_t)O.NOUT * 48);
+            if (!rc) rc = d2h_async(L.h_proof, L.d_proof, L.B * p.proof_len);
+            if (!rc) rc = d2h_async(L.h_err, L.d_err, L.B * 2 * (size_t)p.sh.ell);
+        }
     leave();
 #ifndef CPG_HOST_EMU
     if (k > 1) for (int i = 0; i < k; i++) {
@@ -789,9 +807,10 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
     const uint32_t ell = sh.ell;
     size_t first[P_MAX_LANES], count[P_MAX_LANES];
     const int k = p.split(B, first, count);
+    const int threads = (int)std::max(1u, std::thread::hardware_concurrency());
     std::vector<uint32_t> k12(B * 8);
     std::vector<uint8_t> bad_k(B, 0);
-    for (size_t b = 0; b < B; b++) bad_k[b] = glv_split(ks + 32 * b, k12.data() + 8 * b) ? 0 : 1;
+    parallel_for(threads, B, [&](size_t b) { bad_k[b] = glv_split(ks + 32 * b, k12.data() + 8 * b) ? 0 : 1; });
     for (int i = 0; i < k; i++) {
         ProverLane& L = p.lanes[i];
         const size_t f = first[i], c = count[i];
@@ -799,31 +818,36 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
         // (msm, window), so large shuffles keep the bucket method
         if (int rc = L.reserve(sh, p.proof_len, c, O.NOUT, (p.table_window > 0 && ell <= 2048) ? 1u << (p.table_window - 1) : 0)) return rc;
         L.B = c;
-        if (int rc = cpg_h2d(L.d_in48, inputs + f * 2 * (size_t)ell * 48, c * 2 * (size_t)ell * 48)) return rc;
+        // the two large inputs go through pinned staging, copied by all host threads
+        const size_t in_row = 2 * (size_t)ell * 48, rand_row = (size_t)sh.NR * 32;
+        parallel_for(threads, c, [&](size_t j) {
+            memcpy(L.h_in + j * in_row, inputs + (f + j) * in_row, in_row);
+            memcpy(L.h_rand + j * rand_row, rand + (f + j) * rand_row, rand_row);
+        });
+        if (int rc = cpg_h2d(L.d_in48, L.h_in, c * in_row)) return rc;
         if (int rc = cpg_h2d(L.d_perm, perms + f * (size_t)ell, c * (size_t)ell * 4)) return rc;
         if (int rc = cpg_h2d(L.d_k, ks + f * 32, c * 32)) return rc;
         if (int rc = cpg_h2d(L.d_k12, k12.data() + f * 8, c * 32)) return rc;
-        if (int rc = cpg_h2d(L.d_rand, rand + f * (size_t)sh.NR * 32, c * (size_t)sh.NR * 32)) return rc;
+        if (int rc = cpg_h2d(L.d_rand, L.h_rand, c * rand_row)) return rc;
     }
     p.lastB = B; p.lastK = k;
-    if (int rc = prove_device_all(p, k)) return rc;
-    // results: T|U, M|proof, per-lane status
-    std::vector<uint8_t> outs(B * (size_t)O.NOUT * 48), proofs(B * p.proof_len), err(B * 2 * (size_t)ell);
+    if (int rc = prove_device_all(p, k, true)) return rc;
+    if (int rc = cpg_sync()) return rc;
+    // results: T|U, M|proof, per-lane status, straight from the lanes' pinned buffers
     for (int i = 0; i < k; i++) {
         ProverLane& L = p.lanes[i];
         const size_t f = first[i], c = count[i];
-        if (int rc = cpg_d2h(out_tu + f * 2 * (size_t)ell * 48, L.d_tu48, c * 2 * (size_t)ell * 48)) return rc;
-        if (int rc = cpg_d2h(outs.data() + f * (size_t)O.NOUT * 48, L.d_outs, c * (size_t)O.NOUT * 48)) return rc;
-        if (int rc = cpg_d2h(proofs.data() + f * p.proof_len, L.d_proof, c * p.proof_len)) return rc;
-        if (int rc = cpg_d2h(err.data() + f * 2 * (size_t)ell, L.d_err, c * 2 * (size_t)ell)) return rc;
-    }
-    for (size_t b = 0; b < B; b++) {
-        uint8_t* w = out_proofs + b * (p.proof_len + 48);
-        memcpy(w, outs.data() + (b * O.NOUT + O.M) * 48, 48);
-        memcpy(w + 48, proofs.data() + b * p.proof_len, p.proof_len);
-        uint8_t bad = bad_k[b];
-        for (size_t i = 0; i < 2 * (size_t)ell; i++) bad |= err[b * 2 * ell + i];
-        if (status) status[b] = bad ? 1 : 0;
+        parallel_for(threads, c, [&](size_t j) {
+            const size_t b = f + j;
+            memcpy(out_tu + b * 2 * (size_t)ell * 48, L.h_tu + j * 2 * (size_t)ell * 48, 2 * (size_t)ell * 48);
+            uint8_t* w = out_proofs + b * (p.proof_len + 48);
+            memcpy(w, L.h_outs + (j * O.NOUT + O.M) * 48, 48);
+            memcpy(w + 48, L.h_proof + j * p.proof_len, p.proof_len);
+            uint8_t bad = bad_k[b];
+            const uint8_t* e = L.h_err + j * 2 * (size_t)ell;
+            for (size_t q = 0; q < 2 * (size_t)ell; q++) bad |= e[q];
+            if (status) status[b] = bad ? 1 : 0;
+        });
     }
     return 0;
 }
