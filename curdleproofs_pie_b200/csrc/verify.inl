@@ -454,6 +454,8 @@ struct Verifier {
     uint32_t group = 1;           // proofs per aggregated check (1 = every proof on its own MSM)
     bool group_auto = false;      // re-pick `group` after every batch from the observed rate of failing proofs
     int group_window = 0;
+    uint32_t cur_group = 1;       // group size of the batch in flight: `group`, halved until a batch of this size holds a whole group
+    void begin_batch(size_t B) { cur_group = group; while (cur_group > 1 && cur_group > B) cur_group >>= 1; }
     size_t rechecked = 0;         // proofs of the last batch that went through the per-proof fallback
     // device buffers of the current batch, kept (and grown on demand) between calls
     size_t cap = 0, lastB = 0;
@@ -523,7 +525,7 @@ struct Verifier {
     // proofs [b0, b0 + nb), b0 a multiple of `group`: whole groups through one aggregated check each
     // (provisional verdicts; recheck_failed_groups settles the failing ones), the tail proof by proof
     int device_check(size_t b0, size_t nb) {
-        const size_t G = group;
+        const size_t G = cur_group;
         const size_t ng = G > 1 ? nb / G : 0, g0 = G > 1 ? b0 / G : 0;
         if (ng) {
             if (int rc = cpg_g1_msm_batched(d_bases + b0 * sh.NV, G * sh.NV, d_vs + b0 * sh.NV * 32, ng, G * sh.NV, group_window, d_var + g0)) return rc;
@@ -550,7 +552,7 @@ struct Verifier {
     // after every sub-batch has been joined: per-proof MSMs for the proofs of the failing groups
     int recheck_failed_groups(size_t B) {
         rechecked = 0;
-        const size_t G = group, ng = G > 1 ? B / G : 0;
+        const size_t G = cur_group, ng = G > 1 ? B / G : 0;
         if (!ng) return 0;
         std::vector<uint8_t> gok(ng);
         if (int rc = cpg_d2h(gok.data(), d_gok, ng)) return rc;
@@ -585,7 +587,8 @@ struct Verifier {
         VBuffers vb = device_buffers();
         size_t S = nstreams > 0 ? (size_t)nstreams : 1;
         if (B < 64 * S) S = 1;
-        size_t align = group > 32 ? group : 32;             // warps of BucketAccumulate hold 32 MSMs; groups do not straddle sub-batches
+        begin_batch(B);
+        size_t align = cur_group > 32 ? cur_group : 32;     // warps of BucketAccumulate hold 32 MSMs; groups do not straddle sub-batches
         size_t per = ((B + S - 1) / S + align - 1) / align * align;
         int rc = 0;
         size_t si = 0;
@@ -764,6 +767,7 @@ int cpg_verify_batch(void* handle, const uint8_t* inputs, const uint8_t* proofs,
     if (int rc = cpg_h2d(v.d_vs, vs.data(), vs.size())) return rc;
     if (int rc = cpg_h2d(v.d_fs, fs.data(), fs.size())) return rc;
     if (int rc = cpg_h2d(v.d_rej, reject.data(), B)) return rc;
+    v.begin_batch(B);
     if (int rc = v.device_check(0, B)) return rc;
     if (int rc = v.recheck_failed_groups(B)) return rc;
     return cpg_d2h(verdicts, v.d_ok, B);
@@ -784,6 +788,7 @@ int cpg_verify_replay_device(void* handle, uint8_t* verdicts) {
         const Layout L(v.sh.lg);
         if (int rc = v.device_decode(0, v.lastB)) return rc;
         if (int rc = v.device_derive(0, v.lastB, L)) return rc;
+        v.begin_batch(v.lastB);
         if (int rc = v.device_check(0, v.lastB)) return rc;
         if (int rc = v.recheck_failed_groups(v.lastB)) return rc;
     }

@@ -23,3 +23,28 @@ def test_verify_batch_cross_proof_groups(seam_lib, on_device, group):
     """SURVEY 8 f-2: groups of proofs share one aggregated MSM, failing groups fall back to per-proof checks;
     the verdict of every lane (honest and corrupted variants side by side) still equals the reference's"""
     vc.check_batch(seam_lib, "shuffle_N8_seed1234.json", transcript_on_device=on_device, fixed_window=4, group=group)
+
+
+def test_adaptive_group_size_follows_the_failure_rate(seam_lib):
+    """group = 0: the library re-picks the group size after every batch (argmin of agg[G] + 1 - (1 - p)^G):
+    all-valid batches drive it to 64, a batch where every second proof is bad drives it down to 2"""
+    import shuffle_cases as sc
+    from curdleproofs_pie_b200 import whisk
+
+    case = sc.load_case("shuffle_N8_seed1234.json")
+    vs = vc.variants(case)
+    honest, bad = vs[0], vs[1]
+    ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), case["N"] - 4, fixed_window=4, lib=seam_lib, group=0)
+    assert ver.group() == 16
+    B = 32
+    assert ver.verify([honest[1]] * B, [honest[2]] * B) == [True] * B
+    assert ver.group() == 64 and ver.rechecked() == 0
+    ins = [honest[1] if i % 2 else bad[1] for i in range(B)]
+    prs = [honest[2] if i % 2 else bad[2] for i in range(B)]
+    want = [bool(i % 2) for i in range(B)]
+    assert ver.verify(ins, prs) == want            # 64 > B: this batch runs with groups of 32 - one group, which fails
+    assert ver.rechecked() == B and ver.group() == 4       # one failing group of 32: p >= 1/32
+    assert ver.verify(ins, prs) == want and ver.group() == 2 and ver.rechecked() == B   # 8 of 8 groups of 4 fail: p >= 1/4
+    assert ver.verify(ins, prs) == want and ver.group() == 2
+    assert ver.verify([honest[1]] * 5, [honest[2]] * 5) == [True] * 5 and ver.rechecked() == 0
+    ver.close()
