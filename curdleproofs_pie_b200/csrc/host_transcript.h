@@ -26,11 +26,11 @@
 #define CPGH_SEL(name) H_##name
 #endif
 
-// The per-proof kernels (transcript + Fr algebra, one thread per proof) were 213 k (ProveStep) and 150 k
-// (VerifyPhase2) SASS instructions with everything inlined.  The Keccak permutation, the Fr product and the Fr
-// inversion are real functions (operands and results in registers): same speed, a quarter of the code and of the
-// nvcc time.  The STROBE absorb loop stays inline: as a function its byte accesses lose their address space
-// (generic LD/ST instead of LDL/LDG) and the transcript kernels slow down by 15 %.
+// The per-proof kernels (transcript + Fr algebra, one thread per proof) are latency-bound.  The Keccak permutation
+// and the Fr inversion are real functions (one copy each instead of one per call site).  The Fr product stays inline:
+// as a call its HFr operands travel through the stack (10 k local loads/stores in an 18 k-instruction VerifyPhase2),
+// which is neutral for batches but 4x slower for a lone large proof; the STROBE absorb loop stays inline because as a
+// function its byte accesses lose their address space (generic LD/ST instead of LDL/LDG).
 #if defined(__CUDACC__)
 #define CPGH_CALL __host__ __device__ __noinline__
 #else
@@ -197,7 +197,7 @@ CPG_HD HFr fr_sub(const HFr& a, const HFr& b) {
     if (br) { u128 c = 0; for (int i = 0; i < 4; i++) { c += (u128)r.l[i] + FR_MOD[i]; r.l[i] = (uint64_t)c; c >>= 64; } }
     return r;
 }
-CPGH_CALL HFr fr_mul(HFr a, HFr b) {
+CPG_HD HFr fr_mul(const HFr& a, const HFr& b) {
     uint64_t t[5] = {0, 0, 0, 0, 0};
     for (int i = 0; i < 4; i++) {
         u128 c = 0;
