@@ -112,3 +112,44 @@ def check_prove_drawn(lib, name, B=3, fixed_window=0):
     ver = whisk.BatchVerifier(crs, ell, fixed_window=fixed_window, lib=lib)
     assert ver.verify([pre + tu for tu, _ in got], [pr for _, pr in got]) == [True] * B
     ver.close()
+
+
+def check_prove_with_identity_trackers(lib, name, fixed_window=0, table_window=None):
+    """Identity points really occur on the wire.  Pre-shuffle trackers that ARE the identity give identity
+    post-shuffle trackers, all-infinity rows in the prover's tables of multiples and infinities inside its MSMs: the
+    batched prover must still emit the bytes the oracle's per-proof restatement emits under the same randomness, and
+    the batched verifier must accept them."""
+    from oracle import ark_surface
+    from oracle.shuffle_ref import ShuffleRef
+
+    ark_surface.set_backend("c")
+    G1Point, Scalar = ark_surface.G1Point, ark_surface.Scalar
+    case = sc.load_case(name)
+    ell = case["N"] - 4
+    crs_bytes = bytes.fromhex(case["crs"])
+    INF = bytes([0xC0]) + bytes(47)
+    R_hex, S_hex = list(case["vec_R"]), list(case["vec_S"])
+    R_hex[1] = INF.hex(); S_hex[1] = INF.hex(); S_hex[ell - 1] = INF.hex()
+    pre = b"".join(bytes.fromhex(h) for h in R_hex + S_hex)
+    # oracle: reference draw order perm -> k -> m_bl(4) -> CurdleProofsProof.new's draws
+    ctx = ShuffleRef(G1Point, Scalar, rng=random.Random(4711))
+    crs = ctx.crs_from_bytes(crs_bytes, ell)
+    dec = lambda lst: [G1Point.from_compressed_bytes_unchecked(bytes.fromhex(h)) for h in lst]  # noqa: E731
+    vec_R, vec_S = dec(R_hex), dec(S_hex)
+    perm = list(range(ell)); ctx.rng.shuffle(perm)
+    k = ctx.rand()
+    vec_T, vec_U, M, m_bl = ctx.shuffle_and_commit(crs, vec_R, vec_S, perm, k)
+    want_proof = ctx.prove(crs, vec_R, vec_S, vec_T, vec_U, M, perm, k, m_bl)
+    want_tu = b"".join(ctx.pb(p) for p in vec_T + vec_U)
+    # the batched prover on the same stream of draws
+    prover = whisk.BatchProver(crs_bytes, ell, fixed_window=fixed_window, lib=lib)
+    if table_window is not None:
+        prover.set_table_window(table_window)
+    (tu, proof), = prover.prove_drawn([pre], random.Random(4711))
+    prover.close()
+    assert tu == want_tu, "post-shuffle trackers differ from the oracle's"
+    assert INF in (tu[48 * i:48 * i + 48] for i in range(2 * ell))
+    assert proof == ctx.pb(M) + want_proof, "proof bytes differ from the oracle's"
+    ver = whisk.BatchVerifier(crs_bytes, ell, fixed_window=fixed_window, lib=lib)
+    assert ver.verify([pre + tu], [proof]) == [ctx.is_valid(crs, vec_R, vec_S, vec_T, vec_U, M, want_proof)]
+    ver.close()

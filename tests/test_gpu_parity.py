@@ -180,6 +180,11 @@ def test_prove_with_randomness_continued_in_c(gpu_lib):
     prc.check_prove_drawn(gpu_lib, "shuffle_N128_seed4096.json", B=5)
 
 
+def test_prove_with_identity_trackers_matches_the_oracle(gpu_lib):
+    prc.check_prove_with_identity_trackers(gpu_lib, "shuffle_N16_seed77.json")
+    prc.check_prove_with_identity_trackers(gpu_lib, "shuffle_N64_seed2024.json", table_window=0)
+
+
 def test_prove_rejects_non_canonical_k(gpu_lib):
     prc.check_rejects_non_canonical_k(gpu_lib, "shuffle_N16_seed77.json")
 

@@ -34,3 +34,8 @@ def test_prove_rejects_non_canonical_k(seam_lib):
 
 def test_prove_with_randomness_continued_in_c(seam_lib):
     pc.check_prove_drawn(seam_lib, "shuffle_N8_seed1234.json", B=2, fixed_window=4)
+
+
+def test_prove_with_identity_trackers_matches_the_oracle(seam_lib):
+    pc.check_prove_with_identity_trackers(seam_lib, "shuffle_N8_seed1234.json", fixed_window=4)
+    pc.check_prove_with_identity_trackers(seam_lib, "shuffle_N16_seed77.json", fixed_window=5, table_window=0)
