@@ -130,6 +130,8 @@ def check_prove_with_identity_trackers(lib, name, fixed_window=0, table_window=N
     INF = bytes([0xC0]) + bytes(47)
     R_hex, S_hex = list(case["vec_R"]), list(case["vec_S"])
     R_hex[1] = INF.hex(); S_hex[1] = INF.hex(); S_hex[ell - 1] = INF.hex()
+    if ell >= 4:                                         # and a repeated tracker: equal points meet inside the MSMs
+        R_hex[3], S_hex[3] = R_hex[2], S_hex[2]
     pre = b"".join(bytes.fromhex(h) for h in R_hex + S_hex)
     # oracle: reference draw order perm -> k -> m_bl(4) -> CurdleProofsProof.new's draws
     ctx = ShuffleRef(G1Point, Scalar, rng=random.Random(4711))
