@@ -6,7 +6,8 @@
 //   STROBE-128, R=166   merlin_transcripts/merlin_transcripts/strobe.py:16-107
 //   Merlin framing      merlin_transcripts/merlin_transcripts/merlin_transcript.py:6-24
 //   scalar challenges   curdleproofs/curdleproofs/curdleproofs_transcript.py:15-25
-// KATs: tests/test_host_transcript.py (merlin_transcripts/test_merlin.py:18,29,40 vectors).
+// KATs: tests/test_host_transcript.py runs merlin_transcripts/test_merlin.py:18,29,40's vectors through THIS code on the
+// host and in a kernel (cpg_merlin_script, verify.inl).
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -124,6 +125,14 @@ struct Strobe128 {
     }
     CPG_HD void meta_ad(const uint8_t* d, size_t n, bool more) { begin_op(F_M | F_A, more); absorb(d, n); }
     CPG_HD void ad(const uint8_t* d, size_t n, bool more) { begin_op(F_A, more); absorb(d, n); }
+    CPG_HD void key(const uint8_t* d, size_t n, bool more) {      // strobe.py:83-85 (not used by Merlin; kept for the STROBE KAT)
+        begin_op(F_A | F_C, more);
+        for (size_t i = 0; i < n; i++) {
+            st.b[pos] = d[i];
+            pos++;
+            if (pos == RATE) run_f();
+        }
+    }
     CPG_HD void prf(uint8_t* out, size_t n, bool more) {
         begin_op(F_I | F_A | F_C, more);
         for (size_t i = 0; i < n; i++) {
@@ -300,6 +309,25 @@ struct Transcript {
         const char ds[8] = "dom-sep";
         append(ds, (const uint8_t*)label, N - 1);
     }
+    // MerlinTranscript.append_message / challenge_bytes with run-time labels (merlin_transcript.py:11-24)
+    CPG_HD void append_rt(const uint8_t* label, size_t nl, const uint8_t* msg, size_t n) {
+        uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+        s.meta_ad(label, nl, false);
+        s.meta_ad(len, 4, true);
+        s.ad(msg, n, false);
+    }
+    CPG_HD void challenge_bytes_rt(const uint8_t* label, size_t nl, uint8_t* out, size_t n) {
+        uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
+        s.meta_ad(label, nl, false);
+        s.meta_ad(len, 4, true);
+        s.prf(out, n, false);
+    }
+    CPG_HD void init_rt(const uint8_t* label, size_t nl) {
+        const uint8_t merlin[11] = {'M', 'e', 'r', 'l', 'i', 'n', ' ', 'v', '1', '.', '0'};
+        s.init(merlin, 11);
+        const uint8_t ds[7] = {'d', 'o', 'm', '-', 's', 'e', 'p'};
+        append_rt(ds, 7, label, nl);
+    }
     template <size_t N> CPG_HD void append(const char (&label)[N], const uint8_t* msg, size_t n) {
         uint8_t len[4] = {(uint8_t)n, (uint8_t)(n >> 8), (uint8_t)(n >> 16), (uint8_t)(n >> 24)};
         s.meta_ad((const uint8_t*)label, N - 1, false);
@@ -326,5 +354,38 @@ struct Transcript {
         }
     }
 };
+
+// A transcript driven by a byte script - how the KAT tests (and any host language) reach this implementation through
+// the C ABI (cpg_merlin_script).  Record: op u8 | more u8 | label_len u16 | n u32 | label | data[n] (no data for the
+// two output ops, where n = bytes wanted).  Returns the number of output bytes, or (size_t)-1 on a malformed script.
+enum { MS_STROBE_INIT = 0, MS_META_AD = 1, MS_AD = 2, MS_PRF = 3, MS_KEY = 4, MS_MERLIN_INIT = 5, MS_MERLIN_APPEND = 6, MS_MERLIN_CHALLENGE = 7 };
+CPG_HD size_t merlin_run_script(const uint8_t* sc, size_t len, uint8_t* out, size_t cap) {
+    Transcript tr;
+    memset(&tr, 0, sizeof tr);
+    size_t p = 0, o = 0;
+    while (p < len) {
+        if (p + 8 > len) return (size_t)-1;
+        const uint8_t op = sc[p], more = sc[p + 1];
+        const size_t nl = (size_t)sc[p + 2] | ((size_t)sc[p + 3] << 8);
+        const size_t n = (size_t)sc[p + 4] | ((size_t)sc[p + 5] << 8) | ((size_t)sc[p + 6] << 16) | ((size_t)sc[p + 7] << 24);
+        p += 8;
+        const bool emits = op == MS_PRF || op == MS_MERLIN_CHALLENGE;
+        if (p + nl + (emits ? 0 : n) > len || (emits && o + n > cap)) return (size_t)-1;
+        const uint8_t* label = sc + p; p += nl;
+        const uint8_t* data = sc + p; if (!emits) p += n;
+        switch (op) {
+        case MS_STROBE_INIT: tr.s.init(data, n); break;
+        case MS_META_AD: tr.s.meta_ad(data, n, more != 0); break;
+        case MS_AD: tr.s.ad(data, n, more != 0); break;
+        case MS_KEY: tr.s.key(data, n, more != 0); break;
+        case MS_PRF: tr.s.prf(out + o, n, more != 0); o += n; break;
+        case MS_MERLIN_INIT: tr.init_rt(data, n); break;
+        case MS_MERLIN_APPEND: tr.append_rt(label, nl, data, n); break;
+        case MS_MERLIN_CHALLENGE: tr.challenge_bytes_rt(label, nl, out + o, n); o += n; break;
+        default: return (size_t)-1;
+        }
+    }
+    return o;
+}
 
 }  // namespace cpgh

@@ -810,7 +810,21 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
     const int threads = (int)std::max(1u, std::thread::hardware_concurrency());
     std::vector<uint32_t> k12(B * 8);
     std::vector<uint8_t> bad_k(B, 0);
-    parallel_for(threads, B, [&](size_t b) { bad_k[b] = glv_split(ks + 32 * b, k12.data() + 8 * b) ? 0 : 1; });
+    // Caller-supplied indices and scalars are checked before anything reaches the device: perm entries index the base
+    // rows and the challenge vector, so each row must be a true permutation of [0, ell) (the reference raises IndexError
+    // otherwise), and k / every blinder must be a canonical scalar (Scalar.from_le_bytes raises ValueError).  A bad lane
+    // is flagged in status[] and proves over a harmless substitute (identity permutation, blinder 1).
+    std::vector<uint32_t> perm_ok(B * (size_t)ell);
+    parallel_for(threads, B, [&](size_t b) {
+        bad_k[b] = glv_split(ks + 32 * b, k12.data() + 8 * b) ? 0 : 1;
+        const uint32_t* pm = perms + b * (size_t)ell;
+        uint32_t* out = perm_ok.data() + b * (size_t)ell;
+        std::vector<uint8_t> seen(ell, 0);
+        bool ok = true;
+        for (uint32_t j = 0; j < ell && ok; j++) { ok = pm[j] < ell && !seen[pm[j]]; if (ok) seen[pm[j]] = 1; }
+        for (uint32_t j = 0; j < ell; j++) out[j] = ok ? pm[j] : j;
+        if (!ok) bad_k[b] = 1;
+    });
     for (int i = 0; i < k; i++) {
         ProverLane& L = p.lanes[i];
         const size_t f = first[i], c = count[i];
@@ -822,10 +836,16 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
         const size_t in_row = 2 * (size_t)ell * 48, rand_row = (size_t)sh.NR * 32;
         parallel_for(threads, c, [&](size_t j) {
             memcpy(L.h_in + j * in_row, inputs + (f + j) * in_row, in_row);
-            memcpy(L.h_rand + j * rand_row, rand + (f + j) * rand_row, rand_row);
+            uint8_t* rr = L.h_rand + j * rand_row;
+            memcpy(rr, rand + (f + j) * rand_row, rand_row);
+            for (uint32_t q = 0; q < sh.NR; q++) {
+                uint64_t w[4];
+                memcpy(w, rr + 32 * (size_t)q, 32);
+                if (cpgh::fr_geq_mod(w)) { memset(rr + 32 * (size_t)q, 0, 32); rr[32 * (size_t)q] = 1; bad_k[f + j] = 1; }
+            }
         });
         if (int rc = cpg_h2d(L.d_in48, L.h_in, c * in_row)) return rc;
-        if (int rc = cpg_h2d(L.d_perm, perms + f * (size_t)ell, c * (size_t)ell * 4)) return rc;
+        if (int rc = cpg_h2d(L.d_perm, perm_ok.data() + f * (size_t)ell, c * (size_t)ell * 4)) return rc;
         if (int rc = cpg_h2d(L.d_k, ks + f * 32, c * 32)) return rc;
         if (int rc = cpg_h2d(L.d_k12, k12.data() + f * 8, c * 32)) return rc;
         if (int rc = cpg_h2d(L.d_rand, L.h_rand, c * rand_row)) return rc;

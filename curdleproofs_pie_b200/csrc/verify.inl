@@ -26,6 +26,9 @@
 
 #include <functional>
 #include <thread>
+#if defined(__linux__)
+#include <sys/random.h>
+#endif
 
 namespace {
 
@@ -75,6 +78,7 @@ struct VBuffers {
     uint8_t* fs;                  // [B][NF][32]  fixed-base coefficients (out)
     uint8_t* reject;              // [B]          structural reject (out)
     uint8_t secret[32];
+    uint64_t nonce;               // per-call counter: identical (proof, lane) pairs do not reuse weights across calls
 };
 
 CPG_HD void verify_phase1(const VShape& sh, const Layout& L, const VBuffers& vb, size_t b) {
@@ -200,9 +204,9 @@ CPG_HD void verify_phase2(const VShape& sh, const Layout& L, const VBuffers& vb,
         Transcript fork = tr;
         fork.append("cpg_batch_secret", vb.secret, 32);
         uint64_t lane = (uint64_t)b;
-        uint8_t lb[8];
-        for (int k = 0; k < 8; k++) lb[k] = (uint8_t)(lane >> (8 * k));
-        fork.append("cpg_batch_lane", lb, 8);
+        uint8_t lb[16];
+        for (int k = 0; k < 8; k++) { lb[k] = (uint8_t)(lane >> (8 * k)); lb[8 + k] = (uint8_t)(vb.nonce >> (8 * k)); }
+        fork.append("cpg_batch_lane", lb, 16);
         uint8_t raw[12 * 32];
         fork.challenge_bytes("cpg_batch_weights", raw, sizeof raw);
         for (int k = 0; k < 12; k++) {
@@ -295,6 +299,12 @@ struct VerifyPhase2 {
     static constexpr const char* kName = "VerifyPhase2";
     VShape sh; Layout L; VBuffers vb; uint64_t b0;
     CPG_HD void operator()(uint64_t b) const { verify_phase2(sh, L, vb, (size_t)(b0 + b)); }
+};
+
+struct MerlinScript {             // one thread: the whole script (cpg_merlin_script with on_device = 1)
+    static constexpr const char* kName = "MerlinScript";
+    const uint8_t* script; size_t len; uint8_t* out; size_t cap; uint64_t* out_len;
+    CPG_HD void operator()(uint64_t) const { *out_len = (uint64_t)cpgh::merlin_run_script(script, len, out, cap); }
 };
 
 struct VerifyDerived {            // thread = proof: D = gh + B, A' = A + T_1 + U_1, their encodings
@@ -450,6 +460,7 @@ struct Verifier {
     void* table = nullptr;        // fixed-base table over the first n + 3
     void* table_gh = nullptr;     // fixed-base table over G_sum, H_sum
     uint8_t secret[32];
+    uint64_t calls = 0;           // batches checked so far (the weights' per-call nonce)
     int var_window = 0;
     uint32_t group = 1;           // proofs per aggregated check (1 = every proof on its own MSM)
     bool group_auto = false;      // re-pick `group` after every batch from the observed rate of failing proofs
@@ -499,11 +510,12 @@ struct Verifier {
         cap = B;
         return 0;
     }
-    VBuffers device_buffers() const {
+    VBuffers device_buffers() {
         VBuffers vb;
         vb.wire = d_wire; vb.psc = d_psc; vb.crs48 = d_crs48; vb.st = d_st; vb.a = d_a; vb.tmp = d_tmp; vb.chal = d_chal;
         vb.derived = d_derived; vb.err = d_err; vb.t0 = d_t0; vb.vs = d_vs; vb.fs = d_fs; vb.reject = d_rej;
         memcpy(vb.secret, secret, 32);
+        vb.nonce = ++calls;
         return vb;
     }
     // ---- the device side of proofs [b0, b0 + nb), in launch order (wire bytes already resident) ----
@@ -627,6 +639,27 @@ struct Verifier {
     }
 };
 
+// 32 bytes for the per-process batching secret: getrandom(2), else /dev/urandom; CPG_TEST_NO_ENTROPY makes both
+// fail so that the refusal path can be tested.  Never a constant (the reference draws fresh random weights per check,
+// cp/msm_accumulator.py:43).
+bool os_random_bytes(uint8_t* out, size_t n) {
+    if (getenv("CPG_TEST_NO_ENTROPY")) return false;
+    size_t got = 0;
+#if defined(__linux__)
+    while (got < n) {
+        ssize_t r = getrandom(out + got, n - got, 0);
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    if (got == n) return true;
+#endif
+    FILE* f = fopen("/dev/urandom", "rb");
+    if (!f) return false;
+    got = fread(out, 1, n, f);
+    fclose(f);
+    return got == n;
+}
+
 // Split one wire proof (after M) into its points (48 B each, in order) and its 7 scalars.
 void split_proof(const uint8_t* p, uint32_t lg, uint8_t* points48, uint8_t* scalars32) {
     auto pts = [&](uint32_t k) { memcpy(points48, p, 48 * (size_t)k); p += 48 * (size_t)k; points48 += 48 * (size_t)k; };
@@ -637,6 +670,54 @@ void split_proof(const uint8_t* p, uint32_t lg, uint8_t* points48, uint8_t* scal
 }  // namespace
 
 extern "C" {
+
+/* The library's STROBE-128 / Merlin transcript (host_transcript.h) driven by a byte script; replaces
+ * merlin_transcripts.MerlinTranscript (merlin_transcript.py:6-24) and Strobe128 (strobe.py:16-107).  on_device = 1 runs
+ * the same code in a one-thread kernel (the placement the batched prover / verifier use per proof). */
+int cpg_merlin_script(const uint8_t* script, size_t len, int on_device, uint8_t* out, size_t out_cap, size_t* out_len) {
+    if (!script || !out || !out_len) return fail("cpg_merlin_script: null argument");
+    *out_len = 0;
+    size_t got;
+    if (!on_device) {
+        got = cpgh::merlin_run_script(script, len, out, out_cap);
+    } else {
+        NEED_INIT();
+        Scratch sc;
+        uint8_t* d_sc = sc.get<uint8_t>(len + 8); uint8_t* d_out = sc.get<uint8_t>(out_cap + 8); uint64_t* d_len = sc.get<uint64_t>(1);
+        if (!d_sc || !d_out || !d_len) return fail("cpg_merlin_script: scratch allocation failed");
+        if (int rc = cpg_h2d(d_sc, script, len)) return rc;
+        if (int rc = cpg_sync()) return rc;                                  // pageable source
+        if (int rc = launch(MerlinScript{d_sc, len, d_out, out_cap, d_len}, 1)) return rc;
+        uint64_t g = 0;
+        if (int rc = cpg_d2h(&g, d_len, 8)) return rc;
+        got = (size_t)g;
+        if (got != (size_t)-1 && got) if (int rc = cpg_d2h(out, d_out, got)) return rc;
+    }
+    if (got == (size_t)-1) return fail("cpg_merlin_script: malformed script or output buffer too small");
+    *out_len = got;
+    return 0;
+}
+
+/* Stateful form for host callers that interleave appends and challenges (the reference's usage,
+ * cp/curdleproofs_transcript.py:6-25): host-only, one Transcript per handle. */
+void* cpg_merlin_new(const uint8_t* label, size_t n) {
+    cpgh::Transcript* t = new cpgh::Transcript;
+    memset(t, 0, sizeof *t);
+    t->init_rt(label, n);
+    return t;
+}
+void* cpg_merlin_clone(const void* h) { return h ? new cpgh::Transcript(*(const cpgh::Transcript*)h) : nullptr; }
+int cpg_merlin_free(void* h) { delete (cpgh::Transcript*)h; return 0; }
+int cpg_merlin_append(void* h, const uint8_t* label, size_t nl, const uint8_t* msg, size_t n) {
+    if (!h) return fail("cpg_merlin_append: null transcript");
+    ((cpgh::Transcript*)h)->append_rt(label, nl, msg, n);
+    return 0;
+}
+int cpg_merlin_challenge(void* h, const uint8_t* label, size_t nl, uint8_t* out, size_t n) {
+    if (!h) return fail("cpg_merlin_challenge: null transcript");
+    ((cpgh::Transcript*)h)->challenge_bytes_rt(label, nl, out, n);
+    return 0;
+}
 
 void* cpg_verifier_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window, int host_threads) {
     if (need_init()) return nullptr;
@@ -650,9 +731,8 @@ void* cpg_verifier_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinder
     v->proof_len = 48 + 1088 + 480 * (size_t)lg;
     v->threads = host_threads > 0 ? host_threads : (int)std::max(1u, std::thread::hardware_concurrency());
     v->crs48.assign(crs_bytes, crs_bytes + 48 * (n + 5));
-    FILE* f = fopen("/dev/urandom", "rb");
-    if (!f || fread(v->secret, 1, 32, f) != 32) memset(v->secret, 0x5a, 32);
-    if (f) fclose(f);
+    // The batching weights are sound only while the prover cannot predict them: no entropy, no verifier.
+    if (!os_random_bytes(v->secret, 32)) { delete v; fail("cpg_verifier_create: the OS gave no random bytes (getrandom and /dev/urandom both failed)"); return nullptr; }
     v->d_crs48 = (uint8_t*)cpg_malloc(48 * (n + 5));
     uint8_t* derr = (uint8_t*)cpg_malloc(n + 5);
     v->d_crs = (Aff*)cpg_malloc(sizeof(Aff) * (n + 5));
@@ -757,6 +837,7 @@ int cpg_verify_batch(void* handle, const uint8_t* inputs, const uint8_t* proofs,
     vb.wire = wire; vb.psc = psc; vb.crs48 = v.crs48.data(); vb.st = st.data(); vb.a = a.data(); vb.tmp = tmp.data(); vb.chal = chal.data();
     vb.derived = derived.data(); vb.err = err.data(); vb.t0 = t0.data(); vb.vs = vs.data(); vb.fs = fs.data(); vb.reject = reject.data();
     memcpy(vb.secret, v.secret, 32);
+    vb.nonce = ++v.calls;
     parallel_for(v.threads, B, [&](size_t b) { verify_phase1(sh, L, vb, b); });     // overlaps the decompression kernel
     if (int rc = cpg_h2d(v.d_chal, chal.data(), chal.size())) return rc;
     if (int rc = v.device_derive(0, B, L)) return rc;

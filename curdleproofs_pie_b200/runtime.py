@@ -73,6 +73,12 @@ _SIGS = {
     "cpg_fr_sub": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "cpg_fr_mul": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "cpg_fr_inverse": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "cpg_merlin_script": (_c.c_int, [_c.c_char_p, _c.c_size_t, _c.c_int, _c.c_char_p, _c.c_size_t, _c.POINTER(_c.c_size_t)]),
+    "cpg_merlin_new": (_c.c_void_p, [_c.c_char_p, _c.c_size_t]),
+    "cpg_merlin_clone": (_c.c_void_p, [_c.c_void_p]),
+    "cpg_merlin_free": (_c.c_int, [_c.c_void_p]),
+    "cpg_merlin_append": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t, _c.c_char_p, _c.c_size_t]),
+    "cpg_merlin_challenge": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t, _c.c_char_p, _c.c_size_t]),
     "cpg_verifier_create": (_c.c_void_p, [_c.c_char_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_int]),
     "cpg_verifier_free": (_c.c_int, [_c.c_void_p]),
     "cpg_verifier_proof_bytes": (_c.c_size_t, [_c.c_void_p]),
@@ -287,6 +293,21 @@ class CpgLib:
         else:
             self.check(fn(a.ptr, b.ptr, k, out.ptr), "cpg_fr_" + name)
         return out
+
+    # -- transcript --
+    def merlin_script(self, records, on_device=False, cap=1 << 16):
+        """records: (op, more, label, data_or_n) tuples (include/cpg.h: cpg_merlin_script) -> concatenated outputs"""
+        blob = bytearray()
+        for op, more, label, data in records:
+            emits = op in (3, 7)
+            n = int(data) if emits else len(data)
+            blob += bytes([op, 1 if more else 0]) + len(label).to_bytes(2, "little") + n.to_bytes(4, "little") + bytes(label)
+            if not emits:
+                blob += bytes(data)
+        out = ctypes.create_string_buffer(cap)
+        got = ctypes.c_size_t()
+        self.check(self.c.cpg_merlin_script(bytes(blob), len(blob), 1 if on_device else 0, out, cap, ctypes.byref(got)), "cpg_merlin_script")
+        return out.raw[:got.value]
 
     def bench_int_pipe(self, kind, iters):
         per_s = ctypes.c_double()

@@ -186,6 +186,7 @@ class BatchProver:
         """Proves len(pre_inputs) shuffles with randomness drawn from `rng` as the reference draws it.
         Returns [(vec_T|vec_U bytes, M|proof bytes)]."""
         B = len(pre_inputs)
+        pre_inputs = self._checked_inputs(pre_inputs)
         perms, ks, rand = self.draw_batch(rng, B)
         out_tu = ctypes.create_string_buffer(max(1, B * 2 * self.ell * 48))
         out_pr = ctypes.create_string_buffer(max(1, B * self.proof_len))
@@ -197,11 +198,27 @@ class BatchProver:
         tu, pr = out_tu.raw, out_pr.raw
         return [(tu[i * w:(i + 1) * w], pr[i * self.proof_len:(i + 1) * self.proof_len]) for i in range(B)]
 
+    def _checked_inputs(self, pre_inputs):
+        """every entry must be exactly vec_R|vec_S = 2*ell*48 bytes: libcpg reads B full rows from the joined buffer"""
+        want = 2 * self.ell * 48
+        out = [bytes(p) for p in pre_inputs]
+        for i, p in enumerate(out):
+            if len(p) != want:
+                raise ValueError("pre_inputs[%d] holds %d bytes, expected 2*ell*48 = %d" % (i, len(p), want))
+        return out
+
     def prove_raw(self, inputs, perms, ks, rand, B):
+        """Flat buffers for B proofs; every length is checked here because libcpg reads B full rows of each.
+        Malformed VALUES (bad encodings, k or a blinder >= r, a perms row that is not a permutation) come back in the
+        per-lane status bytes."""
         import array
 
         perm_arr = array.array("I", perms)
-        assert perm_arr.itemsize == 4 and len(perm_arr) == B * self.ell
+        if perm_arr.itemsize != 4 or len(perm_arr) != B * self.ell:
+            raise ValueError("perms must hold B*ell = %d u32 entries, got %d" % (B * self.ell, len(perm_arr)))
+        for name, buf, want in (("inputs", inputs, B * 2 * self.ell * 48), ("ks", ks, B * 32), ("rand", rand, B * self.n_rand * 32)):
+            if len(buf) != want:
+                raise ValueError("%s holds %d bytes, expected %d" % (name, len(buf), want))
         out_tu = ctypes.create_string_buffer(B * 2 * self.ell * 48)
         out_pr = ctypes.create_string_buffer(B * self.proof_len)
         status = ctypes.create_string_buffer(max(1, B))
@@ -213,8 +230,20 @@ class BatchProver:
         """pre_inputs[i] = vec_R|vec_S bytes, perms[i] = list of ell ints, ks[i] = int, rands[i] = bytes
         from draw_randomness.  Returns [(vec_T|vec_U bytes, M|proof bytes)]; raises on a malformed input."""
         B = len(pre_inputs)
+        if not (len(perms) == len(ks) == len(rands) == B):
+            raise ValueError("pre_inputs, perms, ks and rands must have the same length")
+        pre_inputs = self._checked_inputs(pre_inputs)
+        for i in range(B):
+            if len(perms[i]) != self.ell:
+                raise ValueError("perms[%d] has %d entries, expected ell = %d" % (i, len(perms[i]), self.ell))
+            if any(not 0 <= int(x) < self.ell for x in perms[i]):
+                raise IndexError("perms[%d] holds an index outside [0, ell)" % i)          # the reference's list index raises the same
+            if len(rands[i]) != self.n_rand * 32:
+                raise ValueError("rands[%d] holds %d bytes, expected n_rand*32 = %d" % (i, len(rands[i]), self.n_rand * 32))
+            if not 0 <= int(ks[i]) < 1 << 256:
+                raise ValueError("ks[%d] does not fit 32 bytes" % i)
         flat_perm = [int(x) for p in perms for x in p]
-        tu, pr, st = self.prove_raw(b"".join(pre_inputs), flat_perm, b"".join(int(k).to_bytes(32, "little") for k in ks), b"".join(rands), B)
+        tu, pr, st = self.prove_raw(b"".join(pre_inputs), flat_perm, b"".join(int(k).to_bytes(32, "little") for k in ks), b"".join(bytes(r) for r in rands), B)
         if any(st):
             raise ValueError("serialised data seems to be invalid (lanes %s)" % [i for i, s in enumerate(st) if s])
         w = 2 * self.ell * 48
@@ -232,10 +261,41 @@ class BatchProver:
             pass
 
 
+class WhiskTracker:
+    """(r_G, k_r_G) as 48-byte encodings - the shape of the reference's WhiskTracker (whisk_interface.py:30-33);
+    also unpacks like the (r_G, k_r_G) tuple earlier versions returned."""
+
+    __slots__ = ("r_G", "k_r_G")
+
+    def __init__(self, r_G, k_r_G):
+        self.r_G = bytes(r_G)
+        self.k_r_G = bytes(k_r_G)
+
+    def __iter__(self):
+        return iter((self.r_G, self.k_r_G))
+
+    def __eq__(self, other):
+        try:
+            a, b = other
+        except (TypeError, ValueError):
+            return NotImplemented
+        return (self.r_G, self.k_r_G) == (bytes(a), bytes(b))
+
+    def __repr__(self):
+        return "WhiskTracker(r_G=%s..., k_r_G=%s...)" % (self.r_G[:4].hex(), self.k_r_G[:4].hex())
+
+
+_PROVER_CACHE = {}
+
+
 def GenerateWhiskShuffleProofBatch(crs, pre_shuffle_trackers_per_proof, rng=None):
     """Batched GenerateWhiskShuffleProof (whisk_interface.py:111-140): for each proof draws the
     permutation, k and the blinders from `rng` (default: the `random` module) exactly as the
-    reference does, then proves all of them on the GPU.  Returns [(post_trackers, proof_bytes)]."""
+    reference does, then proves all of them on the GPU.  Returns [(post_trackers, proof_bytes)] with
+    post_trackers a list of WhiskTracker.
+    The default generator is Python's Mersenne Twister, as in the reference (cp/util.py:21-24) - reproducible, NOT a
+    CSPRNG; pass random.SystemRandom() for blinders that are actually unpredictable.
+    The prover (CRS tables, device and pinned buffers) is kept per (crs, ell, n_blinders) like the verifier's."""
     import random as _random
 
     rng = rng or _random
@@ -244,12 +304,22 @@ def GenerateWhiskShuffleProofBatch(crs, pre_shuffle_trackers_per_proof, rng=None
         nbl = 4
     else:
         crs_bytes, ell, nbl = crs.to_bytes(), len(crs.vec_G), len(crs.vec_H)
-    prover = BatchProver(crs_bytes, ell, nbl)
-    inputs = [trackers_to_input(trackers, []) for trackers in pre_shuffle_trackers_per_proof]
+    inputs = []
+    for i, trackers in enumerate(pre_shuffle_trackers_per_proof):
+        trackers = list(trackers)
+        if len(trackers) != ell:
+            raise ValueError("proof %d: %d pre-shuffle trackers, expected ell = %d" % (i, len(trackers), ell))
+        row = trackers_to_input(trackers, [])
+        if len(row) != 2 * ell * 48:
+            raise ValueError("proof %d: every tracker half must be a 48-byte compressed point" % i)
+        inputs.append(row)
+    key = (bytes(crs_bytes), ell, nbl)
+    prover = _PROVER_CACHE.get(key)
+    if prover is None:
+        prover = _PROVER_CACHE[key] = BatchProver(crs_bytes, ell, nbl)
     out = []
     for tu, proof in prover.prove_drawn(inputs, rng):
         T, U = tu[:48 * ell], tu[48 * ell:]
-        post = [(T[48 * i:48 * i + 48], U[48 * i:48 * i + 48]) for i in range(ell)]
+        post = [WhiskTracker(T[48 * i:48 * i + 48], U[48 * i:48 * i + 48]) for i in range(ell)]
         out.append((post, proof))
-    prover.close()
     return out

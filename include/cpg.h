@@ -128,6 +128,25 @@ int cpg_fr_sub(const uint8_t* d_a, const uint8_t* d_b, size_t k, uint8_t* d_out)
 int cpg_fr_mul(const uint8_t* d_a, const uint8_t* d_b, size_t k, uint8_t* d_out);
 int cpg_fr_inverse(const uint8_t* d_a, size_t k, uint8_t* d_out);   /* inverse(0) = 0, cp/util.py:51-54 */
 
+/* ---- Fiat-Shamir transcript ---------------------------------------------------------------------
+ * The library's own STROBE-128 / Merlin implementation (the one its prover and verifier run per proof), driven by a
+ * byte script; replaces merlin_transcripts.MerlinTranscript (merlin_transcripts/merlin_transcript.py:6-24) over
+ * Strobe128 (strobe.py:16-107).  Record: op u8 | more u8 | label_len u16 LE | n u32 LE | label | data[n]
+ * (the two output ops carry no data; n = bytes wanted):
+ *   0 STROBE init(data = protocol label)   1 meta_ad(data, more)   2 ad(data, more)   3 prf(n, more) -> n bytes
+ *   4 key(data, more)   5 MerlinTranscript(data = label)   6 append_message(label, data)   7 challenge_bytes(label, n)
+ * Outputs are concatenated into `out`.  on_device = 1 runs the script in a one-thread kernel, 0 on the calling thread
+ * (host-only; needs no cpg_init). */
+int cpg_merlin_script(const uint8_t* script, size_t len, int on_device, uint8_t* out, size_t out_cap, size_t* out_len);
+
+/* stateful host-side form: MerlinTranscript(label) / append_message / challenge_bytes (merlin_transcript.py:6-24);
+ * dropin/merlin_transcripts binds these so that the unmodified reference's Fiat-Shamir runs off Python */
+void* cpg_merlin_new(const uint8_t* label, size_t n);
+void* cpg_merlin_clone(const void* transcript);
+int cpg_merlin_free(void* transcript);
+int cpg_merlin_append(void* transcript, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t n);
+int cpg_merlin_challenge(void* transcript, const uint8_t* label, size_t label_len, uint8_t* out, size_t n);
+
 /* ---- batched shuffle-proof verification -------------------------------------------------------
  * Replaces, for B proofs at once, IsValidWhiskShuffleProof (cp/whisk_interface.py:74-108) ->
  * CurdleProofsProof.verify (cp/curdleproofs.py:162-248) and everything below it.  Every group
@@ -178,7 +197,10 @@ int cpg_verify_replay_device(void* verifier, uint8_t* verdicts_or_null);
  *               m_bl(4) a_bl(2) c_bl(4) ipa_r(n) ipa_z(n-2) r_t r_u r_a r_b r_k msm_r(n), canonical LE
  *   out_tu    : [B][2*ell*48]  vec_T | vec_U (post-shuffle tracker halves)
  *   out_proofs: [B][cpg_prover_proof_bytes]  M | proof  (WhiskShuffleProof.to_bytes, :57-61)
- *   status    : [B] 0 ok, 1 malformed input (a point encoding, or k >= r) */
+ *   status    : [B] 0 ok, 1 malformed input: a point encoding, k or a blinder >= r, or a perms row that is not a
+ *               permutation of [0, ell).  Such a lane never reaches the device with its bad indices / scalars (it
+ *               proves over a harmless substitute) and its outputs are undefined; the other lanes are unaffected.
+ * Preconditions the caller keeps: every buffer holds B full rows of the sizes above. */
 void* cpg_prover_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window);
 int cpg_prover_free(void* prover);
 size_t cpg_prover_proof_bytes(const void* prover);

@@ -4,8 +4,8 @@ Per-proof CPU restatement of the reference's shuffle argument, written against t
 G1Point/Scalar surface so the same code runs on the oracle arithmetic (golden vectors, CPU
 baseline) and on the CUDA drop-in surface (parity tests).  It follows the reference's
 operation, RNG-draw and Fiat-Shamir order exactly, so that for one ``random.seed`` the proof
-bytes equal those of the unmodified reference (checked in tests/test_oracle_vs_reference.py
-whenever /root/reference is mounted).  Cited sources, all under
+bytes equal those of the unmodified reference (tests/test_oracle_golden.py: against the committed
+fixtures the unmodified reference wrote, and re-generated from /root/reference whenever it is mounted).  Cited sources, all under
 /root/reference/curdleproofs/curdleproofs/:
   curdleproofs.py:50-160 (prove) :162-248 (verify) :275-298 (wire) :301-321 (shuffle+commit)
   same_perm.py:27-72 / :74-120      grand_prod.py:29-119 / :121-177

@@ -155,3 +155,81 @@ def check_prove_with_identity_trackers(lib, name, fixed_window=0, table_window=N
     ver = whisk.BatchVerifier(crs_bytes, ell, fixed_window=fixed_window, lib=lib)
     assert ver.verify([pre + tu], [proof]) == [ctx.is_valid(crs, vec_R, vec_S, vec_T, vec_U, M, want_proof)]
     ver.close()
+
+
+def check_rejects_bad_perm_and_blinders(lib, name, fixed_window=0):
+    """perm entries index device rows - an entry >= ell, a repeated entry or a blinder >= r must flag that
+    lane (status 1) without touching the device with it, while the clean lane still yields the reference's bytes; the
+    Python wrappers refuse wrong lengths before libcpg reads past a buffer."""
+    import pytest
+
+    case = sc.load_case(name)
+    ell = case["N"] - 4
+    prover = whisk.BatchProver(bytes.fromhex(case["crs"]), ell, fixed_window=fixed_window, lib=lib)
+    perm, k, rand = replay_rng(case, prover)
+    pre = b"".join(bytes.fromhex(h) for h in case["vec_R"] + case["vec_S"])
+    oob = list(perm); oob[1] = ell + 7                       # out of range
+    dup = list(perm); dup[0] = dup[1]                        # not a permutation
+    huge = list(perm); huge[2] = 0xFFFFFFFF
+    bad_rand = bytearray(rand); bad_rand[32 * 5:32 * 6] = b"\xff" * 32   # blinder >= r
+    kb = k.to_bytes(32, "little")
+    tu, pr, st = prover.prove_raw(pre * 5, perm + oob + dup + huge + perm, kb * 5, rand * 4 + bytes(bad_rand), 5)
+    assert list(st) == [0, 1, 1, 1, 1]
+    assert pr[:prover.proof_len] == bytes.fromhex(case["M"]) + bytes.fromhex(case["proof"])
+    with pytest.raises(IndexError):
+        prover.prove([pre], [oob], [k], [rand])
+    with pytest.raises(ValueError):
+        prover.prove([pre], [dup], [k], [rand])              # flagged by the library -> ValueError
+    with pytest.raises(ValueError):
+        prover.prove([pre[:-48]], [perm], [k], [rand])       # short tracker row
+    with pytest.raises(ValueError):
+        prover.prove([pre], [perm[:-1]], [k], [rand])
+    with pytest.raises(ValueError):
+        prover.prove([pre], [perm], [k], [rand[:-32]])
+    with pytest.raises(ValueError):
+        prover.prove_raw(pre, perm, kb, rand[:-1], 1)
+    with pytest.raises(ValueError):
+        prover.prove_drawn([pre, pre[:-1]], random.Random(1))
+    prover.close()
+
+
+def check_whisk_api_roundtrip(lib, name, B=3):
+    """GenerateWhiskShuffleProofBatch -> IsValidWhiskShuffleProofBatch (the batched forms of whisk_interface.py:74-140):
+    trackers in, WhiskTracker-shaped objects + proof bytes out, every proof valid, and the first proof equals what the
+    reference's per-proof path draws from the same `random` stream (replayed through prove())."""
+    import pytest
+
+    case = sc.load_case(name)
+    ell = case["N"] - 4
+    crs = (bytes.fromhex(case["crs"]), ell)
+    pre = [(bytes.fromhex(r), bytes.fromhex(s)) for r, s in zip(case["vec_R"], case["vec_S"])]
+    whisk._CACHE.clear(); whisk._PROVER_CACHE.clear()
+    import curdleproofs_pie_b200.runtime as _rt
+    old = _rt._LIB if hasattr(_rt, "_LIB") else None
+    try:
+        _rt._install_library_for_tests(lib)
+        a, b = random.Random(8128), random.Random(8128)
+        res = whisk.GenerateWhiskShuffleProofBatch(crs, [pre] * B, rng=a)
+        assert len(res) == B
+        post0, proof0 = res[0]
+        assert all(isinstance(t, whisk.WhiskTracker) and len(t.r_G) == 48 and len(t.k_r_G) == 48 for t in post0)
+        assert whisk.IsValidWhiskShuffleProofBatch(crs, [pre] * B, [post for post, _ in res], [pr for _, pr in res]) == [True] * B
+        # tuples are accepted on the way back in, and a proof paired with another lane's trackers is rejected
+        as_tuples = [[tuple(t) for t in post] for post, _ in res]
+        assert whisk.IsValidWhiskShuffleProofBatch(crs, [pre] * B, as_tuples[1:] + as_tuples[:1], [pr for _, pr in res]) == [False] * B
+        # same draws through the explicit-randomness entry point
+        prover = whisk._PROVER_CACHE[(crs[0], ell, 4)]
+        p = list(range(ell)); b.shuffle(p)
+        k = b.randint(1, rt.R_ORDER - 1)
+        (tu, pr), = prover.prove([b"".join(r for r, _ in pre) + b"".join(s_ for _, s_ in pre)], [p], [k], [prover.draw_randomness(b)])
+        assert pr == proof0 and tu == b"".join(t.r_G for t in post0) + b"".join(t.k_r_G for t in post0)
+        with pytest.raises(ValueError):
+            whisk.GenerateWhiskShuffleProofBatch(crs, [pre[:-1]], rng=a)
+        with pytest.raises(ValueError):
+            whisk.GenerateWhiskShuffleProofBatch(crs, [pre[:-1] + [(pre[0][0], pre[0][1][:-1])]], rng=a)
+    finally:
+        for c_ in (whisk._CACHE, whisk._PROVER_CACHE):
+            for obj in c_.values():
+                obj.close()
+            c_.clear()
+        _rt._install_library_for_tests(old)

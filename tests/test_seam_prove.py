@@ -39,3 +39,11 @@ def test_prove_with_randomness_continued_in_c(seam_lib):
 def test_prove_with_identity_trackers_matches_the_oracle(seam_lib):
     pc.check_prove_with_identity_trackers(seam_lib, "shuffle_N8_seed1234.json", fixed_window=4)
     pc.check_prove_with_identity_trackers(seam_lib, "shuffle_N16_seed77.json", fixed_window=5, table_window=0)
+
+
+def test_prove_rejects_bad_perm_and_blinders(seam_lib):
+    pc.check_rejects_bad_perm_and_blinders(seam_lib, "shuffle_N8_seed1234.json", fixed_window=4)
+
+
+def test_whisk_api_generate_then_validate(seam_lib):
+    pc.check_whisk_api_roundtrip(seam_lib, "shuffle_N8_seed1234.json", B=2)

@@ -48,3 +48,18 @@ def test_adaptive_group_size_follows_the_failure_rate(seam_lib):
     assert ver.verify(ins, prs) == want and ver.group() == 2
     assert ver.verify([honest[1]] * 5, [honest[2]] * 5) == [True] * 5 and ver.rechecked() == 0
     ver.close()
+
+
+def test_verifier_refuses_to_exist_without_entropy(seam_lib, monkeypatch):
+    """the batching weights are only sound while unpredictable: no OS randomness -> cpg_verifier_create fails
+    (round 1 silently fell back to a constant secret)"""
+    import shuffle_cases as sc
+    from curdleproofs_pie_b200 import runtime as rt
+    from curdleproofs_pie_b200 import whisk
+
+    case = sc.load_case("shuffle_N8_seed1234.json")
+    monkeypatch.setenv("CPG_TEST_NO_ENTROPY", "1")
+    with pytest.raises(rt.CpgError, match="random"):
+        whisk.BatchVerifier(bytes.fromhex(case["crs"]), case["N"] - 4, fixed_window=4, lib=seam_lib)
+    monkeypatch.delenv("CPG_TEST_NO_ENTROPY")
+    whisk.BatchVerifier(bytes.fromhex(case["crs"]), case["N"] - 4, fixed_window=4, lib=seam_lib).close()

@@ -28,6 +28,39 @@ def variants(case):
         bad = bytearray(proof)
         bad[off + 1] ^= 0x04
         out.append(("flip@%d" % off, good, M + bytes(bad), False))
+    # every scalar of the proof, and one point of every named field / vector replaced by ANOTHER VALID point (the CRS's
+    # H): such a proof still decodes, so only the coefficient that verify_phase2 gives this very term can reject it
+    n = case["N"]
+    crs = bytes.fromhex(case["crs"])
+    Hb = crs[48 * n:48 * n + 48]
+    o_rp = 48 * 9
+    o_ipa = o_rp + 32 + 48 * 2                     # L_C | R_C | L_D | R_D, lg points each
+    o_cd = o_ipa + 48 * 4 * lg
+    o_cm = o_cd + 64                               # cm_A (2) | cm_B (2)
+    o_z = o_cm + 48 * 4
+    o_b = o_z + 96                                 # B_a B_t B_u
+    o_msm = o_b + 48 * 3                           # L_A L_T L_U R_A R_T R_U, lg points each
+    o_x = o_msm + 48 * 6 * lg
+    assert o_x + 32 == len(proof)
+    for nm, off in [("r_p", o_rp), ("c", o_cd), ("d", o_cd + 32), ("z_k", o_z), ("z_t", o_z + 32), ("z_u", o_z + 64), ("x", o_x)]:
+        bad = bytearray(proof)
+        bad[off] ^= 0x01
+        out.append(("scalar:" + nm, good, M + bytes(bad), False))
+    named = [("A", 0), ("T1", 48), ("T2", 96), ("U1", 144), ("U2", 192), ("R", 240), ("S", 288), ("B", 336), ("C", 384),
+             ("Bc", o_rp + 32), ("Bd", o_rp + 32 + 48), ("cmA1", o_cm), ("cmA2", o_cm + 48), ("cmB1", o_cm + 96), ("cmB2", o_cm + 144),
+             ("Ba", o_b), ("Bt", o_b + 48), ("Bu", o_b + 96)]
+    for k, nm in enumerate(["L_C", "R_C", "L_D", "R_D"]):
+        named.append((nm + "[0]", o_ipa + 48 * k * lg))
+        named.append((nm + "[last]", o_ipa + 48 * (k * lg + lg - 1)))
+    for k, nm in enumerate(["L_A", "L_T", "L_U", "R_A", "R_T", "R_U"]):
+        named.append((nm + "[0]", o_msm + 48 * k * lg))
+        named.append((nm + "[last]", o_msm + 48 * (k * lg + lg - 1)))
+    for nm, off in named:
+        bad = bytearray(proof)
+        assert bytes(bad[off:off + 48]) != Hb
+        bad[off:off + 48] = Hb
+        out.append(("point:" + nm, good, M + bytes(bad), False))
+    out.append(("point:M", good, Hb + proof, False))
     non_canonical = bytearray(proof)
     non_canonical[48 * 9:48 * 9 + 32] = b"\xff" * 32            # r_p >= r: from_le_bytes raises
     out.append(("scalar>=r", good, M + bytes(non_canonical), False))
