@@ -912,6 +912,7 @@ int cpg_bench_int_pipe(int, uint64_t, double* per_second, float* ms) {
 
 }  // extern "C"
 
+#include "comm.inl"
 #include "verify.inl"
 #include "prove.inl"
 #include "pyrandom.inl"

@@ -65,6 +65,14 @@ _SIGS = {
     "cpg_msm_window_count": (_c.c_int, [_c.c_size_t, _c.c_int]),
     "cpg_g1_msm_window_sums": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "cpg_g1_msm_combine_windows": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p]),
+    "cpg_comm_unique_id": (_c.c_int, [_c.c_char_p]),
+    "cpg_comm_init": (_c.c_int, [_c.c_int, _c.c_int, _c.c_char_p]),
+    "cpg_comm_free": (_c.c_int, []),
+    "cpg_comm_rank": (_c.c_int, []),
+    "cpg_comm_world": (_c.c_int, []),
+    "cpg_comm_nccl_version": (_c.c_int, []),
+    "cpg_comm_allgather": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t]),
+    "cpg_g1_msm_sharded": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
     "cpg_fixed_table_create": (_c.c_void_p, [_c.c_void_p, _c.c_size_t, _c.c_int]),
     "cpg_fixed_table_free": (_c.c_int, [_c.c_void_p]),
     "cpg_fixed_table_bytes": (_c.c_size_t, [_c.c_void_p]),

@@ -1,6 +1,8 @@
-"""Per-proof sharding across GPUs: proofs are independent, so rank r of W owns a
-contiguous block of the batch and no data-path collective is needed; only the verdict bytes are
-gathered at the end.  torch.distributed is plumbing here (NCCL on the GPU box, gloo in CPU tests)."""
+"""Per-proof sharding across GPUs: proofs are independent, so rank r of W owns a contiguous block of
+the batch and no data-path collective is needed; only the verdict bytes (and a timing scalar) are gathered at the end.
+The transport is the library's own communicator (comm.py: NCCL inside libcpg.so); callers without one - the CPU test
+tier - inject `allgather(local_bytes, width) -> [bytes per rank]`.  No torch here."""
+import struct
 
 
 def shard_range(total, rank, world):
@@ -12,29 +14,29 @@ def shard_range(total, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def max_over_ranks(value, dist=None, device="cpu"):
+def _transport(lib, allgather):
+    if allgather is not None:
+        return allgather
+    from . import comm
+
+    return lambda local, width: comm.allgather_bytes(lib, local, width)
+
+
+def max_over_ranks(value, lib=None, allgather=None, world=None):
     """Max of a per-rank scalar (device time in ms) over all ranks."""
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+    if world is None:
+        world = int(lib.c.cpg_comm_world()) if lib is not None else 1
+    if world == 1 and allgather is None:
         return float(value)
-    import torch
-
-    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+    parts = _transport(lib, allgather)(struct.pack("<d", float(value)), 8)
+    return max(struct.unpack("<d", p[:8])[0] for p in parts)
 
 
-def gather_verdicts(local, total, dist=None, device="cpu"):
+def gather_verdicts(local, total, rank=0, world=1, lib=None, allgather=None):
     """Concatenate every rank's verdict bytes (its shard_range block) into the full bitmap, on all ranks."""
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+    if world == 1:
         return bytes(local)
-    import torch
-
-    world = dist.get_world_size()
     sizes = [shard_range(total, r, world) for r in range(world)]
     width = max(hi - lo for lo, hi in sizes)
-    buf = torch.zeros(width, dtype=torch.uint8, device=device)
-    if len(local):
-        buf[:len(local)] = torch.tensor(list(local), dtype=torch.uint8, device=device)
-    outs = [torch.zeros(width, dtype=torch.uint8, device=device) for _ in range(world)]
-    dist.all_gather(outs, buf)
-    return b"".join(bytes(outs[r][:hi - lo].cpu().tolist()) for r, (lo, hi) in enumerate(sizes))
+    parts = _transport(lib, allgather)(bytes(local).ljust(width, b"\0"), width)
+    return b"".join(parts[r][:hi - lo] for r, (lo, hi) in enumerate(sizes))

@@ -114,6 +114,25 @@ int cpg_msm_window_count(size_t n, int window);
 int cpg_g1_msm_window_sums(const void* d_bases_aff, const uint8_t* d_scalars, size_t n, int window,
                            int w_begin, int w_end, void* d_out_jac);
 int cpg_g1_msm_combine_windows(const void* d_wsums_jac, int window, void* d_out_jac);
+/* ---- multi-GPU: the communicator and the path's one collective, inside the library ------------------
+ * One process per GPU.  Rank 0 obtains an id (cpg_comm_unique_id, 128 bytes), the host plumbing hands it to the other
+ * ranks (any channel: curdleproofs_pie_b200/comm.py uses a TCP socket on MASTER_ADDR), every rank calls
+ * cpg_comm_init.  NCCL (libnccl.so.2, dlopen'ed) then moves DEVICE buffers over NVLink/NVSwitch on the library's
+ * current stream - no torch, no host bounce.  Without cpg_comm_init the world is 1 and every call degenerates to
+ * its single-GPU form.  Replaces nothing in the reference (it is single-process); SURVEY 8e specifies it. */
+int cpg_comm_unique_id(uint8_t* out128);
+int cpg_comm_init(int rank, int world, const uint8_t* id128);
+int cpg_comm_free(void);
+int cpg_comm_rank(void);
+int cpg_comm_world(void);
+int cpg_comm_nccl_version(void);                 /* e.g. 22809; 0 if NCCL cannot be loaded */
+/* all-gather of bytes_per_rank bytes from every rank into d_recv[world * bytes_per_rank] (device buffers) */
+int cpg_comm_allgather(const void* d_send, void* d_recv, size_t bytes_per_rank);
+/* ONE n-term MSM (multiexp_unchecked, stub :28) over the communicator: this rank's slice of the Pippenger windows,
+ * ONE ncclAllGather of the window sums (ceil(W/world) x 144 B per rank), Horner on every rank; all ranks hold all
+ * bases and scalars and get the same Jacobian result.  window = 0: cpg_msm_pick_window(n). */
+int cpg_g1_msm_sharded(const void* d_bases_aff, const uint8_t* d_scalars, size_t n, int window, void* d_out_jac);
+
 /* fixed-base tables for generators shared by every proof (the CRS, cp/crs.py:19-36):
  * T[i][w][d] = (d+1) 2^(c w) G_i.  Returns NULL on failure. */
 void* cpg_fixed_table_create(const void* d_bases_aff, size_t nb, int window);

@@ -1,5 +1,7 @@
-"""The N>1 path on CPU: world_size-2 gloo processes exercise the per-proof sharding, the
-max-over-ranks timing reduction and the verdict gather that bench.py / a multi-GPU caller use."""
+"""The N>1 path on CPU: world_size-2 gloo processes exercise the per-proof sharding, the max-over-ranks timing
+reduction, the verdict gather and the window-split MSM.  On the GPU box the transport is the library's own NCCL
+communicator (comm.py); here a gloo all-gather of byte strings is injected in its place (the product package itself
+holds no torch import)."""
 import os
 import socket
 import sys
@@ -16,19 +18,35 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def gloo_allgather(dist):
+    """allgather(local_bytes, width) -> [bytes per rank] over torch.distributed (gloo)"""
+    import torch
+
+    def gather(local, width):
+        buf = torch.frombuffer(bytearray(bytes(local).ljust(width, b"\0")), dtype=torch.uint8)
+        outs = [torch.zeros(width, dtype=torch.uint8) for _ in range(dist.get_world_size())]
+        dist.all_gather(outs, buf)
+        return [bytes(o.numpy().tobytes()) for o in outs]
+
+    return gather
+
+
 def _worker(rank, world, port, total, q):
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
 
     from curdleproofs_pie_b200 import sharding
+    from test_dist_gloo import gloo_allgather
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = sharding.shard_range(total, rank, world)
     local = bytes((i * 7 + 3) % 2 for i in range(lo, hi))           # this rank's "verdicts"
-    full = sharding.gather_verdicts(local, total, dist)
-    slowest = sharding.max_over_ranks(10.0 + rank, dist)
+    ag = gloo_allgather(dist)
+    full = sharding.gather_verdicts(local, total, rank, world, allgather=ag)
+    slowest = sharding.max_over_ranks(10.0 + rank, allgather=ag, world=world)
     dist.barrier()
     q.put((rank, lo, hi, full, slowest))
     dist.destroy_process_group()
@@ -77,6 +95,7 @@ def _msm_worker(rank, world, port, n, q):
     import conftest
     import parity_cases as pc
     from curdleproofs_pie_b200 import msm, runtime
+    from test_dist_gloo import gloo_allgather
     from oracle import cref_binding
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -91,7 +110,11 @@ def _msm_worker(rank, world, port, n, q):
     ks = [rng.randrange(pc.R) for _ in range(n)]
     aff, _ = pc.upload_points(lib, [enc[i] for i in idx])
     dk = lib.upload(runtime.scalars_to_bytes(ks))
-    out = msm.msm_large(lib, aff, dk, n, window=6, dist=dist)
+    out = msm.msm_large(lib, aff, dk, n, window=6, gather=gloo_allgather(dist), rank=rank, world=world)
+    # world 1 in the library (no communicator): the sharded entry point is the plain MSM
+    solo = msm.msm_large(lib, aff, dk, n, window=6)
+    assert lib.compress_jac(solo, 1) == lib.compress_jac(out, 1)
+    assert lib.c.cpg_comm_world() == 1 and lib.c.cpg_comm_rank() == 0
     got = lib.compress_jac(out, 1)
     agg = [0] * 16
     for i, k in zip(idx, ks):
