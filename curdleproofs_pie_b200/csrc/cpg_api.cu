@@ -774,12 +774,21 @@ void* cpg_fixed_table_create(const void* d_bases, size_t nb, int window) {
     uint64_t entries = (uint64_t)nb * t->s.W * t->s.NB;
     t->bytes = entries * sizeof(Aff);
     t->table = (Aff*)cpg_malloc(t->bytes);
-    Jac* rows = (Jac*)cpg_malloc(entries * sizeof(Jac));
-    int rc = (!t->table || !rows) ? fail("cpg_fixed_table_create: allocation failed") : 0;
-    if (!rc) rc = launch(FixedTableRows{t->s, (const Aff*)d_bases, rows}, (uint64_t)nb * t->s.W);
-    if (!rc) rc = launch_occ(JacToAff{rows, t->table}, entries);
+    const uint64_t rows = (uint64_t)nb * t->s.W;
+    const uint32_t S = t->s.NB < 64 ? t->s.NB : 64, nseg = t->s.NB / S;
+    const uint64_t nthreads = rows * nseg;
+    const uint64_t chunk = std::min<uint64_t>(nthreads, (uint64_t)148 * 3 * 128 * 4);       // threads per launch: bounds the scratch (96 B per entry in flight)
+    Jac* hj = (Jac*)cpg_malloc(rows * sizeof(Jac));
+    Fq* hz = (Fq*)cpg_malloc(rows * sizeof(Fq));
+    Aff* heads = (Aff*)cpg_malloc(rows * sizeof(Aff));
+    Fq* zs = (Fq*)cpg_malloc(chunk * S * sizeof(Fq));
+    Fq* pz = (Fq*)cpg_malloc(chunk * S * sizeof(Fq));
+    int rc = (!t->table || !hj || !hz || !heads || !zs || !pz) ? fail("cpg_fixed_table_create: allocation failed") : 0;
+    if (!rc) rc = launch(FixedTableHeads{t->s, (const Aff*)d_bases, hj, hz, heads}, nb);
+    for (uint64_t t0 = 0; t0 < nthreads && !rc; t0 += chunk)
+        rc = launch_occ(FixedTableSegs{t->s, S, nseg, heads, t0, zs, pz, t->table}, std::min(chunk, nthreads - t0));
     if (!rc) rc = cpg_sync();
-    cpg_free(rows);
+    cpg_free(hj); cpg_free(hz); cpg_free(heads); cpg_free(zs); cpg_free(pz);
     if (rc) { cpg_free(t->table); delete t; return nullptr; }
     return t;
 }

@@ -378,18 +378,86 @@ struct HornerJac {                 // thread = msm: combine W Jacobian window su
 // no doublings and no bucket reduction: n*W mixed adds (SURVEY 8f-2 direction).
 struct FixedShape { uint32_t nb, c, W, NB; };
 
-struct FixedTableRows {            // thread = (base i, window w): the NB multiples, Jacobian scratch
-    static constexpr const char* kName = "FixedTableRows";
+#ifdef __CUDA_ARCH__
+CPG_HD int clz32(uint32_t v) { return __clz((int)v); }
+#else
+CPG_HD int clz32(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+#endif
+// Table build in two kernels, every inversion shared by Montgomery's trick (round 1 inverted each of the 68.7 M entries
+// of the c = 16 table on its own: 1.7 s per table):
+//   FixedTableHeads  thread = base i: Q_{i,w} = 2^(c w) G_i for all W windows (255 doublings), made affine with ONE inversion
+//   FixedTableSegs   thread = (row (i, w), segment s): entries d = s S + 1 .. (s + 1) S of the row: (s S + 1) Q by
+//                    double-and-add, then S - 1 mixed additions of Q, made affine with ONE inversion per segment
+struct FixedTableHeads {
+    static constexpr const char* kName = "FixedTableHeads";
     FixedShape s;
     const Aff* bases;
-    Jac* rows;                     // [nb*W][NB]
-    CPG_HD void operator()(uint64_t t) const {
-        uint32_t i = (uint32_t)(t / s.W), w = (uint32_t)(t % s.W);
-        Jac p = to_jac(bases[i]);
-        for (uint32_t j = 0; j < w * s.c; j++) p = jac_dbl(p);
-        Jac acc = p;
-        Jac* row = rows + t * (uint64_t)s.NB;
-        for (uint32_t d = 0; d < s.NB; d++) { row[d] = acc; acc = jac_add(acc, p); }
+    Jac* scratch; Fq* pz;          // [nb][W]
+    Aff* heads;                    // [nb][W] (out)
+    CPG_HD void operator()(uint64_t i) const {
+        Jac* m = scratch + i * s.W; Fq* z = pz + i * s.W; Aff* out = heads + i * s.W;
+        Jac acc = to_jac(bases[i]);
+        Fq prod = fq_one();
+        for (uint32_t w = 0; w < s.W; w++) {
+            if (w) for (uint32_t j = 0; j < s.c; j++) acc = jac_dbl(acc);
+            m[w] = acc;
+            if (!is_inf(acc)) prod = mul(prod, acc.Z);
+            z[w] = prod;
+        }
+        Fq inv = fq_inv(prod);
+        for (uint32_t w = s.W; w-- > 0;) {
+            Jac q = m[w];
+            if (is_inf(q)) { out[w] = aff_inf(); continue; }
+            Fq zi = w ? mul(inv, z[w - 1]) : inv;
+            inv = mul(inv, q.Z);
+            Fq zi2 = sqr(zi);
+            Aff r; r.x = mul(q.X, zi2); r.y = mul(q.Y, mul(zi2, zi));
+            out[w] = r;
+        }
+    }
+};
+struct FixedTableSegs {
+    static constexpr const char* kName = "FixedTableSegs";
+    FixedShape s;
+    uint32_t S, nseg;              // entries per segment, segments per row (S * nseg = NB)
+    const Aff* heads;              // [nb*W]
+    uint64_t t0;                   // this launch covers threads t0 + u
+    Fq* zs; Fq* pz;                // [launch size][S]: Z of every entry / prefix products of the non-zero Z
+    Aff* table;                    // [nb*W][NB] (out; holds X, Y of the Jacobian entry until the back-substitution)
+    CPG_HD void operator()(uint64_t u) const {
+        const uint64_t t = t0 + u, row = t / nseg;
+        const uint32_t seg = (uint32_t)(t % nseg);
+        const Aff Q = heads[row];
+        Aff* out = table + row * (uint64_t)s.NB + (uint64_t)seg * S;
+        Fq* z = zs + u * S; Fq* pp = pz + u * S;
+        // first entry of the segment: (seg S + 1) Q, bits from the top
+        const uint32_t first = seg * S + 1;
+        Jac acc = jac_inf();
+        for (int b = 31 - clz32(first); b >= 0; b--) {
+            acc = jac_dbl(acc);
+            if ((first >> b) & 1) acc = jac_add_mixed(acc, Q);
+        }
+        Fq prod = fq_one();
+        for (uint32_t d = 0; d < S; d++) {
+            Aff xy; xy.x = acc.X; xy.y = acc.Y;
+            const bool inf = is_inf(acc);
+            out[d] = inf ? aff_inf() : xy;
+            z[d] = inf ? fq_zero() : acc.Z;
+            if (!inf) prod = mul(prod, acc.Z);
+            pp[d] = prod;
+            acc = jac_add_mixed(acc, Q);
+        }
+        Fq inv = fq_inv(prod);
+        for (uint32_t d = S; d-- > 0;) {
+            const Fq zd = z[d];
+            if (zd.is_zero()) continue;                                  // identity entry: already written as (0, 0)
+            Fq zi = d ? mul(inv, pp[d - 1]) : inv;
+            inv = mul(inv, zd);
+            Fq zi2 = sqr(zi);
+            Aff q = out[d];
+            Aff r; r.x = mul(q.x, zi2); r.y = mul(q.y, mul(zi2, zi));
+            out[d] = r;
+        }
     }
 };
 struct JacToAff {                  // thread = one point (one Fq inversion each)

@@ -35,28 +35,46 @@ struct POut {
 constexpr uint32_t P_MAX_OUT = 10;     // outputs per round (the SameScalar round has 10)
 constexpr uint32_t P_MAX_VAR = 6;      // of which with a variable-base part
 
-struct PShape { uint32_t ell, n, lg, NF, NR, rounds; };
+struct PShape { uint32_t ell, n, lg, NF, NR, rounds; uint32_t CH, nch; };   // CH * nch >= n: chunks of the two-pass reductions
 
-// per-proof scalar state; the Fr vectors live in PBuffers::vec
-struct PState {
+// A round of a proof is split in two:
+//   * the TRANSCRIPT step (prove_transcript): strictly sequential Keccak work plus O(1) scalars - absorb the previous
+//     round's outputs, squeeze this round's challenges.  One proof per GPU thread for big batches, or on host threads
+//     for a few (large) proofs, where a CPU core runs the Keccak chain ~20x faster than a lone GPU thread (the north
+//     star's placement: "the sequential Merlin/STROBE transcript stays on the host").  Same CPG_HD source either way.
+//   * the VECTOR kernels (ProveVec, ProveReduce*, ProveScan*): all Fr vector work - the grand product and its prefix
+//     products, the blinding polynomials, the IPA / SameMSM folds and the coefficient rows of the round's MSMs - one
+//     thread per (proof, element), sums and products in two short passes (cp/grand_prod.py:49-51, cp/ipa.py:33-46,
+//     142-146, cp/same_msm.py:122-126).  A lone n = 16384 proof therefore runs 16 384 threads wide instead of one.
+// The three small structs below are all that crosses between the two halves (and, with the transcript on the host, PCIe).
+struct PChal {                    // transcript -> vector kernels: the challenges in force
+    HFr alpha_sp, beta_sp, alpha_gp, beta_gp, beta_gp_inv, alpha_ipa, beta_ipa, gam, gam_inv, alpha_msm;
+};
+struct PRes {                     // vector kernels -> transcript: scalars the transcript absorbs or the wire proof carries
+    HFr gprod, r_p, z, c0, c1, d0, d1, x0, x1;
+};
+struct PTr {                      // transcript-side state of one proof
     cpgh::Transcript tr;
-    HFr k, alpha_sp, beta_sp, gprod, alpha_gp, beta_gp, beta_gp_inv, r_p, z;
-    HFr alpha_ipa, beta_ipa, r_t, r_u, r_a, r_b, r_k, z_k, z_t, z_u, alpha_msm;
-    uint32_t len;                 // current folded length of the running loop
+    HFr k, c_final, d_final, z_k, z_t, z_u;
 };
 
 // vectors per proof, each n entries: see PV_* below
-enum { PV_A = 0, PV_APERM, PV_FACT, PV_C, PV_D, PV_X, PV_WG, PV_WGP, PV_W2, PV_ACOEF, PV_MCOEF, PV_BCOEF, PV_U, PV_COUNT };
+enum { PV_APERM = 0, PV_FACT, PV_C, PV_D, PV_X, PV_WG, PV_WGP, PV_W2, PV_ACOEF, PV_MCOEF, PV_BCOEF, PV_U, PV_COUNT };
 
-struct PBuffers {
+struct PBuffers {                 // device side (the vector kernels, and the transcript when it runs on the device)
     const uint8_t* in48;          // [B][2 ell][48]  vec_R | vec_S wire bytes
     const uint8_t* tu48;          // [B][2 ell][48]  vec_T | vec_U wire bytes (round 0 output)
     const uint32_t* perm;         // [B][ell]
     const uint8_t* kbytes;        // [B][32]
     const uint8_t* rand;          // [B][NR][32]     m_bl(4) a_bl(2) c_bl(4) ipa_r(n) ipa_z(n-2) r_t r_u r_a r_b r_k msm_r(n)
     const uint8_t* crs48;         // CRS wire bytes
-    PState* st;                   // [B]
+    PTr* trs;                     // [B]
+    PChal* chal;                  // [B]
+    PRes* res;                    // [B]
+    HFr* achal;                   // [B][ell]        the vec_a challenges, proof-major (written by the transcript)
     HFr* vec;                     // [PV_COUNT][n][B]  (batch-innermost, see FrVec)
+    HFr* part;                    // [2][nch][B]     partial sums / products of the two-pass reductions
+    HFr* red;                     // [2][B]          their totals
     uint8_t* outs48;              // [B][NOUT][48]   compressed outputs, by output id
     uint8_t* fs;                  // [P_MAX_OUT][B][NF][32]  fixed-base coefficient rows of the round being prepared (output-major)
     uint8_t* vs;                  // [P_MAX_VAR][B][ell][32] variable-base coefficient rows
@@ -64,8 +82,8 @@ struct PBuffers {
     uint64_t B;
 };
 
-// A per-proof Fr vector.  Storage is batch-innermost, vec[which][i][b]: the 32 lanes of a warp (32
-// consecutive proofs) touch 32 consecutive elements, instead of 32 rows that lie 13*n*32 bytes apart.
+// A per-proof Fr vector.  Storage is batch-innermost, vec[which][i][b]: consecutive threads (consecutive proofs, same
+// element) touch consecutive words.
 struct FrVec {
     HFr* p; uint64_t stride;
     CPG_HD HFr& operator[](uint32_t i) const { return p[(uint64_t)i * stride]; }
@@ -74,349 +92,412 @@ struct FrVec {
 CPG_HD FrVec pvec(const PShape& sh, const PBuffers& pb, size_t b, int which) { return FrVec{pb.vec + (size_t)which * sh.n * pb.B + b, pb.B}; }
 CPG_HD uint8_t* frow(const PShape& sh, const PBuffers& pb, size_t b, uint32_t o) { return pb.fs + ((size_t)o * pb.B + b) * (size_t)sh.NF * 32; }
 CPG_HD uint8_t* vrow(const PShape& sh, const PBuffers& pb, size_t b, uint32_t o) { return pb.vs + ((size_t)o * pb.B + b) * (size_t)sh.ell * 32; }
-CPG_HD HFr prand(const PBuffers& pb, const PShape& sh, size_t b, uint32_t i) {
-    HFr v; cpgh::fr_from_bytes(&v, pb.rand + (b * sh.NR + i) * 32); return v;
+CPG_HD HFr prand_at(const uint8_t* rand, const PShape& sh, size_t b, uint32_t i) {
+    HFr v; cpgh::fr_from_bytes(&v, rand + (b * sh.NR + i) * 32); return v;   // canonical: cpg_prove_batch checked every blinder
 }
-CPG_HD void zero_rows(const PShape& sh, const PBuffers& pb, size_t b, uint32_t nfix, uint32_t nvar) {
-    for (uint32_t o = 0; o < nfix; o++) cpgh::zero_bytes(frow(sh, pb, b, o), (size_t)sh.NF * 32);
-    for (uint32_t o = 0; o < nvar; o++) cpgh::zero_bytes(vrow(sh, pb, b, o), (size_t)sh.ell * 32);
-}
-CPG_HD HFr ip(const FrVec& a, const FrVec& b, uint32_t n) {
-    HFr acc = cpgh::fr_zero();
-    for (uint32_t i = 0; i < n; i++) acc = cpgh::fr_add(acc, cpgh::fr_mul(a[i], b[i]));
-    return acc;
-}
-// fixed-table index of leaf L of G_wb = vec_G | vec_H[:2] | G_t | G_u
+CPG_HD HFr prand(const PBuffers& pb, const PShape& sh, size_t b, uint32_t i) { return prand_at(pb.rand, sh, b, i); }
+CPG_HD void put(uint8_t* row, uint32_t i, const HFr& v) { cpgh::fr_to_bytes(row + 32 * (size_t)i, v); }
+CPG_HD void put0(uint8_t* row, uint32_t i) { uint64_t* q = (uint64_t*)(row + 32 * (size_t)i); q[0] = q[1] = q[2] = q[3] = 0; }
+// fixed-table index of leaf L of G_wb = vec_G | vec_H[:2] | G_t | G_u, and back (-1: the table entry is not a leaf of G_wb)
 CPG_HD uint32_t gwb_index(const PShape& sh, uint32_t L) { return L < sh.ell + 2 ? L : L + 3; }   // ell+2 -> n+1 (G_t), ell+3 -> n+2 (G_u)
+CPG_HD int gwb_leaf(const PShape& sh, uint32_t i) { return i < sh.ell + 2 ? (int)i : (i == sh.n + 1 ? (int)sh.ell + 2 : (i == sh.n + 2 ? (int)sh.ell + 3 : -1)); }
 
 // offsets into the rand array
 struct PRand { uint32_t m_bl = 0, a_bl = 4, c_bl = 6, ipa_r = 10, ipa_z, r_t, r_u, r_a, r_b, r_k, msm_r, NR;
     CPG_HD explicit PRand(uint32_t n) { ipa_z = ipa_r + n; r_t = ipa_z + (n - 2); r_u = r_t + 1; r_a = r_u + 1; r_b = r_a + 1; r_k = r_b + 1; msm_r = r_k + 1; NR = msm_r + n; } };
 
-// One round of one proof.  Rounds: 0 M | 1 A | 2 B | 3 C | 4 D,B_c,B_d | 5..4+lg IPA | 5+lg SameScalar |
-// 6+lg A',B_a,B_t,B_u | 7+lg..6+2lg SameMSM | 7+2lg finish (assemble the wire proof).
-CPG_HD void prove_step(const PShape& sh, const POut& O, const PBuffers& pb, uint32_t round, size_t b) {
+// Rounds: 0 M | 1 A | 2 B | 3 C | 4 D,B_c,B_d | 5..4+lg IPA | 5+lg SameScalar | 6+lg A',B_a,B_t,B_u |
+// 7+lg..6+2lg SameMSM | 7+2lg finish (assemble the wire proof).
+struct PRounds { uint32_t IPA0, SS, MSM_INIT, MSM0, FIN;
+    CPG_HD explicit PRounds(uint32_t lg) { IPA0 = 5; SS = 5 + lg; MSM_INIT = 6 + lg; MSM0 = 7 + lg; FIN = 7 + 2 * lg; } };
+
+// ---- the transcript step of one round of one proof -------------------------------------------------------------------
+// Every pointer lives in the memory space of whoever runs it (device buffers, or the host mirrors of ProverLane).
+struct PTBuf {
+    const uint8_t* in48; const uint8_t* tu48; const uint8_t* kbytes; const uint8_t* rand; const uint8_t* crs48;
+    const uint8_t* outs48;        // [B][NOUT][48]
+    PTr* trs; PChal* chal; const PRes* res; HFr* achal;
+    uint8_t* proof;               // [B][proof_len]
+};
+CPG_HD void prove_transcript(const PShape& sh, const POut& O, const PTBuf& pt, uint32_t round, size_t b) {
     using namespace cpgh;
     const uint32_t ell = sh.ell, n = sh.n, lg = sh.lg;
     const PRand RO(n);
-    PState& s = pb.st[b];
-    const uint8_t* outs = pb.outs48 + b * (size_t)O.NOUT * 48;
-    FrVec a = pvec(sh, pb, b, PV_A);
-    FrVec aperm = pvec(sh, pb, b, PV_APERM);
-    FrVec fact = pvec(sh, pb, b, PV_FACT);
-    FrVec c = pvec(sh, pb, b, PV_C);
-    FrVec d = pvec(sh, pb, b, PV_D);
-    FrVec x = pvec(sh, pb, b, PV_X);
-    FrVec wG = pvec(sh, pb, b, PV_WG);
-    FrVec wGp = pvec(sh, pb, b, PV_WGP);
-    FrVec w2 = pvec(sh, pb, b, PV_W2);
-    FrVec Acoef = pvec(sh, pb, b, PV_ACOEF);
-    FrVec Mcoef = pvec(sh, pb, b, PV_MCOEF);
-    FrVec Bcoef = pvec(sh, pb, b, PV_BCOEF);
-    FrVec uvec = pvec(sh, pb, b, PV_U);
-    const uint32_t* perm = pb.perm + b * (size_t)ell;
+    const PRounds R(lg);
+    if (round == 0) return;                                                // M needs no challenge
+    PTr& s = pt.trs[b];
+    PChal ch = pt.chal[b];
+    const PRes& rs = pt.res[b];
+    const uint8_t* outs = pt.outs48 + b * (size_t)O.NOUT * 48;
+    HFr* a = pt.achal + b * (size_t)ell;
+    // the STROBE state is worked on in thread-local storage and written back once (per-thread structs in global memory
+    // make every byte XOR an uncoalesced read-modify-write)
     Transcript tr;
-    if (round > 0) tr = s.tr;
-
-    if (round == 0) {                                   // M = MSM(vec_G, sigma) + MSM(vec_H, m_bl)   (curdleproofs.py:310-319)
-        fr_from_bytes(&s.k, pb.kbytes + b * 32);
-        zero_rows(sh, pb, b, 1, 0);
-        for (uint32_t i = 0; i < n; i++) Mcoef[i] = i < ell ? fr_from_u64(perm[i]) : prand(pb, sh, b, RO.m_bl + (i - ell));
-        uint8_t* f = frow(sh, pb, b, 0);
-        for (uint32_t i = 0; i < n; i++) fr_to_bytes(f + 32 * (size_t)i, Mcoef[i]);
-        return;                                         // no transcript yet
-    }
-    if (round == 1) {                                   // step1 -> vec_a -> A                         (curdleproofs.py:65-77)
+    if (round > 1) tr = s.tr;
+    if (round == 1) {                                   // step1 -> vec_a                              (curdleproofs.py:65-71)
+        fr_from_bytes(&s.k, pt.kbytes + b * 32);
         tr.init("curdleproofs");
-        const uint8_t* in = pb.in48 + b * (size_t)(2 * ell) * 48;
-        const uint8_t* tu = pb.tu48 + b * (size_t)(2 * ell) * 48;
+        const uint8_t* in = pt.in48 + b * (size_t)(2 * ell) * 48;
+        const uint8_t* tu = pt.tu48 + b * (size_t)(2 * ell) * 48;
         for (uint32_t i = 0; i < 2 * ell; i++) tr.append_point("curdleproofs_step1", in + 48 * (size_t)i);
         for (uint32_t i = 0; i < 2 * ell; i++) tr.append_point("curdleproofs_step1", tu + 48 * (size_t)i);
         tr.append_point("curdleproofs_step1", outs + 48 * O.M);
         for (uint32_t i = 0; i < ell; i++) a[i] = tr.challenge("curdleproofs_vec_a");
-        for (uint32_t i = 0; i < ell; i++) aperm[i] = a[perm[i]];
-        aperm[ell] = prand(pb, sh, b, RO.a_bl); aperm[ell + 1] = prand(pb, sh, b, RO.a_bl + 1);   // a_bl; r_a' = a_bl | 0 0
-        aperm[ell + 2] = fr_zero(); aperm[ell + 3] = fr_zero();
-        zero_rows(sh, pb, b, 1, 0);
-        uint8_t* f = frow(sh, pb, b, 0);
-        for (uint32_t i = 0; i < n; i++) { Acoef[i] = aperm[i]; fr_to_bytes(f + 32 * (size_t)i, Acoef[i]); }
-        s.tr = tr;
-        return;
-    }
-    if (round == 2) {                                   // same_perm: alpha, beta, B                   (same_perm.py:43-55)
+    } else if (round == 2) {                            // same_perm: alpha, beta                     (same_perm.py:43-46)
         tr.append_point("same_perm_step1", outs + 48 * O.A);
         tr.append_point("same_perm_step1", outs + 48 * O.M);
         for (uint32_t i = 0; i < ell; i++) tr.append_fr("same_perm_step1", a[i]);
-        s.alpha_sp = tr.challenge("same_perm_alpha");
-        s.beta_sp = tr.challenge("same_perm_beta");
-        HFr g = fr_one();
-        for (uint32_t i = 0; i < ell; i++) {
-            fact[i] = fr_add(fr_add(aperm[i], fr_mul(fr_from_u64(perm[i]), s.alpha_sp)), s.beta_sp);
-            g = fr_mul(g, fact[i]);
-        }
-        s.gprod = g;
-        zero_rows(sh, pb, b, 1, 0);
-        uint8_t* f = frow(sh, pb, b, 0);
-        for (uint32_t i = 0; i < n; i++) {
-            HFr t = fr_add(Acoef[i], fr_mul(s.alpha_sp, Mcoef[i]));
-            if (i < ell) t = fr_add(t, s.beta_sp);
-            Bcoef[i] = t;
-            fr_to_bytes(f + 32 * (size_t)i, t);
-        }
-        s.tr = tr;
-        return;
-    }
-    if (round == 3) {                                   // gprod step 1: alpha, C                      (grand_prod.py:44-54)
+        ch.alpha_sp = tr.challenge("same_perm_alpha");
+        ch.beta_sp = tr.challenge("same_perm_beta");
+    } else if (round == 3) {                            // gprod step 1: alpha                        (grand_prod.py:44-46)
         tr.append_point("gprod_step1", outs + 48 * O.B);
-        tr.append_fr("gprod_step1", s.gprod);
-        s.alpha_gp = tr.challenge("gprod_alpha");
-        c[0] = fr_one();
-        for (uint32_t i = 0; i + 1 < ell; i++) c[i + 1] = fr_mul(c[i], fact[i]);
-        for (uint32_t i = 0; i < 4; i++) c[ell + i] = prand(pb, sh, b, RO.c_bl + i);
-        // b_bl = r_a' + alpha_sp m_bl ; rb_alpha = b_bl + alpha_gp ; r_p = <rb_alpha, c_bl>
-        HFr rp = fr_zero();
-        for (uint32_t i = 0; i < 4; i++) {
-            HFr bbl = fr_add(aperm[ell + i], fr_mul(s.alpha_sp, Mcoef[ell + i]));
-            d[ell + i] = fr_add(bbl, s.alpha_gp);        // park rb_alpha in d's blinder slots
-            rp = fr_add(rp, fr_mul(d[ell + i], c[ell + i]));
+        tr.append_fr("gprod_step1", rs.gprod);
+        ch.alpha_gp = tr.challenge("gprod_alpha");
+    } else if (round == 4) {                            // gprod step 2: beta                         (grand_prod.py:59-61)
+        tr.append_point("gprod_step2", outs + 48 * O.C);
+        tr.append_fr("gprod_step2", rs.r_p);
+        ch.beta_gp = tr.challenge("gprod_beta");
+        ch.beta_gp_inv = fr_inv(ch.beta_gp);
+    } else if (round == R.IPA0) {                       // IPA: alpha, beta                           (ipa.py:100-105)
+        tr.append_point("ipa_step1", outs + 48 * O.C);
+        tr.append_point("ipa_step1", outs + 48 * O.D);
+        tr.append_fr("ipa_step1", rs.z);
+        tr.append_point("ipa_step1", outs + 48 * O.Bc);
+        tr.append_point("ipa_step1", outs + 48 * O.Bd);
+        ch.alpha_ipa = tr.challenge("ipa_alpha");
+        ch.beta_ipa = tr.challenge("ipa_beta");
+    } else if (round > R.IPA0 && round <= R.SS) {       // IPA rounds: gamma                          (ipa.py:136-139)
+        const uint8_t* pr = outs + 48 * (size_t)(O.ipa0 + 4 * (round - R.IPA0 - 1));
+        for (uint32_t k = 0; k < 4; k++) tr.append_point("ipa_loop", pr + 48 * k);
+        ch.gam = tr.challenge("ipa_gamma");
+        ch.gam_inv = fr_inv(ch.gam);
+        if (round == R.SS) {                            // last fold: c_final, d_final
+            s.c_final = fr_add(rs.c0, fr_mul(ch.gam_inv, rs.c1));
+            s.d_final = fr_add(rs.d0, fr_mul(ch.gam, rs.d1));
         }
-        s.r_p = rp;
-        zero_rows(sh, pb, b, 1, 0);
-        uint8_t* f = frow(sh, pb, b, 0);
-        for (uint32_t i = 0; i < n; i++) fr_to_bytes(f + 32 * (size_t)i, c[i]);
-        s.tr = tr;
+    } else if (round == R.MSM_INIT) {                   // SameScalar: alpha, responses               (same_scalar.py:46-63)
+        const uint32_t ss[10] = {O.Rp, O.Sp, O.T1, O.T2, O.U1, O.U2, O.A1, O.A2, O.B1, O.B2};
+        for (uint32_t k = 0; k < 10; k++) tr.append_point("sameexp_points", outs + 48 * (size_t)ss[k]);
+        HFr alpha = tr.challenge("same_scalar_alpha");
+        const HFr r_t = prand_at(pt.rand, sh, b, RO.r_t), r_u = prand_at(pt.rand, sh, b, RO.r_u);
+        const HFr r_a = prand_at(pt.rand, sh, b, RO.r_a), r_b = prand_at(pt.rand, sh, b, RO.r_b), r_k = prand_at(pt.rand, sh, b, RO.r_k);
+        s.z_k = fr_add(r_k, fr_mul(s.k, alpha));
+        s.z_t = fr_add(r_a, fr_mul(r_t, alpha));
+        s.z_u = fr_add(r_b, fr_mul(r_u, alpha));
+    } else if (round == R.MSM0) {                       // SameMSM: alpha                             (same_msm.py:79-88)
+        tr.append_point("same_msm_step1", outs + 48 * O.Ap);
+        tr.append_point("same_msm_step1", outs + 48 * O.T2);
+        tr.append_point("same_msm_step1", outs + 48 * O.U2);
+        uint8_t INF[48]; memset(INF, 0, 48); INF[0] = 0xc0;
+        const uint8_t* Hb = pt.crs48 + 48 * (size_t)n;
+        const uint8_t* tu = pt.tu48 + b * (size_t)(2 * ell) * 48;
+        for (uint32_t i = 0; i < ell; i++) tr.append_point("same_msm_step1", tu + 48 * (size_t)i);
+        tr.append_point("same_msm_step1", INF); tr.append_point("same_msm_step1", INF);
+        tr.append_point("same_msm_step1", Hb); tr.append_point("same_msm_step1", INF);
+        for (uint32_t i = 0; i < ell; i++) tr.append_point("same_msm_step1", tu + 48 * (size_t)(ell + i));
+        tr.append_point("same_msm_step1", INF); tr.append_point("same_msm_step1", INF);
+        tr.append_point("same_msm_step1", INF); tr.append_point("same_msm_step1", Hb);
+        tr.append_point("same_msm_step1", outs + 48 * O.Ba);
+        tr.append_point("same_msm_step1", outs + 48 * O.Bt);
+        tr.append_point("same_msm_step1", outs + 48 * O.Bu);
+        ch.alpha_msm = tr.challenge("same_msm_alpha");
+    } else if (round > R.MSM0 && round <= R.FIN) {      // SameMSM rounds: gamma                      (same_msm.py:115-119)
+        const uint8_t* pr = outs + 48 * (size_t)(O.msm0 + 6 * (round - R.MSM0 - 1));
+        for (uint32_t k = 0; k < 6; k++) tr.append_point("same_msm_loop", pr + 48 * k);
+        ch.gam = tr.challenge("same_msm_gamma");
+        ch.gam_inv = fr_inv(ch.gam);
+        if (round == R.FIN) {                           // last fold + wire assembly                  (curdleproofs.py:275-285)
+            HFr x_final = fr_add(rs.x0, fr_mul(ch.gam_inv, rs.x1));
+            uint8_t* w = pt.proof + b * (size_t)(1088 + 480 * (size_t)lg);
+            auto ptc = [&](uint32_t id) { memcpy(w, outs + 48 * (size_t)id, 48); w += 48; };
+            auto sc = [&](const HFr& v) { fr_to_bytes(w, v); w += 32; };
+            ptc(O.A); ptc(O.T1); ptc(O.T2); ptc(O.U1); ptc(O.U2); ptc(O.Rp); ptc(O.Sp);
+            ptc(O.B); ptc(O.C); sc(rs.r_p);
+            ptc(O.Bc); ptc(O.Bd);
+            for (uint32_t k = 0; k < 4; k++) {           // L_C[], R_C[], L_D[], R_D[]  (ipa.py:260-270)
+                const uint32_t sel[4] = {0, 2, 1, 3};    // stored per round as L_C, L_D, R_C, R_D
+                for (uint32_t j = 0; j < lg; j++) ptc(O.ipa0 + 4 * j + sel[k]);
+            }
+            sc(s.c_final); sc(s.d_final);
+            ptc(O.A1); ptc(O.A2); ptc(O.B1); ptc(O.B2); sc(s.z_k); sc(s.z_t); sc(s.z_u);
+            ptc(O.Ba); ptc(O.Bt); ptc(O.Bu);
+            for (uint32_t k = 0; k < 6; k++) for (uint32_t j = 0; j < lg; j++) ptc(O.msm0 + 6 * j + k);   // L_A L_T L_U R_A R_T R_U
+            sc(x_final);
+        }
+    }
+    s.tr = tr;
+    pt.chal[b] = ch;
+}
+struct ProveTranscript {          // thread = proof (device placement)
+    static constexpr const char* kName = "ProveTranscript";
+    PShape sh; POut O; PTBuf pt; uint32_t round;
+    CPG_HD void operator()(uint64_t b) const { prove_transcript(sh, O, pt, round, (size_t)b); }
+};
+
+// ---- the vector kernels -------------------------------------------------------------------------------------------
+// Element-wise stage `phase` of round `round` for element i of proof b; i runs over the NF = n + 3 entries of a
+// fixed-base coefficient row (vec_G | vec_H | H | G_t | G_u), of which the first n are also the indices of the Fr vectors.
+// Every entry of every coefficient row of the round is written (zeros included), so rows need no separate clearing.
+CPG_HD void prove_vec(const PShape& sh, const PBuffers& pb, uint32_t round, uint32_t phase, size_t b, uint32_t i) {
+    using namespace cpgh;
+    const uint32_t ell = sh.ell, n = sh.n, lg = sh.lg;
+    const PRand RO(n);
+    const PRounds R(lg);
+    const PChal& ch = pb.chal[b];
+    PRes& rs = pb.res[b];
+    const uint32_t* perm = pb.perm + b * (size_t)ell;
+    FrVec aperm = pvec(sh, pb, b, PV_APERM), fact = pvec(sh, pb, b, PV_FACT), c = pvec(sh, pb, b, PV_C), d = pvec(sh, pb, b, PV_D);
+    FrVec x = pvec(sh, pb, b, PV_X), wG = pvec(sh, pb, b, PV_WG), wGp = pvec(sh, pb, b, PV_WGP), w2 = pvec(sh, pb, b, PV_W2);
+    FrVec Acoef = pvec(sh, pb, b, PV_ACOEF), Mcoef = pvec(sh, pb, b, PV_MCOEF), Bcoef = pvec(sh, pb, b, PV_BCOEF), uvec = pvec(sh, pb, b, PV_U);
+    uint8_t* f0 = frow(sh, pb, b, 0);
+
+    if (round == 0) {                                   // M = MSM(vec_G, sigma) + MSM(vec_H, m_bl)   (curdleproofs.py:310-319)
+        if (i < n) { HFr v = i < ell ? fr_from_u64(perm[i]) : prand(pb, sh, b, RO.m_bl + (i - ell)); Mcoef[i] = v; put(f0, i, v); }
+        else put0(f0, i);
         return;
     }
-    if (round == 4) {                                   // gprod step 2: beta, D; IPA blinders, B_c, B_d (grand_prod.py:59-90, ipa.py:27-48,97-98)
-        tr.append_point("gprod_step2", outs + 48 * O.C);
-        tr.append_fr("gprod_step2", s.r_p);
-        s.beta_gp = tr.challenge("gprod_beta");
-        s.beta_gp_inv = fr_inv(s.beta_gp);
-        // d_i = b_i beta^(i+1) - beta^i ; d_bl = beta^(ell+1) rb_alpha ; u_i = beta^-(i+1) (blinders beta^-(ell+1))
-        HFr pw = fr_one(), ui = s.beta_gp_inv;
-        for (uint32_t i = 0; i < ell; i++) {
-            HFr pw1 = fr_mul(pw, s.beta_gp);
-            d[i] = fr_sub(fr_mul(fact[i], pw1), pw);
-            uvec[i] = ui;
-            ui = fr_mul(ui, s.beta_gp_inv);
-            pw = pw1;
+    if (round == 1) {                                   // A = MSM(vec_G, sigma(a)) + MSM(vec_H, a_bl | 0 0)  (curdleproofs.py:72-77)
+        if (i < n) {
+            HFr v = i < ell ? pb.achal[b * (size_t)ell + perm[i]] : (i < ell + 2 ? prand(pb, sh, b, RO.a_bl + (i - ell)) : fr_zero());
+            aperm[i] = v; Acoef[i] = v; put(f0, i, v);
+        } else put0(f0, i);
+        return;
+    }
+    if (round == 2) {                                   // B; the grand product's factors              (same_perm.py:49-55)
+        if (i < n) {
+            if (i < ell) fact[i] = fr_add(fr_add(aperm[i], fr_mul(fr_from_u64(perm[i]), ch.alpha_sp)), ch.beta_sp);
+            HFr t = fr_add(Acoef[i], fr_mul(ch.alpha_sp, Mcoef[i]));
+            if (i < ell) t = fr_add(t, ch.beta_sp);
+            Bcoef[i] = t; put(f0, i, t);
+        } else put0(f0, i);
+        return;
+    }
+    if (round == 3) {                                   // C (prefix products c[0..ell) come from ProveScan)   (grand_prod.py:49-57)
+        if (i < ell) put(f0, i, c[i]);
+        else if (i < n) {
+            HFr cb = prand(pb, sh, b, RO.c_bl + (i - ell));
+            c[i] = cb;
+            d[i] = fr_add(fr_add(aperm[i], fr_mul(ch.alpha_sp, Mcoef[i])), ch.alpha_gp);   // rb_alpha, parked in d's blinder slots
+            put(f0, i, cb);
+        } else put0(f0, i);
+        if (i == 0) {                                   // r_p = <rb_alpha, c_bl>
+            HFr rp = fr_zero();
+            for (uint32_t q = 0; q < 4; q++) {
+                HFr rb = fr_add(fr_add(aperm[ell + q], fr_mul(ch.alpha_sp, Mcoef[ell + q])), ch.alpha_gp);
+                rp = fr_add(rp, fr_mul(rb, prand(pb, sh, b, RO.c_bl + q)));
+            }
+            rs.r_p = rp;
         }
-        HFr beta_l = pw, beta_l1 = fr_mul(pw, s.beta_gp);     // beta^ell, beta^(ell+1)
-        for (uint32_t i = 0; i < 4; i++) { d[ell + i] = fr_mul(beta_l1, d[ell + i]); uvec[ell + i] = ui; }   // ui = beta^-(ell+1)
-        s.z = fr_sub(fr_add(fr_mul(s.r_p, beta_l1), fr_mul(s.gprod, beta_l)), fr_one());
-        // IPA blinders (ipa.py:27-48): r in x (scratch), z in w2 (scratch)
-        FrVec r = x, zz = w2;
-        for (uint32_t i = 0; i < n; i++) r[i] = prand(pb, sh, b, RO.ipa_r + i);
-        for (uint32_t i = 0; i + 2 < n; i++) zz[i] = prand(pb, sh, b, RO.ipa_z + i);
-        HFr omega = fr_add(ip(r, d, n), ip(zz, c, n - 2));
-        HFr delta = ip(r, zz, n - 2);
+        return;
+    }
+    if (round == 4 && phase == 0) {                     // d, u = beta^-(i+1), IPA blinders            (grand_prod.py:66-89, ipa.py:27-31)
+        if (i < n) {
+            if (i < ell) {
+                HFr pw = fr_pow_u64(ch.beta_gp, i), pw1 = fr_mul(pw, ch.beta_gp);
+                d[i] = fr_sub(fr_mul(fact[i], pw1), pw);                 // b_i beta^(i+1) - beta^i
+                uvec[i] = fr_pow_u64(ch.beta_gp_inv, i + 1);
+            } else {
+                d[i] = fr_mul(fr_pow_u64(ch.beta_gp, ell + 1), d[i]);   // d_bl = beta^(ell+1) rb_alpha
+                uvec[i] = fr_pow_u64(ch.beta_gp_inv, ell + 1);
+            }
+            x[i] = prand(pb, sh, b, RO.ipa_r + i);                      // r (scratch in x)
+            if (i + 2 < n) w2[i] = prand(pb, sh, b, RO.ipa_z + i);       // z (scratch in w2); its last two entries follow the sums
+        }
+        if (i == 0) {
+            HFr beta_l = fr_pow_u64(ch.beta_gp, ell), beta_l1 = fr_mul(beta_l, ch.beta_gp);
+            rs.z = fr_sub(fr_add(fr_mul(rs.r_p, beta_l1), fr_mul(rs.gprod, beta_l)), fr_one());
+        }
+        return;
+    }
+    if (round == 4) {                                   // rows of D, B_c, B_d                          (grand_prod.py:90, ipa.py:97-98)
+        uint8_t *fD = f0, *fBc = frow(sh, pb, b, 1), *fBd = frow(sh, pb, b, 2);
+        if (i < n) {
+            HFr t = i < ell ? fr_sub(Bcoef[i], ch.beta_gp_inv) : fr_add(Bcoef[i], ch.alpha_gp);
+            HFr r = x[i], zz = w2[i];
+            put(fD, i, t); put(fBc, i, r); put(fBd, i, fr_mul(zz, uvec[i]));
+            wG[i] = r; wGp[i] = zz;                                       // r_c / r_d wait here until alpha is known
+        } else { put0(fD, i); put0(fBc, i); put0(fBd, i); }
+        return;
+    }
+    if (round >= R.IPA0 && round < R.SS) {              // IPA rounds                                   (ipa.py:107-151)
+        const uint32_t j = round - R.IPA0, len = n >> j, m = len / 2;
+        if (phase == 0) {
+            if (j == 0) {
+                if (i < n) {                            // c = r_c + alpha c ; d = r_d + alpha d ; leaf weights reset
+                    c[i] = fr_add(wG[i], fr_mul(ch.alpha_ipa, c[i]));
+                    d[i] = fr_add(wGp[i], fr_mul(ch.alpha_ipa, d[i]));
+                    wG[i] = fr_one(); wGp[i] = uvec[i];
+                }
+            } else {                                    // fold the halves of the previous length 2 len
+                if (i < len) { c[i] = fr_add(c[i], fr_mul(ch.gam_inv, c[len + i])); d[i] = fr_add(d[i], fr_mul(ch.gam, d[len + i])); }
+                if (i < n && ((i / len) & 1)) { wG[i] = fr_mul(wG[i], ch.gam); wGp[i] = fr_mul(wGp[i], ch.gam_inv); }
+            }
+            return;
+        }
+        uint8_t *fLC = f0, *fLD = frow(sh, pb, b, 1), *fRC = frow(sh, pb, b, 2), *fRD = frow(sh, pb, b, 3);
+        if (i < n) {
+            const uint32_t q = i % m;
+            if ((i / m) & 1) {                          // the leaf folds into the right half
+                put(fLC, i, fr_mul(c[q], wG[i])); put(fRD, i, fr_mul(d[q], wGp[i]));           // MSM(G_R, c_L), MSM(G'_R, d_L)
+                put0(fRC, i); put0(fLD, i);
+            } else {
+                put(fRC, i, fr_mul(c[m + q], wG[i])); put(fLD, i, fr_mul(d[m + q], wGp[i]));   // MSM(G_L, c_R), MSM(G'_L, d_R)
+                put0(fLC, i); put0(fRD, i);
+            }
+        } else if (i == n) {                            // + H beta <c_L, d_R> and + H beta <c_R, d_L>
+            put(fLC, i, fr_mul(ch.beta_ipa, pb.red[b])); put(fRC, i, fr_mul(ch.beta_ipa, pb.red[pb.B + b]));
+            put0(fLD, i); put0(fRD, i);
+        } else { put0(fLC, i); put0(fLD, i); put0(fRC, i); put0(fRD, i); }
+        if (i == 0 && len == 2) { rs.c0 = c[0]; rs.c1 = c[1]; rs.d0 = d[0]; rs.d1 = d[1]; }
+        return;
+    }
+    if (round == R.SS) {                                // R', S', cm_T, cm_U, cm_A, cm_B              (curdleproofs.py:92-102, same_scalar.py:39-44)
+        // outputs: Rp Sp T1 T2 U1 U2 A1 A2 B1 B2 ; var rows: 0 R' = MSM(vec_R, a), 1 S' = MSM(vec_S, a); the commitments'
+        // k R', r_k R', k S', r_k S' are one scalar-mul each of those results (ProveCombine)
+        for (uint32_t o = 0; o < 10; o++) put0(frow(sh, pb, b, o), i);
+        if (i == n) {                                   // H
+            put(frow(sh, pb, b, 3), i, prand(pb, sh, b, RO.r_t)); put(frow(sh, pb, b, 5), i, prand(pb, sh, b, RO.r_u));
+            put(frow(sh, pb, b, 7), i, prand(pb, sh, b, RO.r_a)); put(frow(sh, pb, b, 9), i, prand(pb, sh, b, RO.r_b));
+        } else if (i == n + 1) {                        // G_t
+            put(frow(sh, pb, b, 2), i, prand(pb, sh, b, RO.r_t)); put(frow(sh, pb, b, 6), i, prand(pb, sh, b, RO.r_a));
+        } else if (i == n + 2) {                        // G_u
+            put(frow(sh, pb, b, 4), i, prand(pb, sh, b, RO.r_u)); put(frow(sh, pb, b, 8), i, prand(pb, sh, b, RO.r_b));
+        }
+        if (i < ell) { uint8_t* vR = vrow(sh, pb, b, 0); put(vR, i, pb.achal[b * (size_t)ell + i]); cpgh::copy32(vrow(sh, pb, b, 1) + 32 * (size_t)i, vR + 32 * (size_t)i); }
+        return;
+    }
+    if (round == R.MSM_INIT) {                          // A', B_a, B_t, B_u                             (same_msm.py:73-77)
+        // x_wb = a_perm | a_bl | r_t r_u ; the blinders r wait in w2 until alpha_msm is known
+        if (i < n) {
+            x[i] = i < ell + 2 ? aperm[i] : prand(pb, sh, b, i == ell + 2 ? RO.r_t : RO.r_u);
+            w2[i] = prand(pb, sh, b, RO.msm_r + i);
+        }
+        uint8_t *fAp = f0, *fBa = frow(sh, pb, b, 1), *fBt = frow(sh, pb, b, 2), *fBu = frow(sh, pb, b, 3);
+        if (i < n) put(fAp, i, Acoef[i]);
+        else if (i == n) put0(fAp, i);
+        else put(fAp, i, prand(pb, sh, b, i == n + 1 ? RO.r_t : RO.r_u));      // + cm_T.T_1 = G_t r_t, + cm_U.T_1 = G_u r_u
+        const int L = gwb_leaf(sh, i);
+        if (L >= 0) put(fBa, i, prand(pb, sh, b, RO.msm_r + (uint32_t)L)); else put0(fBa, i);
+        if (i == n) { put(fBt, i, prand(pb, sh, b, RO.msm_r + ell + 2)); put(fBu, i, prand(pb, sh, b, RO.msm_r + ell + 3)); }   // T_wb = vec_T | 0 0 H 0, U_wb = vec_U | 0 0 0 H
+        else { put0(fBt, i); put0(fBu, i); }
+        if (i < ell) { uint8_t* vT = vrow(sh, pb, b, 0); put(vT, i, prand(pb, sh, b, RO.msm_r + i)); cpgh::copy32(vrow(sh, pb, b, 1) + 32 * (size_t)i, vT + 32 * (size_t)i); }
+        return;
+    }
+    if (round >= R.MSM0 && round < R.FIN) {             // SameMSM rounds                                 (same_msm.py:90-131)
+        const uint32_t j = round - R.MSM0, len = n >> j, m = len / 2;
+        if (phase == 0) {
+            if (j == 0) { if (i < n) { x[i] = fr_add(w2[i], fr_mul(ch.alpha_msm, x[i])); w2[i] = fr_one(); } }
+            else {
+                if (i < len) x[i] = fr_add(x[i], fr_mul(ch.gam_inv, x[len + i]));
+                if (i < n && ((i / len) & 1)) w2[i] = fr_mul(w2[i], ch.gam);
+            }
+            return;
+        }
+        // outputs: 0 L_A 1 L_T 2 L_U 3 R_A 4 R_T 5 R_U ; var rows: 0 L_T (T) 1 L_U (U) 2 R_T (T) 3 R_U (U)
+        // L_* = MSM(v[m:], x_L), R_* = MSM(v[:m], x_R): a leaf in a right half carries x[q] into L_*, else x[m + q] into R_*
+        uint8_t *fLA = f0, *fLT = frow(sh, pb, b, 1), *fLU = frow(sh, pb, b, 2), *fRA = frow(sh, pb, b, 3), *fRT = frow(sh, pb, b, 4), *fRU = frow(sh, pb, b, 5);
+        auto coef_of = [&](uint32_t L, bool* right) { const uint32_t q = L % m; *right = ((L / m) & 1) != 0; return fr_mul(*right ? x[q] : x[m + q], w2[L]); };
+        const int L = gwb_leaf(sh, i);
+        if (L >= 0) { bool right; HFr cf = coef_of((uint32_t)L, &right); if (right) { put(fLA, i, cf); put0(fRA, i); } else { put(fRA, i, cf); put0(fLA, i); } }
+        else { put0(fLA, i); put0(fRA, i); }
+        put0(fLT, i); put0(fLU, i); put0(fRT, i); put0(fRU, i);
+        if (i == n) {                                   // H inside T_wb (leaf ell + 2) and inside U_wb (leaf ell + 3)
+            bool right; HFr cf = coef_of(ell + 2, &right); put(right ? fLT : fRT, i, cf);
+            cf = coef_of(ell + 3, &right); put(right ? fLU : fRU, i, cf);
+        }
+        if (i < ell) {
+            bool right; HFr cf = coef_of(i, &right);
+            uint8_t *vLT = vrow(sh, pb, b, 0), *vLU = vrow(sh, pb, b, 1), *vRT = vrow(sh, pb, b, 2), *vRU = vrow(sh, pb, b, 3);
+            if (right) { put(vLT, i, cf); cpgh::copy32(vLU + 32 * (size_t)i, vLT + 32 * (size_t)i); put0(vRT, i); put0(vRU, i); }
+            else { put(vRT, i, cf); cpgh::copy32(vRU + 32 * (size_t)i, vRT + 32 * (size_t)i); put0(vLT, i); put0(vLU, i); }
+        }
+        if (i == 0 && len == 2) { rs.x0 = x[0]; rs.x1 = x[1]; }
+        return;
+    }
+}
+struct ProveVec {                 // thread = (element i, proof b), proofs innermost
+    static constexpr const char* kName = "ProveVec";
+    PShape sh; PBuffers pb; uint32_t round, phase;
+    CPG_HD void operator()(uint64_t t) const { prove_vec(sh, pb, round, phase, (size_t)(t % pb.B), (uint32_t)(t / pb.B)); }
+};
+
+// Sums and products over a proof's vectors in two short passes: thread (chunk, b) reduces CH consecutive elements,
+// thread b then combines the nch partials (serial depth CH + nch ~ 2 sqrt(n) instead of n).
+enum { PR_PROD_FACT = 0, PR_IPA_BLIND = 1, PR_IPA_LR = 2 };
+struct ProveReduce1 {
+    static constexpr const char* kName = "ProveReduce1";
+    PShape sh; PBuffers pb; uint32_t kind, m;             // m: half length of the IPA round (PR_IPA_LR)
+    CPG_HD void operator()(uint64_t t) const {
+        using namespace cpgh;
+        const size_t b = (size_t)(t % pb.B); const uint32_t k = (uint32_t)(t / pb.B);
+        const uint32_t lo = k * sh.CH, hi0 = lo + sh.CH;
+        HFr* p0 = pb.part + (size_t)k * pb.B + b; HFr* p1 = pb.part + ((size_t)sh.nch + k) * pb.B + b;
+        if (kind == PR_PROD_FACT) {                        // prod_{i < ell} fact[i]
+            FrVec fact = pvec(sh, pb, b, PV_FACT);
+            HFr acc = fr_one();
+            for (uint32_t i = lo; i < hi0 && i < sh.ell; i++) acc = fr_mul(acc, fact[i]);
+            *p0 = acc;
+        } else if (kind == PR_IPA_BLIND) {                 // omega = <r, d> + <z, c>_{n-2}, delta = <r, z>_{n-2}   (ipa.py:33-35)
+            FrVec r = pvec(sh, pb, b, PV_X), zz = pvec(sh, pb, b, PV_W2), c = pvec(sh, pb, b, PV_C), d = pvec(sh, pb, b, PV_D);
+            HFr om = fr_zero(), de = fr_zero();
+            for (uint32_t i = lo; i < hi0 && i < sh.n; i++) {
+                om = fr_add(om, fr_mul(r[i], d[i]));
+                if (i + 2 < sh.n) { om = fr_add(om, fr_mul(zz[i], c[i])); de = fr_add(de, fr_mul(r[i], zz[i])); }
+            }
+            *p0 = om; *p1 = de;
+        } else {                                           // <c_L, d_R>, <c_R, d_L> over the current halves       (ipa.py:126-129)
+            FrVec c = pvec(sh, pb, b, PV_C), d = pvec(sh, pb, b, PV_D);
+            HFr l = fr_zero(), r = fr_zero();
+            for (uint32_t i = lo; i < hi0 && i < m; i++) { l = fr_add(l, fr_mul(c[i], d[m + i])); r = fr_add(r, fr_mul(c[m + i], d[i])); }
+            *p0 = l; *p1 = r;
+        }
+    }
+};
+struct ProveReduce2 {             // thread = proof
+    static constexpr const char* kName = "ProveReduce2";
+    PShape sh; PBuffers pb; uint32_t kind;
+    CPG_HD void operator()(uint64_t b) const {
+        using namespace cpgh;
+        const HFr* p0 = pb.part + b; const HFr* p1 = pb.part + (size_t)sh.nch * pb.B + b;
+        if (kind == PR_PROD_FACT) {
+            HFr acc = fr_one();
+            for (uint32_t k = 0; k < sh.nch; k++) acc = fr_mul(acc, p0[(size_t)k * pb.B]);
+            pb.res[b].gprod = acc;
+            return;
+        }
+        HFr s0 = fr_zero(), s1 = fr_zero();
+        for (uint32_t k = 0; k < sh.nch; k++) { s0 = fr_add(s0, p0[(size_t)k * pb.B]); s1 = fr_add(s1, p1[(size_t)k * pb.B]); }
+        if (kind == PR_IPA_LR) { pb.red[b] = s0; pb.red[pb.B + b] = s1; return; }
+        // the last two entries of the blinder z make <r, d> + <z, c> = 0 and <r, z> = 0 (ipa.py:36-46)
+        const uint32_t n = sh.n;
+        FrVec r = pvec(sh, pb, (size_t)b, PV_X), zz = pvec(sh, pb, (size_t)b, PV_W2), c = pvec(sh, pb, (size_t)b, PV_C);
+        const HFr omega = s0, delta = s1;
         HFr inv_c = fr_inv(c[n - 2]);
         HFr t1 = fr_mul(r[n - 2], inv_c);
         HFr last_z = fr_mul(fr_sub(fr_mul(t1, omega), delta), fr_inv(fr_add(fr_neg(fr_mul(t1, c[n - 1])), r[n - 1])));
         HFr pen_z = fr_neg(fr_mul(inv_c, fr_add(fr_mul(last_z, c[n - 1]), omega)));
         zz[n - 2] = pen_z; zz[n - 1] = last_z;
-        zero_rows(sh, pb, b, 3, 0);
-        uint8_t* fD = frow(sh, pb, b, 0); uint8_t* fBc = frow(sh, pb, b, 1); uint8_t* fBd = frow(sh, pb, b, 2);
-        for (uint32_t i = 0; i < n; i++) {
-            HFr t = i < ell ? fr_sub(Bcoef[i], s.beta_gp_inv) : fr_add(Bcoef[i], s.alpha_gp);
-            fr_to_bytes(fD + 32 * (size_t)i, t);
-            fr_to_bytes(fBc + 32 * (size_t)i, r[i]);
-            fr_to_bytes(fBd + 32 * (size_t)i, fr_mul(zz[i], uvec[i]));
-        }
-        // keep r_c / r_d until alpha is known: stash them in wG / wGp (weights are initialised next round)
-        for (uint32_t i = 0; i < n; i++) { wG[i] = r[i]; wGp[i] = zz[i]; }
-        s.tr = tr;
-        return;
     }
-    const uint32_t R_IPA0 = 5, R_SS = 5 + lg, R_MSM_INIT = 6 + lg, R_MSM0 = 7 + lg, R_FIN = 7 + 2 * lg;
-    if (round >= R_IPA0 && round < R_SS) {              // IPA rounds                                   (ipa.py:100-151)
-        const uint32_t j = round - R_IPA0;
-        if (j == 0) {
-            tr.append_point("ipa_step1", outs + 48 * O.C);
-            tr.append_point("ipa_step1", outs + 48 * O.D);
-            tr.append_fr("ipa_step1", s.z);
-            tr.append_point("ipa_step1", outs + 48 * O.Bc);
-            tr.append_point("ipa_step1", outs + 48 * O.Bd);
-            s.alpha_ipa = tr.challenge("ipa_alpha");
-            s.beta_ipa = tr.challenge("ipa_beta");
-            for (uint32_t i = 0; i < n; i++) {          // c = r_c + alpha c ; d = r_d + alpha d ; weights reset
-                c[i] = fr_add(wG[i], fr_mul(s.alpha_ipa, c[i]));
-                d[i] = fr_add(wGp[i], fr_mul(s.alpha_ipa, d[i]));
-                wG[i] = fr_one(); wGp[i] = uvec[i];
-            }
-            s.len = n;
-        } else {                                        // absorb the previous round's L/R, fold
-            const uint8_t* pr = outs + 48 * (size_t)(O.ipa0 + 4 * (j - 1));
-            for (uint32_t k = 0; k < 4; k++) tr.append_point("ipa_loop", pr + 48 * k);
-            HFr gam = tr.challenge("ipa_gamma"), gam_inv = fr_inv(gam);
-            uint32_t m = s.len / 2;
-            for (uint32_t i = 0; i < m; i++) {
-                c[i] = fr_add(c[i], fr_mul(gam_inv, c[m + i]));
-                d[i] = fr_add(d[i], fr_mul(gam, d[m + i]));
-            }
-            for (uint32_t L = 0; L < n; L++) if ((L / m) & 1) { wG[L] = fr_mul(wG[L], gam); wGp[L] = fr_mul(wGp[L], gam_inv); }
-            s.len = m;
-        }
-        // outputs of this round: L_C, L_D, R_C, R_D over the leaves
-        const uint32_t len = s.len, m = len / 2;
-        zero_rows(sh, pb, b, 4, 0);
-        uint8_t* fLC = frow(sh, pb, b, 0); uint8_t* fLD = frow(sh, pb, b, 1); uint8_t* fRC = frow(sh, pb, b, 2); uint8_t* fRD = frow(sh, pb, b, 3);
-        for (uint32_t L = 0; L < n; L++) {
-            uint32_t i = L % m;
-            if ((L / m) & 1) {                          // leaf folds into the right half
-                fr_to_bytes(fLC + 32 * (size_t)L, fr_mul(c[i], wG[L]));          // MSM(G_R, c_L)
-                fr_to_bytes(fRD + 32 * (size_t)L, fr_mul(d[i], wGp[L]));         // MSM(G'_R, d_L)
-            } else {
-                fr_to_bytes(fRC + 32 * (size_t)L, fr_mul(c[m + i], wG[L]));      // MSM(G_L, c_R)
-                fr_to_bytes(fLD + 32 * (size_t)L, fr_mul(d[m + i], wGp[L]));     // MSM(G'_L, d_R)
-            }
-        }
-        fr_to_bytes(fLC + 32 * (size_t)n, fr_mul(s.beta_ipa, ip(c, d + m, m)));  // + H beta <c_L, d_R>
-        fr_to_bytes(fRC + 32 * (size_t)n, fr_mul(s.beta_ipa, ip(c + m, d, m)));  // + H beta <c_R, d_L>
-        s.tr = tr;
-        return;
+};
+// c[i] = prod_{q < i} fact[q], i < ell (cp/grand_prod.py:49-51, a sequential loop there): chunk products (ProveReduce1),
+// an exclusive scan of the nch chunk products by one thread per proof, then every chunk expands its own prefix.
+struct ProveScanTop {             // thread = proof
+    static constexpr const char* kName = "ProveScanTop";
+    PShape sh; PBuffers pb;
+    CPG_HD void operator()(uint64_t b) const {
+        HFr run = cpgh::fr_one();
+        for (uint32_t k = 0; k < sh.nch; k++) { HFr* p = pb.part + (size_t)k * pb.B + b; HFr v = *p; *p = run; run = cpgh::fr_mul(run, v); }
     }
-    if (round == R_SS) {                                // last IPA fold; R, S, cm_T, cm_U, cm_A, cm_B   (curdleproofs.py:92-102, same_scalar.py:39-44)
-        {
-            const uint8_t* pr = outs + 48 * (size_t)(O.ipa0 + 4 * (lg - 1));
-            for (uint32_t k = 0; k < 4; k++) tr.append_point("ipa_loop", pr + 48 * k);
-            HFr gam = tr.challenge("ipa_gamma"), gam_inv = fr_inv(gam);
-            c[0] = fr_add(c[0], fr_mul(gam_inv, c[1]));                           // c_final, d_final
-            d[0] = fr_add(d[0], fr_mul(gam, d[1]));
-        }
-        s.r_t = prand(pb, sh, b, RO.r_t); s.r_u = prand(pb, sh, b, RO.r_u);
-        s.r_a = prand(pb, sh, b, RO.r_a); s.r_b = prand(pb, sh, b, RO.r_b); s.r_k = prand(pb, sh, b, RO.r_k);
-        zero_rows(sh, pb, b, 10, 2);
-        // order: Rp Sp T1 T2 U1 U2 A1 A2 B1 B2 ; var rows: 0 R' = MSM(vec_R, a), 1 S' = MSM(vec_S, a); the
-        // commitments' k R', r_k R', k S', r_k S' are one scalar-mul each of those results (ProveCombine)
-        uint8_t *vR = vrow(sh, pb, b, 0), *vS = vrow(sh, pb, b, 1);
-        for (uint32_t i = 0; i < ell; i++) {
-            fr_to_bytes(vR + 32 * (size_t)i, a[i]);
-            cpgh::copy32(vS + 32 * (size_t)i, vR + 32 * (size_t)i);
-        }
-        const size_t iH = n, iGt = n + 1, iGu = n + 2;
-        fr_to_bytes(frow(sh, pb, b, 2) + 32 * iGt, s.r_t);      // cm_T = (G_t r_t, R' k + H r_t)
-        fr_to_bytes(frow(sh, pb, b, 3) + 32 * iH, s.r_t);
-        fr_to_bytes(frow(sh, pb, b, 4) + 32 * iGu, s.r_u);      // cm_U = (G_u r_u, S' k + H r_u)
-        fr_to_bytes(frow(sh, pb, b, 5) + 32 * iH, s.r_u);
-        fr_to_bytes(frow(sh, pb, b, 6) + 32 * iGt, s.r_a);      // cm_A = (G_t r_a, R' r_k + H r_a)
-        fr_to_bytes(frow(sh, pb, b, 7) + 32 * iH, s.r_a);
-        fr_to_bytes(frow(sh, pb, b, 8) + 32 * iGu, s.r_b);      // cm_B = (G_u r_b, S' r_k + H r_b)
-        fr_to_bytes(frow(sh, pb, b, 9) + 32 * iH, s.r_b);
-        s.tr = tr;
-        return;
+};
+struct ProveScanApply {           // thread = (chunk, proof)
+    static constexpr const char* kName = "ProveScanApply";
+    PShape sh; PBuffers pb;
+    CPG_HD void operator()(uint64_t t) const {
+        const size_t b = (size_t)(t % pb.B); const uint32_t k = (uint32_t)(t / pb.B);
+        FrVec fact = pvec(sh, pb, b, PV_FACT), c = pvec(sh, pb, b, PV_C);
+        HFr run = pb.part[(size_t)k * pb.B + b];
+        for (uint32_t i = k * sh.CH; i < (k + 1) * sh.CH && i < sh.ell; i++) { c[i] = run; run = cpgh::fr_mul(run, fact[i]); }
     }
-    if (round == R_MSM_INIT) {                          // SameScalar responses; A', B_a, B_t, B_u       (same_scalar.py:46-63, same_msm.py:73-77)
-        const uint32_t ss[10] = {O.Rp, O.Sp, O.T1, O.T2, O.U1, O.U2, O.A1, O.A2, O.B1, O.B2};
-        for (uint32_t k = 0; k < 10; k++) tr.append_point("sameexp_points", outs + 48 * (size_t)ss[k]);
-        HFr alpha = tr.challenge("same_scalar_alpha");
-        s.z_k = fr_add(s.r_k, fr_mul(s.k, alpha));
-        s.z_t = fr_add(s.r_a, fr_mul(s.r_t, alpha));
-        s.z_u = fr_add(s.r_b, fr_mul(s.r_u, alpha));
-        // x_wb = a_perm | a_bl | r_t r_u ; r = msm blinders (kept in w2 until alpha_msm is known)
-        for (uint32_t i = 0; i < ell + 2; i++) x[i] = aperm[i];
-        x[ell + 2] = s.r_t; x[ell + 3] = s.r_u;
-        for (uint32_t i = 0; i < n; i++) w2[i] = prand(pb, sh, b, RO.msm_r + i);
-        zero_rows(sh, pb, b, 4, 2);
-        // outputs: 0 A' 1 B_a 2 B_t 3 B_u ; var rows: 0 B_t (T) 1 B_u (U)
-        uint8_t *fAp = frow(sh, pb, b, 0), *fBa = frow(sh, pb, b, 1), *fBt = frow(sh, pb, b, 2), *fBu = frow(sh, pb, b, 3);
-        for (uint32_t i = 0; i < n; i++) fr_to_bytes(fAp + 32 * (size_t)i, Acoef[i]);
-        fr_to_bytes(fAp + 32 * (size_t)(n + 1), s.r_t);          // + cm_T.T_1 = G_t r_t
-        fr_to_bytes(fAp + 32 * (size_t)(n + 2), s.r_u);          // + cm_U.T_1 = G_u r_u
-        for (uint32_t L = 0; L < n; L++) fr_to_bytes(fBa + 32 * (size_t)gwb_index(sh, L), w2[L]);
-        uint8_t *vT = vrow(sh, pb, b, 0), *vU = vrow(sh, pb, b, 1);
-        for (uint32_t i = 0; i < ell; i++) { fr_to_bytes(vT + 32 * (size_t)i, w2[i]); cpgh::copy32(vU + 32 * (size_t)i, vT + 32 * (size_t)i); }
-        fr_to_bytes(fBt + 32 * (size_t)n, w2[ell + 2]);          // T_wb = vec_T | 0 0 H 0
-        fr_to_bytes(fBu + 32 * (size_t)n, w2[ell + 3]);          // U_wb = vec_U | 0 0 0 H
-        s.tr = tr;
-        return;
-    }
-    if (round >= R_MSM0 && round < R_FIN) {             // SameMSM rounds                                 (same_msm.py:79-131)
-        const uint32_t j = round - R_MSM0;
-        if (j == 0) {
-            tr.append_point("same_msm_step1", outs + 48 * O.Ap);
-            tr.append_point("same_msm_step1", outs + 48 * O.T2);
-            tr.append_point("same_msm_step1", outs + 48 * O.U2);
-            uint8_t INF[48]; memset(INF, 0, 48); INF[0] = 0xc0;
-            const uint8_t* Hb = pb.crs48 + 48 * (size_t)n;
-            const uint8_t* tu = pb.tu48 + b * (size_t)(2 * ell) * 48;
-            for (uint32_t i = 0; i < ell; i++) tr.append_point("same_msm_step1", tu + 48 * (size_t)i);
-            tr.append_point("same_msm_step1", INF); tr.append_point("same_msm_step1", INF);
-            tr.append_point("same_msm_step1", Hb); tr.append_point("same_msm_step1", INF);
-            for (uint32_t i = 0; i < ell; i++) tr.append_point("same_msm_step1", tu + 48 * (size_t)(ell + i));
-            tr.append_point("same_msm_step1", INF); tr.append_point("same_msm_step1", INF);
-            tr.append_point("same_msm_step1", INF); tr.append_point("same_msm_step1", Hb);
-            tr.append_point("same_msm_step1", outs + 48 * O.Ba);
-            tr.append_point("same_msm_step1", outs + 48 * O.Bt);
-            tr.append_point("same_msm_step1", outs + 48 * O.Bu);
-            s.alpha_msm = tr.challenge("same_msm_alpha");
-            for (uint32_t i = 0; i < n; i++) { x[i] = fr_add(w2[i], fr_mul(s.alpha_msm, x[i])); }
-            for (uint32_t i = 0; i < n; i++) w2[i] = fr_one();
-            s.len = n;
-        } else {
-            const uint8_t* pr = outs + 48 * (size_t)(O.msm0 + 6 * (j - 1));
-            for (uint32_t k = 0; k < 6; k++) tr.append_point("same_msm_loop", pr + 48 * k);
-            HFr gam = tr.challenge("same_msm_gamma"), gam_inv = fr_inv(gam);
-            uint32_t m = s.len / 2;
-            for (uint32_t i = 0; i < m; i++) x[i] = fr_add(x[i], fr_mul(gam_inv, x[m + i]));
-            for (uint32_t L = 0; L < n; L++) if ((L / m) & 1) w2[L] = fr_mul(w2[L], gam);
-            s.len = m;
-        }
-        const uint32_t len = s.len, m = len / 2;
-        zero_rows(sh, pb, b, 6, 4);
-        // outputs: 0 L_A 1 L_T 2 L_U 3 R_A 4 R_T 5 R_U ; var rows: 0 L_T (T) 1 L_U (U) 2 R_T (T) 3 R_U (U)
-        uint8_t *fLA = frow(sh, pb, b, 0), *fLT = frow(sh, pb, b, 1), *fLU = frow(sh, pb, b, 2), *fRA = frow(sh, pb, b, 3), *fRT = frow(sh, pb, b, 4), *fRU = frow(sh, pb, b, 5);
-        uint8_t *vLT = vrow(sh, pb, b, 0), *vLU = vrow(sh, pb, b, 1), *vRT = vrow(sh, pb, b, 2), *vRU = vrow(sh, pb, b, 3);
-        for (uint32_t L = 0; L < n; L++) {
-            uint32_t i = L % m;
-            bool right = ((L / m) & 1) != 0;
-            HFr coef = fr_mul(right ? x[i] : x[m + i], w2[L]);   // L_* = MSM(v[m:], x_L), R_* = MSM(v[:m], x_R)
-            uint8_t* fA = right ? fLA : fRA;
-            fr_to_bytes(fA + 32 * (size_t)gwb_index(sh, L), coef);
-            if (L < ell) {
-                uint8_t* vT = right ? vLT : vRT;
-                fr_to_bytes(vT + 32 * (size_t)L, coef);
-                cpgh::copy32((right ? vLU : vRU) + 32 * (size_t)L, vT + 32 * (size_t)L);
-            } else if (L == ell + 2) {
-                fr_to_bytes((right ? fLT : fRT) + 32 * (size_t)n, coef);          // H inside T_wb
-            } else if (L == ell + 3) {
-                fr_to_bytes((right ? fLU : fRU) + 32 * (size_t)n, coef);          // H inside U_wb
-            }
-        }
-        s.tr = tr;
-        return;
-    }
-    if (round == R_FIN) {                               // last SameMSM fold + wire assembly             (curdleproofs.py:275-285)
-        {
-            const uint8_t* pr = outs + 48 * (size_t)(O.msm0 + 6 * (lg - 1));
-            for (uint32_t k = 0; k < 6; k++) tr.append_point("same_msm_loop", pr + 48 * k);
-            HFr gam = tr.challenge("same_msm_gamma"), gam_inv = fr_inv(gam);
-            x[0] = fr_add(x[0], fr_mul(gam_inv, x[1]));                           // x_final
-        }
-        uint8_t* w = pb.proof + b * (size_t)(1088 + 480 * (size_t)lg);
-        auto pt = [&](uint32_t id) { memcpy(w, outs + 48 * (size_t)id, 48); w += 48; };
-        auto sc = [&](const HFr& v) { fr_to_bytes(w, v); w += 32; };
-        pt(O.A); pt(O.T1); pt(O.T2); pt(O.U1); pt(O.U2); pt(O.Rp); pt(O.Sp);
-        pt(O.B); pt(O.C); sc(s.r_p);
-        pt(O.Bc); pt(O.Bd);
-        for (uint32_t k = 0; k < 4; k++) {               // L_C[], R_C[], L_D[], R_D[]  (ipa.py:260-270)
-            const uint32_t sel[4] = {0, 2, 1, 3};        // stored per round as L_C, L_D, R_C, R_D
-            for (uint32_t j = 0; j < lg; j++) pt(O.ipa0 + 4 * j + sel[k]);
-        }
-        sc(c[0]); sc(d[0]);
-        pt(O.A1); pt(O.A2); pt(O.B1); pt(O.B2); sc(s.z_k); sc(s.z_t); sc(s.z_u);
-        pt(O.Ba); pt(O.Bt); pt(O.Bu);
-        for (uint32_t k = 0; k < 6; k++) for (uint32_t j = 0; j < lg; j++) pt(O.msm0 + 6 * j + k);   // L_A L_T L_U R_A R_T R_U
-        sc(x[0]);
-        s.tr = tr;
-        return;
-    }
-}
-
-struct ProveStep {                // thread = proof
-    static constexpr const char* kName = "ProveStep";
-    PShape sh; POut O; PBuffers pb; uint32_t round;
-    CPG_HD void operator()(uint64_t b) const { prove_step(sh, O, pb, round, (size_t)b); }
 };
 
 // T_j = k R_perm[j], U_j = k S_perm[j]: thread = (proof, j in [0, 2 ell))            (curdleproofs.py:310-314)
@@ -476,7 +557,7 @@ struct VarOffsets {
 
 // One lane = the device buffers of a contiguous sub-batch.  A batch is split over `nlanes` lanes whose
 // rounds are issued alternately on separate streams, so the latency-bound per-proof kernels of one lane
-// (ProveStep: one thread per proof, 32 warps for 4096 proofs) run under the MSM kernels of the other.
+// (ProveTranscript: one thread per proof, 32 warps for 4096 proofs) run under the MSM kernels of the other.
 // k = k1 + k2 lambda as integers, lambda = 0xac45a4010001a40200000000ffffffff (g1.cuh::jac_mul_glv); out = k1[4] | k2[4]
 // returns false (and splits 0) when k is not a canonical scalar (k >= r): k2 would not fit 128 bits
 bool glv_split(const uint8_t* k32, uint32_t* out) {
@@ -503,7 +584,11 @@ constexpr size_t TAB_CHUNK = 148 * 3 * 128 * 2;   // bases per VarTableBuild lau
 struct ProverLane {
     size_t cap = 0, B = 0;
     uint8_t *d_in48 = nullptr, *d_tu48 = nullptr, *d_k = nullptr, *d_rand = nullptr, *d_outs = nullptr, *d_fs = nullptr, *d_vs = nullptr, *d_proof = nullptr, *d_err = nullptr;
-    uint32_t *d_perm = nullptr, *d_off = nullptr; Aff* d_bases = nullptr; PState* d_st = nullptr; HFr* d_vec = nullptr; Jac *d_fix = nullptr, *d_var = nullptr;
+    uint32_t *d_perm = nullptr, *d_off = nullptr; Aff* d_bases = nullptr; HFr* d_vec = nullptr; Jac *d_fix = nullptr, *d_var = nullptr;
+    PTr* d_trs = nullptr; PChal* d_chal = nullptr; PRes* d_res = nullptr; HFr *d_achal = nullptr, *d_part = nullptr, *d_red = nullptr;
+    // host mirrors for the transcript on host threads (few, large proofs): pinned, exchanged once per round
+    PChal* h_chal = nullptr; PRes* h_res = nullptr; HFr* h_achal = nullptr; std::vector<PTr> h_trs; std::vector<uint8_t> h_k;
+    bool host_transcript = false;
     uint8_t *h_tu = nullptr, *h_outs = nullptr, *h_proof = nullptr, *h_err = nullptr;   // pinned: results leave per lane
     uint8_t *h_in = nullptr, *h_rand = nullptr;   // pinned staging of the two large inputs (pageable caller memory copies at a third of the rate)
     uint32_t* d_k12 = nullptr;    // [B][8] GLV halves of k
@@ -512,12 +597,15 @@ struct ProverLane {
 #ifndef CPG_HOST_EMU
     cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
 #endif
-    std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_off, d_bases, d_st, d_vec, d_fix, d_var, d_tab, d_tab_jac, d_tab_pz, d_k12}; }
+    std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_off, d_bases, d_vec, d_fix, d_var, d_tab, d_tab_jac, d_tab_pz, d_k12,
+                                        d_trs, d_chal, d_res, d_achal, d_part, d_red}; }
     void release() {
         for (void* q : all()) cpg_free(q);
         cpg_host_free(h_tu); cpg_host_free(h_outs); cpg_host_free(h_proof); cpg_host_free(h_err); cpg_host_free(h_in); cpg_host_free(h_rand);
+        cpg_host_free(h_chal); cpg_host_free(h_res); cpg_host_free(h_achal);
+        h_chal = nullptr; h_res = nullptr; h_achal = nullptr; d_trs = nullptr; d_chal = nullptr; d_res = nullptr; d_achal = d_part = d_red = nullptr;
         h_tu = h_outs = h_proof = h_err = h_in = h_rand = nullptr;
-        d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = d_off = nullptr; d_bases = nullptr; d_st = nullptr; d_vec = nullptr; d_fix = d_var = nullptr; d_tab = nullptr; d_tab_jac = nullptr; d_tab_pz = nullptr; d_k12 = nullptr;
+        d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = d_off = nullptr; d_bases = nullptr; d_vec = nullptr; d_fix = d_var = nullptr; d_tab = nullptr; d_tab_jac = nullptr; d_tab_pz = nullptr; d_k12 = nullptr;
         cap = 0;
     }
     int reserve(const PShape& sh, size_t proof_len, size_t Bn, uint32_t NOUT, uint32_t ts) {
@@ -535,14 +623,21 @@ struct ProverLane {
         d_vs = (uint8_t*)cpg_malloc(Bn * P_MAX_VAR * ell * 32); d_proof = (uint8_t*)cpg_malloc(Bn * proof_len);
         d_err = (uint8_t*)cpg_malloc(Bn * 2 * ell);           d_perm = (uint32_t*)cpg_malloc(Bn * ell * 4);
         d_off = (uint32_t*)cpg_malloc(Bn * P_MAX_VAR * 4);
-        d_bases = (Aff*)cpg_malloc(sizeof(Aff) * Bn * 4 * ell); d_st = (PState*)cpg_malloc(sizeof(PState) * Bn);
+        d_bases = (Aff*)cpg_malloc(sizeof(Aff) * Bn * 4 * ell);
+        d_trs = (PTr*)cpg_malloc(sizeof(PTr) * Bn);           d_chal = (PChal*)cpg_malloc(sizeof(PChal) * Bn);
+        d_res = (PRes*)cpg_malloc(sizeof(PRes) * Bn);         d_achal = (HFr*)cpg_malloc(sizeof(HFr) * Bn * ell);
+        d_part = (HFr*)cpg_malloc(sizeof(HFr) * Bn * 2 * sh.nch); d_red = (HFr*)cpg_malloc(sizeof(HFr) * Bn * 2);
+        h_chal = (PChal*)cpg_host_alloc(sizeof(PChal) * Bn); h_res = (PRes*)cpg_host_alloc(sizeof(PRes) * Bn);
+        h_achal = (HFr*)cpg_host_alloc(sizeof(HFr) * Bn * ell);
+        if (h_chal) memset(h_chal, 0, sizeof(PChal) * Bn);
+        h_trs.assign(Bn, PTr());
         d_vec = (HFr*)cpg_malloc(sizeof(HFr) * Bn * PV_COUNT * n);
         d_fix = (Jac*)cpg_malloc(sizeof(Jac) * Bn * P_MAX_OUT); d_var = (Jac*)cpg_malloc(sizeof(Jac) * Bn * P_MAX_VAR);
         h_tu = (uint8_t*)cpg_host_alloc(Bn * 2 * ell * 48); h_outs = (uint8_t*)cpg_host_alloc(Bn * NOUT * 48);
         h_proof = (uint8_t*)cpg_host_alloc(Bn * proof_len);   h_err = (uint8_t*)cpg_host_alloc(Bn * 2 * ell);
         h_in = (uint8_t*)cpg_host_alloc(Bn * 2 * ell * 48);   h_rand = (uint8_t*)cpg_host_alloc(Bn * sh.NR * 32);
         for (void* q : all()) if (!q) { release(); return fail("cpg_prove_batch: device allocation failed"); }
-        if (!h_tu || !h_outs || !h_proof || !h_err || !h_in || !h_rand) { release(); return fail("cpg_prove_batch: pinned host allocation failed"); }
+        if (!h_tu || !h_outs || !h_proof || !h_err || !h_in || !h_rand || !h_chal || !h_res || !h_achal) { release(); return fail("cpg_prove_batch: pinned host allocation failed"); }
         cap = Bn;
         return 0;
     }
@@ -558,6 +653,11 @@ struct Prover {
     int var_window = 0;
     int table_window = 6;         // per-base tables of 2^(c-1) multiples for the T / U MSMs (0: bucket method for those too)
     int nlanes = 2, lastK = 1;
+    int transcript_mode = 2;      // 0 host threads, 1 one GPU thread per proof, 2 by batch size (cpg_prover_set_transcript)
+    int threads = 1;
+    // A CPU core runs a proof's Keccak chain ~20x faster than a lone GPU thread, the GPU runs thousands of chains at
+    // once: the host takes the transcript while a lane holds fewer proofs than ~16 per host thread.
+    bool host_transcript_for(size_t B) const { return transcript_mode == 0 || (transcript_mode == 2 && B <= 16 * (size_t)threads); }
     size_t lane_min = 256;        // proofs per lane below which a batch is not split
     size_t lastB = 0;
     ProverLane lanes[P_MAX_LANES];
@@ -609,7 +709,9 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
     const size_t B = p.B;
     PBuffers pb;
     pb.in48 = p.d_in48; pb.tu48 = p.d_tu48; pb.perm = p.d_perm; pb.kbytes = p.d_k; pb.rand = p.d_rand; pb.crs48 = pr.d_crs48;
-    pb.st = p.d_st; pb.vec = p.d_vec; pb.outs48 = p.d_outs; pb.fs = p.d_fs; pb.vs = p.d_vs; pb.proof = p.d_proof; pb.B = B;
+    pb.trs = p.d_trs; pb.chal = p.d_chal; pb.res = p.d_res; pb.achal = p.d_achal; pb.part = p.d_part; pb.red = p.d_red;
+    pb.vec = p.d_vec; pb.outs48 = p.d_outs; pb.fs = p.d_fs; pb.vs = p.d_vs; pb.proof = p.d_proof; pb.B = B;
+    const PRounds RD(lg);
 
     // per round: (first output id, count) and which outputs carry a variable-base part over which vector
     struct RoundPlan { uint32_t nout; uint32_t ids[P_MAX_OUT]; int32_t var_row[P_MAX_OUT]; uint32_t nvar; uint32_t var_set[P_MAX_VAR]; int scale_kind[P_MAX_OUT]; };
@@ -634,9 +736,53 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
         else if (r < 7 + 2 * lg) { uint32_t base = O.msm0 + 6 * (r - 7 - lg); add(base, -1); add(base + 1, 2); add(base + 2, 3); add(base + 3, -1); add(base + 4, 2); add(base + 5, 3); }
         return pl;
     };
+    // ---- transcript step: absorb the previous round's outputs, squeeze this round's challenges ----
+    if (r > 0) {
+        if (p.host_transcript) {
+            // the previous round's compressed outputs and scalars come to the host, the challenges go back
+            if (int rc = d2h_async(p.h_outs, p.d_outs, B * (size_t)O.NOUT * 48)) return rc;
+            if (int rc = d2h_async(p.h_res, p.d_res, B * sizeof(PRes))) return rc;
+            if (r == 1) if (int rc = d2h_async(p.h_tu, p.d_tu48, B * 2 * (size_t)ell * 48)) return rc;
+            if (int rc = cpg_sync()) return rc;
+            PTBuf pt;
+            pt.in48 = p.h_in; pt.tu48 = p.h_tu; pt.kbytes = p.h_k.data(); pt.rand = p.h_rand; pt.crs48 = pr.crs48.data(); pt.outs48 = p.h_outs;
+            pt.trs = p.h_trs.data(); pt.chal = p.h_chal; pt.res = p.h_res; pt.achal = p.h_achal; pt.proof = p.h_proof;
+            parallel_for(pr.threads, B, [&](size_t b) { prove_transcript(sh, O, pt, r, b); });
+            if (int rc = cpg_h2d(p.d_chal, p.h_chal, B * sizeof(PChal))) return rc;
+            if (r == 1) if (int rc = cpg_h2d(p.d_achal, p.h_achal, B * (size_t)ell * sizeof(HFr))) return rc;
+        } else {
+            PTBuf pt;
+            pt.in48 = p.d_in48; pt.tu48 = p.d_tu48; pt.kbytes = p.d_k; pt.rand = p.d_rand; pt.crs48 = pr.d_crs48; pt.outs48 = p.d_outs;
+            pt.trs = p.d_trs; pt.chal = p.d_chal; pt.res = p.d_res; pt.achal = p.d_achal; pt.proof = p.d_proof;
+            if (int rc = launch<64>(ProveTranscript{sh, O, pt, r}, B)) return rc;
+        }
+    }
+    if (r == RD.FIN) return 0;
+    // ---- vector kernels: this round's Fr vector work and coefficient rows, one thread per (proof, element) ----
     {
-        if (int rc = launch<64>(ProveStep{sh, O, pb, r}, B)) return rc;
-        if (r == 7 + 2 * lg) return 0;
+        auto V = [&](uint32_t phase) { return launch(ProveVec{sh, pb, r, phase}, (uint64_t)sh.NF * B); };
+        auto R1 = [&](uint32_t kind, uint32_t m) { return launch(ProveReduce1{sh, pb, kind, m}, (uint64_t)sh.nch * B); };
+        auto R2 = [&](uint32_t kind) { return launch(ProveReduce2{sh, pb, kind}, B); };
+        int rc = 0;
+        if (r == 2) { rc = V(0); if (!rc) rc = R1(PR_PROD_FACT, 0); if (!rc) rc = R2(PR_PROD_FACT); }
+        else if (r == 3) {
+            rc = R1(PR_PROD_FACT, 0);
+            if (!rc) rc = launch(ProveScanTop{sh, pb}, B);
+            if (!rc) rc = launch(ProveScanApply{sh, pb}, (uint64_t)sh.nch * B);
+            if (!rc) rc = V(0);
+        }
+        else if (r == 4) { rc = V(0); if (!rc) rc = R1(PR_IPA_BLIND, 0); if (!rc) rc = R2(PR_IPA_BLIND); if (!rc) rc = V(1); }
+        else if (r >= RD.IPA0 && r < RD.SS) {
+            rc = V(0);
+            if (!rc) rc = R1(PR_IPA_LR, (sh.n >> (r - RD.IPA0)) / 2);
+            if (!rc) rc = R2(PR_IPA_LR);
+            if (!rc) rc = V(1);
+        }
+        else if (r >= RD.MSM0) { rc = V(0); if (!rc) rc = V(1); }
+        else rc = V(0);
+        if (rc) return rc;
+    }
+    {
         RoundPlan pl = plan_for(r);
         // fixed-base part of every output of the round: B*nout MSMs over the CRS table (rows are output-major)
         if (int rc = cpg_g1_msm_fixed_batched(pr.table, p.d_fs, B * pl.nout, 0, p.d_fix)) return rc;
@@ -700,7 +846,7 @@ int prove_device_all(Prover& p, int k, bool download = false) {
             enter(i);
             rc = d2h_async(L.h_tu, L.d_tu48, L.B * 2 * (size_t)p.sh.ell * 48);
             if (!rc) rc = d2h_async(L.h_outs, L.d_outs, L.B * (size_t)O.NOUT * 48);
-            if (!rc) rc = d2h_async(L.h_proof, L.d_proof, L.B * p.proof_len);
+            if (!rc && !L.host_transcript) rc = d2h_async(L.h_proof, L.d_proof, L.B * p.proof_len);   // (host transcript: assembled in place)
             if (!rc) rc = d2h_async(L.h_err, L.d_err, L.B * 2 * (size_t)p.sh.ell);
         }
     leave();
@@ -726,6 +872,9 @@ void* cpg_prover_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders,
     Prover* p = new Prover;
     p->sh.ell = (uint32_t)ell; p->sh.n = (uint32_t)n; p->sh.lg = lg; p->sh.NF = (uint32_t)n + 3;
     p->sh.NR = PRand((uint32_t)n).NR; p->sh.rounds = 8 + 2 * lg;
+    p->sh.CH = 16; while ((size_t)p->sh.CH * p->sh.CH < n) p->sh.CH *= 2;      // ~sqrt(n): both passes of a reduction stay short
+    p->sh.nch = (uint32_t)((n + p->sh.CH - 1) / p->sh.CH);
+    p->threads = (int)std::max(1u, std::thread::hardware_concurrency());
     p->proof_len = 1088 + 480 * (size_t)lg;
     p->crs48.assign(crs_bytes, crs_bytes + 48 * (n + 5));
     p->d_crs48 = (uint8_t*)cpg_malloc(48 * (n + 5));
@@ -780,6 +929,12 @@ int cpg_prover_set_table_window(void* handle, int window) {
     ((Prover*)handle)->table_window = window == 1 ? 0 : window;
     return 0;
 }
+int cpg_prover_set_transcript(void* handle, int mode) {
+    if (!handle) return fail("cpg_prover_set_transcript: null prover");
+    if (mode < 0 || mode > 2) return fail("cpg_prover_set_transcript: 0 (host threads), 1 (GPU thread per proof) or 2 (by batch size)");
+    ((Prover*)handle)->transcript_mode = mode;
+    return 0;
+}
 int cpg_prover_set_lanes(void* handle, int nlanes, size_t min_proofs_per_lane) {
     if (!handle) return fail("cpg_prover_set_lanes: null prover");
     if (nlanes < 1 || nlanes > P_MAX_LANES) return fail("cpg_prover_set_lanes: 1..4 lanes");
@@ -832,6 +987,8 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
         // (msm, window), so large shuffles keep the bucket method
         if (int rc = L.reserve(sh, p.proof_len, c, O.NOUT, (p.table_window > 0 && ell <= 2048) ? 1u << (p.table_window - 1) : 0)) return rc;
         L.B = c;
+        L.host_transcript = p.host_transcript_for(c);
+        L.h_k.assign(ks + f * 32, ks + (f + c) * 32);
         // the two large inputs go through pinned staging, copied by all host threads
         const size_t in_row = 2 * (size_t)ell * 48, rand_row = (size_t)sh.NR * 32;
         parallel_for(threads, c, [&](size_t j) {

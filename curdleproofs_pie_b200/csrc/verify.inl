@@ -453,7 +453,10 @@ struct Verifier {
     uint32_t nbl;
     size_t proof_len;             // 48 (M) + 1088 + 480 lg
     int threads;
-    int transcript_on_device = 1;
+    int transcript_mode = 2;      // 0 host threads, 1 one GPU thread per proof, 2 by batch size (cpg_verifier_set_transcript)
+    int transcript_on_device = 1; // placement of the batch in flight (begin of cpg_verify_batch)
+    // A CPU core runs one proof's Keccak chain ~20x faster than a lone GPU thread; the GPU runs thousands at once.
+    bool device_transcript_for(size_t B) const { return transcript_mode == 1 || (transcript_mode == 2 && B > 16 * (size_t)threads); }
     std::vector<uint8_t> crs48;   // vec_G | vec_H | H | G_t | G_u | G_sum | H_sum  (n + 5 points)
     Aff* d_crs = nullptr;         // n + 5 affine points
     uint8_t* d_crs48 = nullptr;   // the same as wire bytes (device transcript appends H)
@@ -786,7 +789,12 @@ int cpg_verifier_set_group(void* handle, int group, int group_window) {
 }
 int cpg_verifier_group(const void* handle) { return handle ? (int)((const Verifier*)handle)->group : 0; }
 size_t cpg_verifier_rechecked(const void* handle) { return handle ? ((const Verifier*)handle)->rechecked : 0; }
-int cpg_verifier_set_transcript(void* handle, int on_device) { if (!handle) return 1; ((Verifier*)handle)->transcript_on_device = on_device ? 1 : 0; return 0; }
+int cpg_verifier_set_transcript(void* handle, int mode) {
+    if (!handle) return fail("cpg_verifier_set_transcript: null verifier");
+    if (mode < 0 || mode > 2) return fail("cpg_verifier_set_transcript: 0 (host threads), 1 (GPU thread per proof) or 2 (by batch size)");
+    ((Verifier*)handle)->transcript_mode = mode;
+    return 0;
+}
 
 /* inputs : [B][4*ell*48]   vec_R | vec_S | vec_T | vec_U   (tracker halves, whisk_interface.py:96-100)
  * proofs : [B][proof_len]  M | proof                        (WhiskShuffleProof.to_bytes, :57-61)
@@ -802,6 +810,7 @@ int cpg_verify_batch(void* handle, const uint8_t* inputs, const uint8_t* proofs,
     const size_t in_len = (size_t)(NI - 1) * 48;
     if (int rc = v.reserve(B)) return rc;
     v.lastB = B;
+    v.transcript_on_device = v.device_transcript_for(B) ? 1 : 0;
 
     // ---- stage wire points contiguously per proof: R|S|T|U|M|proof points|(slot for D) ----
     uint8_t* wire = v.h_wire;

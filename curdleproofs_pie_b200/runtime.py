@@ -106,6 +106,7 @@ _SIGS = {
     "cpg_prover_set_window": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "cpg_pyrandom_draw_shuffles": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "cpg_prover_set_table_window": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "cpg_prover_set_transcript": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "cpg_prover_set_lanes": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_size_t]),
     "cpg_prove_replay_device": (_c.c_int, [_c.c_void_p]),
     "cpg_prove_batch": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_char_p, _c.c_char_p, _c.c_size_t, _c.c_char_p, _c.c_char_p, _c.c_char_p]),

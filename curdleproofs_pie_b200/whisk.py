@@ -34,9 +34,11 @@ class BatchVerifier:
     def set_window(self, c):
         self.lib.check(self.lib.c.cpg_verifier_set_window(self.handle, int(c)), "cpg_verifier_set_window")
 
-    def set_transcript(self, on_device):
-        """True: transcript + coefficients per proof on the GPU (default); False: on host threads."""
-        self.lib.check(self.lib.c.cpg_verifier_set_transcript(self.handle, 1 if on_device else 0), "cpg_verifier_set_transcript")
+    def set_transcript(self, mode):
+        """True / "device": transcript + coefficients per proof on the GPU; False / "host": on host threads;
+        "auto" (the default): by batch size."""
+        mode = {"host": 0, "device": 1, "auto": 2, True: 1, False: 0}.get(mode, mode)
+        self.lib.check(self.lib.c.cpg_verifier_set_transcript(self.handle, int(mode)), "cpg_verifier_set_transcript")
 
     def set_streams(self, n):
         self.lib.check(self.lib.c.cpg_verifier_set_streams(self.handle, int(n)), "cpg_verifier_set_streams")
@@ -144,6 +146,11 @@ class BatchProver:
 
     def set_table_window(self, c):
         self.lib.check(self.lib.c.cpg_prover_set_table_window(self.handle, int(c)), "cpg_prover_set_table_window")
+
+    def set_transcript(self, mode):
+        """0 / "host": Fiat-Shamir on host threads; 1 / "device": one GPU thread per proof; 2 / "auto": by batch size"""
+        mode = {"host": 0, "device": 1, "auto": 2}.get(mode, mode)
+        self.lib.check(self.lib.c.cpg_prover_set_transcript(self.handle, int(mode)), "cpg_prover_set_transcript")
 
     def set_lanes(self, k, min_proofs_per_lane=0):
         self.lib.check(self.lib.c.cpg_prover_set_lanes(self.handle, int(k), int(min_proofs_per_lane)), "cpg_prover_set_lanes")

@@ -181,9 +181,11 @@ int cpg_verifier_free(void* verifier);
 size_t cpg_verifier_proof_bytes(const void* verifier);
 size_t cpg_verifier_input_bytes(const void* verifier);
 int cpg_verifier_set_window(void* verifier, int var_window);
-/* where the Fiat-Shamir transcript + coefficient algebra run: 1 = one proof per GPU thread (default;
- * only wire bytes cross PCIe), 0 = on `host_threads` host threads (the reference's placement) */
-int cpg_verifier_set_transcript(void* verifier, int on_device);
+/* where the Fiat-Shamir transcript + coefficient algebra run: 1 = one proof per GPU thread (only wire bytes cross
+ * PCIe: right for thousands of proofs), 0 = on `host_threads` host threads (the reference's placement: right for a
+ * few, or large, proofs - a CPU core runs the sequential Keccak chain ~20x faster than one GPU thread),
+ * 2 (default) = by batch size */
+int cpg_verifier_set_transcript(void* verifier, int mode);
 /* sub-batches in flight on separate CUDA streams (1..8, default 4; device transcript only); the host stages the wire
  * bytes of sub-batch k + 1 while the GPU works on sub-batch k */
 int cpg_verifier_set_streams(void* verifier, int nstreams);
@@ -232,6 +234,11 @@ int cpg_prover_set_table_window(void* prover, int window);
 /* sub-batches ("lanes", 1..4, default 2) whose rounds are issued alternately on separate streams: the
  * one-thread-per-proof transcript kernels of one lane run under the MSM kernels of the other */
 int cpg_prover_set_lanes(void* prover, int nlanes, size_t min_proofs_per_lane /* 0 = 256: smaller batches are not split */);
+/* where a proof's Fiat-Shamir transcript runs (its Fr vector work is always GPU kernels, one thread per element):
+ * 0 = host threads (the reference's placement; right for a few large proofs: a CPU core runs the sequential Keccak
+ * chain ~20x faster than one GPU thread), 1 = one GPU thread per proof (right for thousands of proofs: nothing
+ * crosses PCIe between rounds), 2 (default) = by batch size */
+int cpg_prover_set_transcript(void* prover, int mode);
 int cpg_prove_replay_device(void* prover);   /* device side of the last batch again, inputs resident */
 int cpg_prove_batch(void* prover, const uint8_t* inputs, const uint32_t* perms, const uint8_t* ks, const uint8_t* rand,
                     size_t B, uint8_t* out_tu, uint8_t* out_proofs, uint8_t* status);

@@ -136,9 +136,11 @@ def case_msm(lib, cref, B, n, window=0, shared=False, seed=4, edge=False):
     assert got == want, (B, n, window, shared)
 
 
-def case_fixed(lib, cref, B, nb, window, seed=5):
+def case_fixed(lib, cref, B, nb, window, seed=5, with_identity=False):
+    """with_identity: the base vector also holds the identity - its whole table row is identities, which the shared
+    inversions of the table build (Montgomery's trick per base / per 64-entry segment) must skip"""
     rng = random.Random(seed)
-    blobs, enc = rand_points(cref, rng, nb)
+    blobs, enc = rand_points(cref, rng, nb, with_identity=with_identity)
     aff, _ = upload_points(lib, enc)
     table = lib.fixed_table(aff, nb, window)
     assert table.nbytes > 0

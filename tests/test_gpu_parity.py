@@ -60,6 +60,8 @@ def test_fixed_base(gpu_lib, cref):
     pc.case_fixed(gpu_lib, cref, 8, 131, 8)
     pc.case_fixed(gpu_lib, cref, 3, 5, 4)
     pc.case_fixed(gpu_lib, cref, 2, 1300, 5)      # few MSMs over many bases: the bases are split over threads (one large proof)
+    pc.case_fixed(gpu_lib, cref, 4, 9, 12, with_identity=True)     # 2048-entry rows: 32 segments per row, identity rows skipped
+    pc.case_fixed(gpu_lib, cref, 2, 3, 16)                         # the bench's table window
 
 
 def test_fr(gpu_lib):

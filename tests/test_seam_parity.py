@@ -50,6 +50,10 @@ def test_msm_empty(seam_lib, cref):
 
 def test_fixed_base(seam_lib, cref):
     pc.case_fixed(seam_lib, cref, 2, 5, 4)
+    # rows longer than one 64-entry segment (NB = 128 / 256: 2 / 4 segments, each with its own shared inversion),
+    # and an identity base whose rows are all identities
+    pc.case_fixed(seam_lib, cref, 2, 3, 8, with_identity=True)
+    pc.case_fixed(seam_lib, cref, 1, 2, 9)
 
 
 def test_fr(seam_lib):

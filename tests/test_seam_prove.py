@@ -3,12 +3,22 @@ proof bytes against the reference's golden fixtures."""
 import prove_cases as pc
 
 
-def test_prove_bytes_N8(seam_lib):
-    pc.check_prove(seam_lib, "shuffle_N8_seed1234.json", fixed_window=4)
+import pytest
 
 
-def test_prove_bytes_N16_two_lanes(seam_lib):
-    pc.check_prove(seam_lib, "shuffle_N16_seed77.json", copies=2, fixed_window=5, window=3)
+@pytest.mark.parametrize("transcript", ["host", "device"])
+def test_prove_bytes_N8(seam_lib, transcript):
+    pc.check_prove(seam_lib, "shuffle_N8_seed1234.json", fixed_window=4, transcript=transcript)
+
+
+@pytest.mark.parametrize("transcript", ["host", "device"])
+def test_prove_bytes_N16_two_lanes(seam_lib, transcript):
+    pc.check_prove(seam_lib, "shuffle_N16_seed77.json", copies=2, fixed_window=5, window=3, transcript=transcript)
+
+
+def test_prove_bytes_N64_chunked_reductions(seam_lib):
+    """n = 64: the two-pass sums / prefix products run over 4 chunks of 16 (n <= 16 has a single chunk)"""
+    pc.check_prove(seam_lib, "shuffle_N64_seed2024.json", fixed_window=4, transcript="device")
 
 
 def test_prove_then_verify_N8(seam_lib):
