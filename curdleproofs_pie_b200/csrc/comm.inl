@@ -77,6 +77,31 @@ void comm_block(size_t total, int rank, int world, size_t* lo, size_t* hi) {
     *hi = *lo + base + (r < extra ? 1 : 0);
 }
 
+// How ONE proof is split over the ranks (BASELINE config 5): every rank holds the whole proof's inputs and runs the
+// (cheap, deterministic) transcript and Fr vector work in full, but evaluates each round's MSMs only over ITS block of
+// the leaves - CRS bases through a fixed-base table of that block only, trackers / proof points through the bucket
+// method - and one all-gather per round exchanges the partial sums (<= 16 Jacobian points per proof).
+// `virt`: all ranks' blocks are evaluated one after the other in THIS process - the CPU test tier's stand-in for the
+// communicator (CPG_TEST_VIRTUAL_RANKS=k, honoured only while no communicator exists); the block logic and the
+// summation are the product's own.
+struct Shard {
+    int world = 1, rank = 0; bool virt = false;
+    bool on() const { return world > 1; }
+    int first() const { return virt ? 0 : rank; }
+    int last() const { return virt ? world : rank + 1; }
+};
+Shard shard_now() {
+    Shard s;
+    if (g_comm_world > 1) { s.world = g_comm_world; s.rank = g_comm_rank; return s; }
+    if (const char* e = getenv("CPG_TEST_VIRTUAL_RANKS")) { int k = atoi(e); if (k > 1 && k <= 64) { s.world = k; s.virt = true; } }
+    return s;
+}
+// gather = [world][cnt] partial sums, this rank's block already in place; afterwards every block is (in-place all-gather)
+int shard_exchange(const Shard& sd, Jac* gather, size_t cnt) {
+    if (!sd.on() || sd.virt) return 0;
+    return comm_allgather(gather + (size_t)sd.rank * cnt, gather, cnt * sizeof(Jac));
+}
+
 }  // namespace
 
 extern "C" {

@@ -151,6 +151,9 @@ struct ProfRec { const char* name; cudaEvent_t a, b; uint64_t threads; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 std::mutex g_prof_mu;
+// work counters of the table-lookup MSMs, gathered only while profiling: (term, window) pairs with a non-zero
+// coefficient = mixed additions FixedMsmWindow / VarTableMsmWindow really perform (they skip zero coefficients)
+unsigned long long* g_d_counters = nullptr;   // [0] fixed-base, [1] per-base tracker tables
 
 template <int BLOCK = 128, int MINB = 1, class F>
 int launch(const F& f, uint64_t n) {
@@ -503,6 +506,8 @@ int cpg_profile_reset(void) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
     for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     g_prof.clear();
+    if (!g_d_counters) cudaMalloc(&g_d_counters, 2 * sizeof(unsigned long long));
+    if (g_d_counters) cudaMemset(g_d_counters, 0, 2 * sizeof(unsigned long long));
 #endif
     return 0;
 }
@@ -524,6 +529,13 @@ int cpg_profile_report(char* buf, size_t cap) {
         agg[i].ms += ms; agg[i].launches++; agg[i].threads += r.threads;
     }
     std::string out = "{";
+    if (g_d_counters) {
+        unsigned long long c[2] = {0, 0};
+        cudaMemcpy(c, g_d_counters, sizeof c, cudaMemcpyDeviceToHost);
+        char line[160];
+        snprintf(line, sizeof line, "\"_counters\": {\"fixed_msm_terms\": %llu, \"var_table_msm_terms\": %llu}%s", c[0], c[1], agg.empty() ? "" : ", ");
+        out += line;
+    }
     for (size_t i = 0; i < agg.size(); i++) {
         char line[256];
         snprintf(line, sizeof line, "%s\"%s\": {\"ms\": %.6f, \"launches\": %llu, \"threads\": %llu}", i ? ", " : "",
@@ -613,7 +625,7 @@ int cpg_g1_fold(const void* L, const void* R, const uint8_t* x, size_t rows, siz
 
 /* ---- batched Pippenger ---- */
 static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint32_t* d_base_off, const uint8_t* d_scalars,
-                            size_t B, size_t n, int window, void* d_out, uint32_t w0 = 0, uint32_t wn = 0);
+                            size_t B, size_t n, int window, void* d_out, uint32_t w0 = 0, uint32_t wn = 0, size_t sc_stride = 0, size_t sc_off = 0);
 int cpg_g1_msm_batched(const void* d_bases, size_t base_stride, const uint8_t* d_scalars,
                        size_t B, size_t n, int window, void* d_out) {
     return msm_batched_impl(d_bases, base_stride, nullptr, d_scalars, B, n, window, d_out);
@@ -658,8 +670,9 @@ int cpg_g1_msm_combine_windows(const void* d_wsums_jac, int window, void* d_out_
     return launch_horner_jac(HornerJac{windows_for((uint32_t)window), (uint32_t)window, (const Jac*)d_wsums_jac, (Jac*)d_out_jac}, 1);
 }
 // wn = 0: all windows and the final Horner; wn > 0: only windows [w0, w0+wn), output = their sums (B must be 1)
+// sc_stride / sc_off: the scalar of (msm m, term i) is d_scalars[m*sc_stride + sc_off + i] (sc_stride = 0: rows of n, no offset)
 static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint32_t* d_base_off, const uint8_t* d_scalars,
-                            size_t B, size_t n, int window, void* d_out, uint32_t w0, uint32_t wn) {
+                            size_t B, size_t n, int window, void* d_out, uint32_t w0, uint32_t wn, size_t sc_stride, size_t sc_off) {
     NEED_INIT();
     if (!B) return 0;
     if (n == 0) {  // empty sums are the identity (compute_MSM returns Z1 for empty input)
@@ -677,6 +690,7 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
     if (slice && B != 1) return fail("cpg_g1_msm_batched: window slices are for single MSMs");
     MsmShape s; s.n = (uint32_t)n; s.c = c; s.W = rc.W; s.NB = 1u << (c - 1); s.base_stride = base_stride; s.base_off = nullptr;
     s.w0 = slice ? w0 : 0; s.wn = slice ? wn : rc.W;
+    s.sc_stride = sc_stride ? sc_stride : n; s.sc_off = sc_off;
     const bool large = few || n > 2048 || s.NB > 256;
     if (g_msm_path == 1 && large) return fail("cpg_g1_msm_batched: the per-window path handles n <= 2048 and windows <= 9 bits");
     // reduction levels: NB = prod ch_j
@@ -709,7 +723,7 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
         Xyzz* buckets = sc.get<Xyzz>(BW * s.NB);
         int16_t* dig = sc.get<int16_t>((uint64_t)nb * n * s.W);
         if (!boff || !sorted || !buckets || !dig) return fail("cpg_g1_msm_batched: scratch allocation failed");
-        const uint32_t* ks = (const uint32_t*)d_scalars + (uint64_t)b0 * n * 8;
+        const uint32_t* ks = (const uint32_t*)d_scalars + (uint64_t)b0 * s.sc_stride * 8;
         const Aff* bases = (const Aff*)d_bases + (d_base_off ? 0 : (uint64_t)b0 * base_stride);
         s.base_off = d_base_off ? d_base_off + b0 : nullptr;
         if (int r = launch(RecodeDigits{s, rc, ks, dig}, (uint64_t)nb * n)) return r;
@@ -801,11 +815,21 @@ int cpg_fixed_table_free(void* table) {
 }
 size_t cpg_fixed_table_bytes(const void* table) { return table ? ((const FixedTable*)table)->bytes : 0; }
 
+}  // extern "C"
+// row_stride / row_off: the table's bases take entries row_off .. row_off + nb of coefficient rows that are row_stride
+// entries long (a rank of a sharded proof holds the table of its own bases only); row_stride = 0: rows of nb, no offset
+static int msm_fixed_impl(const void* table, const uint8_t* d_scalars, size_t B, int accumulate, void* d_out, size_t row_stride, size_t row_off);
+extern "C" {
 int cpg_g1_msm_fixed_batched(const void* table, const uint8_t* d_scalars, size_t B, int accumulate, void* d_out) {
+    return msm_fixed_impl(table, d_scalars, B, accumulate, d_out, 0, 0);
+}
+}  // extern "C"
+static int msm_fixed_impl(const void* table, const uint8_t* d_scalars, size_t B, int accumulate, void* d_out, size_t row_stride, size_t row_off) {
     NEED_INIT();
     if (!table) return fail("cpg_g1_msm_fixed_batched: null table");
     if (!B) return 0;
     const FixedTable* t = (const FixedTable*)table;
+    if (!row_stride) row_stride = t->s.nb;
     Recode rc = make_recode(t->s.c);
     Scratch sc;
     // few MSMs over many bases (a single large proof): split the bases so that no thread walks thousands of them
@@ -813,7 +837,10 @@ int cpg_g1_msm_fixed_batched(const void* table, const uint8_t* d_scalars, size_t
     if ((uint64_t)B * t->s.W < 8192 && t->s.nb >= 1024) { nchunk = t->s.nb / 256; if (nchunk > 64) nchunk = 64; }
     Xyzz* partial = sc.get<Xyzz>((uint64_t)B * t->s.W * nchunk);
     if (!partial) return fail("cpg_g1_msm_fixed_batched: scratch allocation failed");
-    if (int r = launch<128, 3>(FixedMsmWindow{t->s, rc, (uint32_t)B, nchunk, t->table, (const uint32_t*)d_scalars, partial}, (((uint64_t)B + 31) / 32) * 32 * t->s.W * nchunk)) return r;
+#ifndef CPG_HOST_EMU
+    if (g_prof_on && g_d_counters) if (int r = launch(CountNonZero{(const uint32_t*)d_scalars, g_d_counters, t->s.nb, row_stride, row_off}, (uint64_t)B * t->s.nb)) return r;
+#endif
+    if (int r = launch<128, 3>(FixedMsmWindow{t->s, rc, (uint32_t)B, nchunk, t->table, (const uint32_t*)d_scalars, row_stride, row_off, partial}, (((uint64_t)B + 31) / 32) * 32 * t->s.W * nchunk)) return r;
     uint32_t np = t->s.W * nchunk;
     if (np > 256) {                                                      // long partial lists: two stages of short serial sums
         const uint32_t per = nchunk;                                     // np = W * nchunk: W groups of nchunk
@@ -824,6 +851,7 @@ int cpg_g1_msm_fixed_batched(const void* table, const uint8_t* d_scalars, size_t
     }
     return launch_occ(SumWindows{np, partial, (Jac*)d_out, accumulate}, B);
 }
+extern "C" {
 
 /* ---- Fr vectors ---- */
 int cpg_fr_add(const uint8_t* a, const uint8_t* b, size_t k, uint8_t* out) {

@@ -299,6 +299,13 @@ CPG_HD void fr_batch_inv(HFr* v, size_t n, HFr* scratch) {
     }
 }
 
+// the identity's 48-byte encoding: appended for the blinder slots of T_wb / U_wb (cp/curdleproofs.py:124-136)
+#define CPGH_INF48_INIT {0xc0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}
+static const uint8_t H_INF48[48] = CPGH_INF48_INIT;
+#if defined(__CUDACC__)
+static __device__ __constant__ uint8_t D_INF48[48] = CPGH_INF48_INIT;
+#endif
+
 // -------------------------------------------------------------- Merlin + challenges ---
 // Labels are string literals; their length is taken at compile time (no strlen in device code).
 struct Transcript {

@@ -50,6 +50,8 @@ struct MsmShape {
                                   // arrays are indexed mw = msm*wn + (w - w0)
     uint64_t base_stride;         // bases of msm m start at m*base_stride (0 = shared by all) ...
     const uint32_t* base_off;     // ... unless this is set: bases of msm m start at base_off[m] (in points)
+    uint64_t sc_stride, sc_off;   // scalar of (msm m, term i) = scalars[m*sc_stride + sc_off + i]: a rank of a sharded proof
+                                  // evaluates a sub-range of every coefficient row (sc_stride = n, sc_off = 0 otherwise)
 };
 
 // 0 --- signed digits of one scalar, all windows ---------------------------------------------
@@ -62,7 +64,7 @@ struct RecodeDigits {
     int16_t* dig;                 // [B][n][W] (out)
     CPG_HD void operator()(uint64_t t) const {      // t = msm*n + term
         uint32_t kp[8];
-        recode_add(rc, scalars + 8 * t, kp);
+        recode_add(rc, scalars + 8 * ((t / s.n) * s.sc_stride + s.sc_off + t % s.n), kp);
         int16_t* out = dig + t * (uint64_t)s.W;
         for (uint32_t w = 0; w < s.W; w++) out[w] = (int16_t)recode_digit(rc, kp, w);
     }
@@ -476,7 +478,8 @@ struct FixedMsmWindow {            // sum_i +-T[i][w][|d|-1] for one (msm, windo
     uint32_t B;
     uint32_t nchunk;               // 1, or (few MSMs over many bases: one large proof) the bases split over nchunk threads
     const Aff* table;
-    const uint32_t* scalars;       // [B][nb][8]
+    const uint32_t* scalars;       // [B][row_stride][8]; the table's nb bases take entries row_off .. row_off + nb of every row
+    uint64_t row_stride, row_off;
     Xyzz* partial;                 // [B*W*nchunk]
     // A warp = one window of 32 consecutive MSMs (lane = msm): all lanes walk the same bases of the same
     // table segment, and callers that order their MSMs by kind (the prover: output-major) give every
@@ -489,7 +492,7 @@ struct FixedMsmWindow {            // sum_i +-T[i][w][|d|-1] for one (msm, windo
         if (m >= B) return;
         const uint32_t per = (s.nb + nchunk - 1) / nchunk;
         const uint32_t i0 = ch * per, i1 = i0 + per < s.nb ? i0 + per : s.nb;
-        const uint32_t* ks = scalars + m * s.nb * 8;
+        const uint32_t* ks = scalars + (m * row_stride + row_off) * 8;
         Xyzz acc = xyzz_inf();
         uint32_t kp[8];
         for (uint32_t i = i0; i < i1; i++) {
@@ -503,6 +506,30 @@ struct FixedMsmWindow {            // sum_i +-T[i][w][|d|-1] for one (msm, windo
             acc = xyzz_add_mixed(acc, cneg(q2, d < 0));
         }
         partial[(m * s.W + w) * nchunk + ch] = acc;
+    }
+};
+struct CountNonZero {              // thread = scalar: *count += 1 for every non-zero one (work model of the table MSMs, profiling only)
+    static constexpr const char* kName = "CountNonZero";
+    const uint32_t* scalars; unsigned long long* count;
+    uint64_t nb, row_stride, row_off;   // scalar t = (row t / nb, entry row_off + t % nb)
+    CPG_HD void operator()(uint64_t t) const {
+        const uint32_t* k = scalars + 8 * ((t / nb) * row_stride + row_off + t % nb);
+        if ((k[0] | k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) != 0) {
+#ifdef __CUDA_ARCH__
+            atomicAdd(count, 1ULL);
+#else
+            __atomic_fetch_add(count, 1ULL, __ATOMIC_RELAXED);
+#endif
+        }
+    }
+};
+struct SumRanks {                  // thread = output t: sum over the ranks' partial sums (after the all-gather of a sharded proof's round)
+    static constexpr const char* kName = "SumRanks";
+    uint32_t world; uint64_t count, nfirst; const Jac* all; Jac* out_first; Jac* out_second;   // all = [world][count]; t < nfirst -> out_first
+    CPG_HD void operator()(uint64_t t) const {
+        Jac acc = all[t];
+        for (uint32_t r = 1; r < world; r++) acc = jac_add(acc, all[(uint64_t)r * count + t]);
+        if (t < nfirst) out_first[t] = acc; else out_second[t - nfirst] = acc;
     }
 };
 struct SumPartials {               // thread = (msm, group): plain sum of `per` consecutive partials (first stage for long partial lists)

@@ -188,7 +188,7 @@ CPG_HD void prove_transcript(const PShape& sh, const POut& O, const PTBuf& pt, u
         tr.append_point("same_msm_step1", outs + 48 * O.Ap);
         tr.append_point("same_msm_step1", outs + 48 * O.T2);
         tr.append_point("same_msm_step1", outs + 48 * O.U2);
-        uint8_t INF[48]; memset(INF, 0, 48); INF[0] = 0xc0;
+        const uint8_t* INF = CPGH_SEL(INF48);
         const uint8_t* Hb = pt.crs48 + 48 * (size_t)n;
         const uint8_t* tu = pt.tu48 + b * (size_t)(2 * ell) * 48;
         for (uint32_t i = 0; i < ell; i++) tr.append_point("same_msm_step1", tu + 48 * (size_t)i);
@@ -585,6 +585,7 @@ struct ProverLane {
     size_t cap = 0, B = 0;
     uint8_t *d_in48 = nullptr, *d_tu48 = nullptr, *d_k = nullptr, *d_rand = nullptr, *d_outs = nullptr, *d_fs = nullptr, *d_vs = nullptr, *d_proof = nullptr, *d_err = nullptr;
     uint32_t *d_perm = nullptr, *d_off = nullptr; Aff* d_bases = nullptr; HFr* d_vec = nullptr; Jac *d_fix = nullptr, *d_var = nullptr;
+    Jac* d_gather = nullptr;      // [world][B * (P_MAX_OUT + P_MAX_VAR)] partial sums of a sharded proof's round
     PTr* d_trs = nullptr; PChal* d_chal = nullptr; PRes* d_res = nullptr; HFr *d_achal = nullptr, *d_part = nullptr, *d_red = nullptr;
     // host mirrors for the transcript on host threads (few, large proofs): pinned, exchanged once per round
     PChal* h_chal = nullptr; PRes* h_res = nullptr; HFr* h_achal = nullptr; std::vector<PTr> h_trs; std::vector<uint8_t> h_k;
@@ -598,20 +599,21 @@ struct ProverLane {
     cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
 #endif
     std::vector<void*> all() { return {d_in48, d_tu48, d_k, d_rand, d_outs, d_fs, d_vs, d_proof, d_err, d_perm, d_off, d_bases, d_vec, d_fix, d_var, d_tab, d_tab_jac, d_tab_pz, d_k12,
-                                        d_trs, d_chal, d_res, d_achal, d_part, d_red}; }
+                                        d_trs, d_chal, d_res, d_achal, d_part, d_red, d_gather}; }
     void release() {
         for (void* q : all()) cpg_free(q);
         cpg_host_free(h_tu); cpg_host_free(h_outs); cpg_host_free(h_proof); cpg_host_free(h_err); cpg_host_free(h_in); cpg_host_free(h_rand);
         cpg_host_free(h_chal); cpg_host_free(h_res); cpg_host_free(h_achal);
-        h_chal = nullptr; h_res = nullptr; h_achal = nullptr; d_trs = nullptr; d_chal = nullptr; d_res = nullptr; d_achal = d_part = d_red = nullptr;
+        h_chal = nullptr; h_res = nullptr; h_achal = nullptr; d_trs = nullptr; d_chal = nullptr; d_res = nullptr; d_achal = d_part = d_red = nullptr; d_gather = nullptr;
         h_tu = h_outs = h_proof = h_err = h_in = h_rand = nullptr;
         d_in48 = d_tu48 = d_k = d_rand = d_outs = d_fs = d_vs = d_proof = d_err = nullptr; d_perm = d_off = nullptr; d_bases = nullptr; d_vec = nullptr; d_fix = d_var = nullptr; d_tab = nullptr; d_tab_jac = nullptr; d_tab_pz = nullptr; d_k12 = nullptr;
         cap = 0;
     }
-    int reserve(const PShape& sh, size_t proof_len, size_t Bn, uint32_t NOUT, uint32_t ts) {
+    int reserve(const PShape& sh, size_t proof_len, size_t Bn, uint32_t NOUT, uint32_t ts, int world = 1) {
         if (Bn <= cap && ts == tab_ts) return 0;
         release();
         tab_ts = ts;
+        d_gather = (Jac*)cpg_malloc(sizeof(Jac) * (world > 1 ? (size_t)world * Bn * (P_MAX_OUT + P_MAX_VAR) : 1));
         d_k12 = (uint32_t*)cpg_malloc(Bn * 32);
         d_tab = (Aff*)cpg_malloc(sizeof(Aff) * (Bn * 2 * sh.ell * (size_t)ts + 1));
         d_tab_jac = (Jac*)cpg_malloc(sizeof(Jac) * (TAB_CHUNK * (size_t)ts + 1));
@@ -650,6 +652,8 @@ struct Prover {
     std::vector<uint8_t> crs48;
     Aff* d_crs = nullptr; uint8_t* d_crs48 = nullptr;
     void* table = nullptr;        // fixed-base table over vec_G | vec_H | H | G_t | G_u
+    Shard shard;                  // world > 1: ONE proof's leaves split over ranks (cpg_prover_create_sharded)
+    std::vector<void*> shard_tables;   // [world] (only this rank's entry unless the ranks are emulated): table of that rank's block of the CRS bases
     int var_window = 0;
     int table_window = 6;         // per-base tables of 2^(c-1) multiples for the T / U MSMs (0: bucket method for those too)
     int nlanes = 2, lastK = 1;
@@ -667,7 +671,7 @@ struct Prover {
     void release() { for (ProverLane& L : lanes) L.release(); }
     // contiguous split of B proofs; small batches stay on one lane (nothing to hide behind)
     int split(size_t B, size_t* first, size_t* count) const {
-        int k = (B >= lane_min * (size_t)nlanes) ? nlanes : 1;
+        int k = (B >= lane_min * (size_t)nlanes && !shard.on()) ? nlanes : 1;   // (a sharded proof's collectives stay on one stream)
         for (int i = 0; i < k; i++) { first[i] = B * i / k; count[i] = B * (i + 1) / k - first[i]; }
         return k;
     }
@@ -755,6 +759,25 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
             pt.in48 = p.d_in48; pt.tu48 = p.d_tu48; pt.kbytes = p.d_k; pt.rand = p.d_rand; pt.crs48 = pr.d_crs48; pt.outs48 = p.d_outs;
             pt.trs = p.d_trs; pt.chal = p.d_chal; pt.res = p.d_res; pt.achal = p.d_achal; pt.proof = p.d_proof;
             if (int rc = launch<64>(ProveTranscript{sh, O, pt, r}, B)) return rc;
+            if (getenv("CPG_DEBUG_SHADOW")) {               // debugging aid: re-run the step on the host, compare the transcript states (this is how a
+                                                            // device-only miscompilation of the identity's encoding was found; tools/prove_consistency.py)
+                std::vector<PChal> dev(B);
+                if (int rc = d2h_async(p.h_outs, p.d_outs, B * (size_t)O.NOUT * 48)) return rc;
+                if (int rc = d2h_async(p.h_res, p.d_res, B * sizeof(PRes))) return rc;
+                if (int rc = d2h_async(p.h_tu, p.d_tu48, B * 2 * (size_t)ell * 48)) return rc;
+                if (int rc = cpg_d2h(dev.data(), p.d_chal, B * sizeof(PChal))) return rc;
+                PTBuf ht;
+                ht.in48 = p.h_in; ht.tu48 = p.h_tu; ht.kbytes = p.h_k.data(); ht.rand = p.h_rand; ht.crs48 = pr.crs48.data(); ht.outs48 = p.h_outs;
+                ht.trs = p.h_trs.data(); ht.chal = p.h_chal; ht.res = p.h_res; ht.achal = p.h_achal; ht.proof = p.h_proof;
+                for (size_t b = 0; b < B; b++) prove_transcript(sh, O, ht, r, b);
+                size_t bad = 0;
+                for (size_t b = 0; b < B; b++) if (memcmp(&dev[b], &p.h_chal[b], sizeof(PChal))) bad++;
+                std::vector<PTr> dtr(B);
+                if (int rc = cpg_d2h(dtr.data(), p.d_trs, B * sizeof(PTr))) return rc;
+                size_t badtr = 0;
+                for (size_t b = 0; b < B; b++) if (memcmp(dtr[b].tr.s.st.b, p.h_trs[b].tr.s.st.b, 200) || dtr[b].tr.s.pos != p.h_trs[b].tr.s.pos) badtr++;
+                fprintf(stderr, "[shadow] round %u: %zu of %zu challenge sets differ, %zu transcript states differ\n", r, bad, B, badtr);
+            }
         }
     }
     if (r == RD.FIN) return 0;
@@ -784,6 +807,29 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
     }
     {
         RoundPlan pl = plan_for(r);
+        if (pr.shard.on()) {
+            // ONE proof over several ranks: each rank sums its block of the CRS leaves (its own table) and of the
+            // tracker leaves (bucket method over a sub-range of every coefficient row); one all-gather per round
+            const Shard& sd = pr.shard;
+            const size_t nfix = B * pl.nout, nv = B * pl.nvar, cnt = nfix + nv;
+            if (pl.nvar) {
+                VarOffsets vo; vo.B = B; vo.ell = ell; vo.off = p.d_off; vo.tables = 0;
+                for (uint32_t v = 0; v < P_MAX_VAR; v++) vo.set[v] = v < pl.nvar ? pl.var_set[v] : 0;
+                if (int rc = launch(vo, nv)) return rc;
+            }
+            for (int rk = sd.first(); rk < sd.last(); rk++) {
+                Jac* slot = p.d_gather + (size_t)rk * cnt;
+                size_t lo, hi;
+                comm_block(sh.NF, rk, sd.world, &lo, &hi);
+                if (int rc = msm_fixed_impl(pr.shard_tables[rk], p.d_fs, nfix, 0, slot, sh.NF, lo)) return rc;
+                if (pl.nvar) {
+                    comm_block(ell, rk, sd.world, &lo, &hi);
+                    if (int rc = msm_batched_impl(p.d_bases + lo, 0, p.d_off, p.d_vs, nv, hi - lo, pr.var_window, slot + nfix, 0, 0, ell, lo)) return rc;
+                }
+            }
+            if (int rc = shard_exchange(sd, p.d_gather, cnt)) return rc;
+            if (int rc = launch_occ(SumRanks{(uint32_t)sd.world, cnt, nfix, p.d_gather, p.d_fix, p.d_var}, cnt)) return rc;
+        } else {
         // fixed-base part of every output of the round: B*nout MSMs over the CRS table (rows are output-major)
         if (int rc = cpg_g1_msm_fixed_batched(pr.table, p.d_fs, B * pl.nout, 0, p.d_fix)) return rc;
         if (pl.nvar) {                                  // variable-base parts: ONE batched MSM over all B*nvar instances
@@ -800,10 +846,14 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
                 Scratch sc;
                 Xyzz* partial = sc.get<Xyzz>(M * rc_.W);
                 if (!partial) return fail("cpg_prove_batch: scratch allocation failed");
+#ifndef CPG_HOST_EMU
+                if (g_prof_on && g_d_counters) if (int rc = launch(CountNonZero{(const uint32_t*)p.d_vs, g_d_counters + 1, ell, ell, 0}, M * ell)) return rc;
+#endif
                 if (int rc = launch<128, 3>(VarTableMsmWindow{ell, p.tab_ts, rc_.W, rc_, (uint32_t)M, p.d_tab, p.d_off, (const uint32_t*)p.d_vs, partial}, ((M + 31) / 32) * 32 * rc_.W)) return rc;
                 MsmShape hs; memset(&hs, 0, sizeof hs); hs.W = rc_.W; hs.c = c;
                 if (int rc = launch_occ(Horner{hs, partial, p.d_var}, M)) return rc;
             } else if (int rc = cpg_g1_msm_batched_off(p.d_bases, p.d_off, p.d_vs, B * pl.nvar, ell, pr.var_window, p.d_var)) return rc;
+        }
         }
         ProveCombine pc;
         pc.nout = pl.nout; pc.NOUT = O.NOUT; pc.B = B; pc.fixed = p.d_fix; pc.var = p.d_var; pc.outs48 = p.d_outs;
@@ -863,7 +913,17 @@ int prove_device_all(Prover& p, int k, bool download = false) {
 
 extern "C" {
 
+static void* prover_create_impl(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window, bool sharded);
 void* cpg_prover_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window) {
+    return prover_create_impl(crs_bytes, ell, n_blinders, fixed_window, false);
+}
+/* ONE proof at a time over ALL ranks of the communicator (BASELINE config 5): every rank calls this and every later
+ * cpg_prove_batch with identical arguments and gets identical outputs; the proof's leaves are split over the ranks
+ * (this rank builds the CRS table of its block only) and each round's partial sums cross by one all-gather. */
+void* cpg_prover_create_sharded(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window) {
+    return prover_create_impl(crs_bytes, ell, n_blinders, fixed_window, true);
+}
+static void* prover_create_impl(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window, bool sharded) {
     if (need_init()) return nullptr;
     size_t n = ell + n_blinders;
     uint32_t lg = 0;
@@ -887,7 +947,17 @@ void* cpg_prover_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders,
     if (!rc) rc = cpg_d2h(err.data(), derr, n + 5);
     cpg_free(derr);
     if (!rc) for (uint8_t e : err) if (e) { rc = fail("cpg_prover_create: CRS holds an invalid point encoding"); break; }
-    if (!rc) { p->table = cpg_fixed_table_create(p->d_crs, n + 3, fixed_window > 0 ? fixed_window : 12); if (!p->table) rc = 1; }
+    if (sharded) p->shard = shard_now();
+    if (!rc && p->shard.on()) {
+        p->shard_tables.assign(p->shard.world, nullptr);
+        for (int rk = p->shard.first(); rk < p->shard.last() && !rc; rk++) {
+            size_t lo, hi;
+            comm_block(n + 3, rk, p->shard.world, &lo, &hi);
+            if (hi == lo) { rc = fail("cpg_prover_create_sharded: more ranks than CRS bases"); break; }
+            p->shard_tables[rk] = cpg_fixed_table_create(p->d_crs + lo, hi - lo, fixed_window > 0 ? fixed_window : 12);
+            if (!p->shard_tables[rk]) rc = 1;
+        }
+    } else if (!rc) { p->table = cpg_fixed_table_create(p->d_crs, n + 3, fixed_window > 0 ? fixed_window : 12); if (!p->table) rc = 1; }
 #ifndef CPG_HOST_EMU
     if (!rc) rc = ck(cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming), "cudaEventCreate");
     for (ProverLane& L : p->lanes) {
@@ -908,6 +978,7 @@ int cpg_prover_free(void* handle) {
     if (p->fork) cudaEventDestroy(p->fork);
 #endif
     cpg_fixed_table_free(p->table);
+    for (void* t : p->shard_tables) cpg_fixed_table_free(t);
     cpg_free(p->d_crs); cpg_free(p->d_crs48);
     delete p;
     return 0;
@@ -985,7 +1056,7 @@ int cpg_prove_batch(void* handle, const uint8_t* inputs, const uint32_t* perms, 
         const size_t f = first[i], c = count[i];
         // per-base tables pay off for the many small MSMs of Whisk-size proofs; one thread walks all ell terms of a
         // (msm, window), so large shuffles keep the bucket method
-        if (int rc = L.reserve(sh, p.proof_len, c, O.NOUT, (p.table_window > 0 && ell <= 2048) ? 1u << (p.table_window - 1) : 0)) return rc;
+        if (int rc = L.reserve(sh, p.proof_len, c, O.NOUT, (p.table_window > 0 && ell <= 2048 && !p.shard.on()) ? 1u << (p.table_window - 1) : 0, p.shard.world)) return rc;
         L.B = c;
         L.host_transcript = p.host_transcript_for(c);
         L.h_k.assign(ks + f * 32, ks + (f + c) * 32);

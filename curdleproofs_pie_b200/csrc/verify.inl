@@ -147,8 +147,9 @@ CPG_HD void verify_phase2(const VShape& sh, const Layout& L, const VBuffers& vb,
     const uint8_t* pp = row + (size_t)NI * 48;
     const uint8_t* Dbytes = vb.derived + b * 96;
     const uint8_t* Apbytes = Dbytes + 48;
-    uint8_t INF[48];
-    memset(INF, 0, 48); INF[0] = 0xc0;
+    // (a constant, not a local array: nvcc 12.9 miscompiled `uint8_t INF[48]; memset; INF[0] = 0xc0` in the prover's
+    // transcript step for sm_100a - the appended bytes were not the identity's - while the same source was right on the host)
+    const uint8_t* INF = CPGH_SEL(INF48);
     Transcript tr = s.tr;
     // grand product -> IPA statement
     HFr beta_l = fr_pow_u64(s.beta_gp, ell), beta_l1 = fr_mul(beta_l, s.beta_gp);
@@ -461,6 +462,9 @@ struct Verifier {
     Aff* d_crs = nullptr;         // n + 5 affine points
     uint8_t* d_crs48 = nullptr;   // the same as wire bytes (device transcript appends H)
     void* table = nullptr;        // fixed-base table over the first n + 3
+    Shard shard;                  // world > 1: every proof's leaves split over ranks (cpg_verifier_create_sharded)
+    std::vector<void*> shard_tables;   // table of each rank's block of the CRS bases (only this rank's unless the ranks are emulated)
+    Jac* d_gather = nullptr; size_t gather_cap = 0;
     void* table_gh = nullptr;     // fixed-base table over G_sum, H_sum
     uint8_t secret[32];
     uint64_t calls = 0;           // batches checked so far (the weights' per-call nonce)
@@ -469,7 +473,7 @@ struct Verifier {
     bool group_auto = false;      // re-pick `group` after every batch from the observed rate of failing proofs
     int group_window = 0;
     uint32_t cur_group = 1;       // group size of the batch in flight: `group`, halved until a batch of this size holds a whole group
-    void begin_batch(size_t B) { cur_group = group; while (cur_group > 1 && cur_group > B) cur_group >>= 1; }
+    void begin_batch(size_t B) { cur_group = shard.on() ? 1 : group; while (cur_group > 1 && cur_group > B) cur_group >>= 1; }
     size_t rechecked = 0;         // proofs of the last batch that went through the per-proof fallback
     // device buffers of the current batch, kept (and grown on demand) between calls
     size_t cap = 0, lastB = 0;
@@ -533,6 +537,28 @@ struct Verifier {
     }
     int device_check_each(size_t b0, size_t nb) {
         if (!nb) return 0;
+        if (shard.on()) {
+            // each rank sums its block of the NV variable bases and of the NF CRS bases of every proof; ONE all-gather
+            // of 2 partial sums per proof, then the test on every rank (identical verdicts)
+            const size_t cnt = 2 * nb;
+            if ((size_t)shard.world * cnt > gather_cap) {
+                cpg_free(d_gather);
+                gather_cap = (size_t)shard.world * cnt;
+                d_gather = (Jac*)cpg_malloc(sizeof(Jac) * gather_cap);
+                if (!d_gather) { gather_cap = 0; return fail("cpg_verify_batch: device allocation failed"); }
+            }
+            for (int rk = shard.first(); rk < shard.last(); rk++) {
+                Jac* slot = d_gather + (size_t)rk * cnt;
+                size_t lo, hi;
+                comm_block(sh.NV, rk, shard.world, &lo, &hi);
+                if (int rc = msm_batched_impl(d_bases + b0 * sh.NV + lo, sh.NV, nullptr, d_vs + b0 * sh.NV * 32, nb, hi - lo, var_window, slot, 0, 0, sh.NV, lo)) return rc;
+                comm_block(sh.NF, rk, shard.world, &lo, &hi);
+                if (int rc = msm_fixed_impl(shard_tables[rk], d_fs + b0 * sh.NF * 32, nb, 0, slot + nb, sh.NF, lo)) return rc;
+            }
+            if (int rc = shard_exchange(shard, d_gather, cnt)) return rc;
+            if (int rc = launch_occ(SumRanks{(uint32_t)shard.world, cnt, nb, d_gather, d_var + b0, d_fix + b0}, cnt)) return rc;
+            return launch(AddFixedAndTest{d_var + b0, d_fix + b0, d_rej + b0, d_ok + b0}, nb);
+        }
         if (int rc = cpg_g1_msm_batched(d_bases + b0 * sh.NV, sh.NV, d_vs + b0 * sh.NV * 32, nb, sh.NV, var_window, d_var + b0)) return rc;
         if (int rc = cpg_g1_msm_fixed_batched(table, d_fs + b0 * sh.NF * 32, nb, 0, d_fix + b0)) return rc;
         return launch(AddFixedAndTest{d_var + b0, d_fix + b0, d_rej + b0, d_ok + b0}, nb);
@@ -722,7 +748,17 @@ int cpg_merlin_challenge(void* h, const uint8_t* label, size_t nl, uint8_t* out,
     return 0;
 }
 
+static void* verifier_create_impl(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window, int host_threads, bool sharded);
 void* cpg_verifier_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window, int host_threads) {
+    return verifier_create_impl(crs_bytes, ell, n_blinders, fixed_window, host_threads, false);
+}
+/* Every proof over ALL ranks of the communicator (BASELINE config 5's verify side): every rank calls this and every later
+ * cpg_verify_batch with identical arguments and gets identical verdicts; each proof's MSM terms are split over the
+ * ranks and the 2 partial sums per proof cross by one all-gather.  The batching secret is rank 0's. */
+void* cpg_verifier_create_sharded(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window, int host_threads) {
+    return verifier_create_impl(crs_bytes, ell, n_blinders, fixed_window, host_threads, true);
+}
+static void* verifier_create_impl(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window, int host_threads, bool sharded) {
     if (need_init()) return nullptr;
     size_t n = ell + n_blinders;
     uint32_t lg = 0;
@@ -746,7 +782,27 @@ void* cpg_verifier_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinder
     if (!rc) rc = cpg_d2h(err.data(), derr, n + 5);
     cpg_free(derr);
     if (!rc) for (uint8_t e : err) if (e) { rc = fail("cpg_verifier_create: CRS holds an invalid point encoding"); break; }
-    if (!rc) { v->table = cpg_fixed_table_create(v->d_crs, n + 3, fixed_window > 0 ? fixed_window : 12); if (!v->table) rc = 1; }
+    if (sharded) v->shard = shard_now();
+    if (!rc && v->shard.on()) {
+        // all ranks must weigh the checks alike: rank 0's secret reaches the others through the communicator
+        if (!v->shard.virt) {
+            Scratch sc;
+            uint8_t* d_all = sc.get<uint8_t>(32 * (size_t)v->shard.world);
+            if (!d_all) rc = fail("cpg_verifier_create_sharded: scratch allocation failed");
+            if (!rc) rc = cpg_h2d(d_all + 32 * (size_t)v->shard.rank, v->secret, 32);
+            if (!rc) rc = cpg_sync();
+            if (!rc) rc = comm_allgather(d_all + 32 * (size_t)v->shard.rank, d_all, 32);
+            if (!rc) rc = cpg_d2h(v->secret, d_all, 32);
+        }
+        v->shard_tables.assign(v->shard.world, nullptr);
+        for (int rk = v->shard.first(); rk < v->shard.last() && !rc; rk++) {
+            size_t lo, hi;
+            comm_block(n + 3, rk, v->shard.world, &lo, &hi);
+            if (hi == lo) { rc = fail("cpg_verifier_create_sharded: more ranks than CRS bases"); break; }
+            v->shard_tables[rk] = cpg_fixed_table_create(v->d_crs + lo, hi - lo, fixed_window > 0 ? fixed_window : 12);
+            if (!v->shard_tables[rk]) rc = 1;
+        }
+    } else if (!rc) { v->table = cpg_fixed_table_create(v->d_crs, n + 3, fixed_window > 0 ? fixed_window : 12); if (!v->table) rc = 1; }
     if (!rc) { v->table_gh = cpg_fixed_table_create(v->d_crs + (n + 3), 2, 8); if (!v->table_gh) rc = 1; }
     if (rc) { cpg_fixed_table_free(v->table); cpg_free(v->d_crs); cpg_free(v->d_crs48); delete v; return nullptr; }
     return v;
@@ -764,6 +820,8 @@ int cpg_verifier_free(void* handle) {
     cpg_host_free(v->h_wire); cpg_host_free(v->h_psc);
     cpg_fixed_table_free(v->table);
     cpg_fixed_table_free(v->table_gh);
+    for (void* t : v->shard_tables) cpg_fixed_table_free(t);
+    cpg_free(v->d_gather);
     cpg_free(v->d_crs);
     cpg_free(v->d_crs48);
     delete v;

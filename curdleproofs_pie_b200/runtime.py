@@ -88,6 +88,8 @@ _SIGS = {
     "cpg_merlin_append": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t, _c.c_char_p, _c.c_size_t]),
     "cpg_merlin_challenge": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t, _c.c_char_p, _c.c_size_t]),
     "cpg_verifier_create": (_c.c_void_p, [_c.c_char_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_int]),
+    "cpg_verifier_create_sharded": (_c.c_void_p, [_c.c_char_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_int]),
+    "cpg_prover_create_sharded": (_c.c_void_p, [_c.c_char_p, _c.c_size_t, _c.c_size_t, _c.c_int]),
     "cpg_verifier_free": (_c.c_int, [_c.c_void_p]),
     "cpg_verifier_proof_bytes": (_c.c_size_t, [_c.c_void_p]),
     "cpg_verifier_input_bytes": (_c.c_size_t, [_c.c_void_p]),
@@ -333,7 +335,10 @@ class CpgLib:
 
         buf = ctypes.create_string_buffer(1 << 16)
         self.check(self.c.cpg_profile_report(buf, len(buf)), "cpg_profile_report")
-        return json.loads(buf.value.decode() or "{}")
+        rep = json.loads(buf.value.decode() or "{}")
+        # non-zero coefficients the table-lookup MSMs met while profiling (their work model), kept beside the kernel times
+        self.last_counters = rep.pop("_counters", {})
+        return rep
 
     def timer_start(self):
         self.check(self.c.cpg_timer_start(), "cpg_timer_start")

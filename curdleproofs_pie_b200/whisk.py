@@ -15,16 +15,19 @@ from . import runtime as _rt
 class BatchVerifier:
     """Holds the device-resident CRS (fixed-base tables) for one (ell, n_blinders)."""
 
-    def __init__(self, crs_bytes, ell, n_blinders=4, fixed_window=0, host_threads=0, lib=None, group=0):
+    def __init__(self, crs_bytes, ell, n_blinders=4, fixed_window=0, host_threads=0, lib=None, group=0, sharded=False):
         """group: proofs per aggregated check (cpg_verifier_set_group): 0 = adaptive (default: the library re-picks
-        the group size after every batch from the observed rate of failing proofs), 1 = one MSM per proof."""
+        the group size after every batch from the observed rate of failing proofs), 1 = one MSM per proof.
+        sharded: every proof is checked by ALL ranks of the library's communicator together (comm.init; BASELINE
+        config 5) - every rank makes the same calls with the same arguments."""
         self.lib = lib or _rt.get_lib()
         self.ell = int(ell)
         self.n_blinders = int(n_blinders)
         crs_bytes = bytes(crs_bytes)
         if len(crs_bytes) != 48 * (self.ell + self.n_blinders + 5):
             raise ValueError("crs_bytes must be CurdleproofsCrs.to_bytes() for (ell, n_blinders)")
-        self.handle = self.lib.c.cpg_verifier_create(crs_bytes, self.ell, self.n_blinders, fixed_window, host_threads)
+        create = self.lib.c.cpg_verifier_create_sharded if sharded else self.lib.c.cpg_verifier_create
+        self.handle = create(crs_bytes, self.ell, self.n_blinders, fixed_window, host_threads)
         if not self.handle:
             raise _rt.CpgError("cpg_verifier_create failed: " + self.lib.last_error())
         self.proof_len = int(self.lib.c.cpg_verifier_proof_bytes(self.handle))
@@ -128,14 +131,17 @@ def IsValidWhiskShuffleProofBatch(crs, pre_shuffle_trackers, post_shuffle_tracke
 class BatchProver:
     """Device-resident CRS tables + lock-step proof generation (cpg_prove_batch)."""
 
-    def __init__(self, crs_bytes, ell, n_blinders=4, fixed_window=0, lib=None):
+    def __init__(self, crs_bytes, ell, n_blinders=4, fixed_window=0, lib=None, sharded=False):
+        """sharded: ONE proof at a time over ALL ranks of the library's communicator (comm.init; BASELINE config 5) -
+        every rank makes the same calls with the same arguments and gets the same bytes."""
         self.lib = lib or _rt.get_lib()
         self.ell = int(ell)
         self.n = self.ell + int(n_blinders)
         crs_bytes = bytes(crs_bytes)
         if len(crs_bytes) != 48 * (self.n + 5):
             raise ValueError("crs_bytes must be CurdleproofsCrs.to_bytes() for (ell, n_blinders)")
-        self.handle = self.lib.c.cpg_prover_create(crs_bytes, self.ell, int(n_blinders), fixed_window)
+        create = self.lib.c.cpg_prover_create_sharded if sharded else self.lib.c.cpg_prover_create
+        self.handle = create(crs_bytes, self.ell, int(n_blinders), fixed_window)
         if not self.handle:
             raise _rt.CpgError("cpg_prover_create failed: " + self.lib.last_error())
         self.proof_len = int(self.lib.c.cpg_prover_proof_bytes(self.handle))

@@ -57,7 +57,9 @@ int cpg_timer_start(void);
 int cpg_timer_stop(float* ms);                  /* synchronises */
 uint64_t cpg_launch_count(void);                /* kernels launched by this library so far */
 /* per-kernel device time: when enabled every launch is bracketed by a CUDA event pair on its
- * stream; report() synchronises and writes JSON {"Kernel": {"ms":..,"launches":..,"threads":..}} */
+ * stream; report() synchronises and writes JSON {"Kernel": {"ms":..,"launches":..,"threads":..}, ...,
+ * "_counters": {"fixed_msm_terms": n, "var_table_msm_terms": n}} - the counters are the non-zero coefficients the
+ * table-lookup MSMs met since the last reset (each costs one mixed addition per window: their work model) */
 int cpg_profile_enable(int on);
 int cpg_profile_reset(void);
 int cpg_profile_report(char* buf, size_t cap);
@@ -177,6 +179,11 @@ int cpg_merlin_challenge(void* transcript, const uint8_t* label, size_t label_le
  *   proofs    : [B][cpg_verifier_proof_bytes]  M | proof      (WhiskShuffleProof.to_bytes, :57-61)
  *   verdicts  : [B], 1 = the reference would return True */
 void* cpg_verifier_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window, int host_threads);
+/* BASELINE config 5's verify side: every proof over ALL ranks of the communicator (cpg_comm_init).  Every rank calls
+ * this and every later cpg_verify_batch with identical arguments and gets identical verdicts: each proof's MSM terms
+ * (CRS bases through a table of this rank's block only, trackers / proof points through the bucket method) are split
+ * over the ranks and the 2 partial sums per proof cross by ONE all-gather inside the library. */
+void* cpg_verifier_create_sharded(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window, int host_threads);
 int cpg_verifier_free(void* verifier);
 size_t cpg_verifier_proof_bytes(const void* verifier);
 size_t cpg_verifier_input_bytes(const void* verifier);
@@ -223,6 +230,11 @@ int cpg_verify_replay_device(void* verifier, uint8_t* verdicts_or_null);
  *               proves over a harmless substitute) and its outputs are undefined; the other lanes are unaffected.
  * Preconditions the caller keeps: every buffer holds B full rows of the sizes above. */
 void* cpg_prover_create(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window);
+/* BASELINE config 5's prove side: ONE proof at a time over ALL ranks of the communicator.  Every rank calls this and
+ * every later cpg_prove_batch with identical arguments and gets identical outputs: the proof's leaves are split over
+ * the ranks, each round's partial sums (<= 16 Jacobian points per proof) cross by ONE all-gather inside the library;
+ * the transcript and the Fr vector kernels are replicated (cheap and deterministic). */
+void* cpg_prover_create_sharded(const uint8_t* crs_bytes, size_t ell, size_t n_blinders, int fixed_window);
 int cpg_prover_free(void* prover);
 size_t cpg_prover_proof_bytes(const void* prover);
 size_t cpg_prover_rand_scalars(const void* prover);

@@ -64,14 +64,14 @@ def rebuild_inputs(lib, case, n_rand):
     return crs48, pre48, perm, k, rand
 
 
-def check_large(lib, name, fixed_window=8):
+def check_large(lib, name, fixed_window=8, sharded=False):
     """prove: trackers and proof bytes equal the reference's; verify: the reference's verdicts on the honest
     and the swapped inputs.  Returns the timings."""
     case = load_case(name)
     N = case["N"]
     ell = N - 4
     t0 = time.perf_counter()
-    prover = whisk.BatchProver(_crs_probe(lib, case), ell, fixed_window=fixed_window, lib=lib)
+    prover = whisk.BatchProver(_crs_probe(lib, case), ell, fixed_window=fixed_window, lib=lib, sharded=sharded)
     crs48, pre48, perm, k, rand = rebuild_inputs(lib, case, prover.n_rand)
     t1 = time.perf_counter()
     (tu, proof), = prover.prove([pre48], [perm], [k], [rand])
@@ -81,7 +81,7 @@ def check_large(lib, name, fixed_window=8):
     assert proof[:48].hex() == case["M"]
     assert len(proof) - 48 == case["proof_len"]
     assert sha(proof[48:]) == case["proof_sha256"], "proof bytes differ from the reference's"
-    ver = whisk.BatchVerifier(crs48, ell, fixed_window=fixed_window, lib=lib)
+    ver = whisk.BatchVerifier(crs48, ell, fixed_window=fixed_window, lib=lib, sharded=sharded)
     w = 48 * ell
     R_, S_, T_, U_ = pre48[:w], pre48[w:], tu[:w], tu[w:]
     t3 = time.perf_counter()

@@ -25,12 +25,12 @@ def replay_rng(case, prover):
     return perm, k, rand
 
 
-def check_prove(lib, name, copies=1, fixed_window=0, window=0, lanes=None, table_window=None, transcript=None):
+def check_prove(lib, name, copies=1, fixed_window=0, window=0, lanes=None, table_window=None, transcript=None, sharded=False):
     """transcript: None (library default: by batch size), "host" or "device" - where the Fiat-Shamir step of every
     round runs; the Fr vector kernels are the same either way"""
     case = sc.load_case(name)
     ell = case["N"] - 4
-    prover = whisk.BatchProver(bytes.fromhex(case["crs"]), ell, fixed_window=fixed_window, lib=lib)
+    prover = whisk.BatchProver(bytes.fromhex(case["crs"]), ell, fixed_window=fixed_window, lib=lib, sharded=sharded)
     if transcript is not None:
         prover.set_transcript(transcript)
     if lanes:

@@ -57,3 +57,15 @@ def test_prove_rejects_bad_perm_and_blinders(seam_lib):
 
 def test_whisk_api_generate_then_validate(seam_lib):
     pc.check_whisk_api_roundtrip(seam_lib, "shuffle_N8_seed1234.json", B=2)
+
+
+@pytest.mark.parametrize("ranks", [2, 3, 8])
+def test_one_proof_split_over_ranks(seam_lib, monkeypatch, ranks):
+    """BASELINE config 5's decomposition: the leaves of ONE proof split over `ranks` blocks (CRS bases through a table
+    per block, trackers through the bucket method over sub-ranges of the coefficient rows), partial sums added up -
+    the communicator is emulated in-process (CPG_TEST_VIRTUAL_RANKS), everything else is the product's own code.
+    Bytes still equal the reference's; ranks = 8 > ell = 4 leaves some blocks without trackers."""
+    monkeypatch.setenv("CPG_TEST_VIRTUAL_RANKS", str(ranks))
+    pc.check_prove(seam_lib, "shuffle_N8_seed1234.json", fixed_window=4, sharded=True, transcript="host")
+    if ranks == 3:
+        pc.check_prove(seam_lib, "shuffle_N16_seed77.json", copies=2, fixed_window=5, window=3, sharded=True, transcript="device")

@@ -63,3 +63,11 @@ def test_verifier_refuses_to_exist_without_entropy(seam_lib, monkeypatch):
         whisk.BatchVerifier(bytes.fromhex(case["crs"]), case["N"] - 4, fixed_window=4, lib=seam_lib)
     monkeypatch.delenv("CPG_TEST_NO_ENTROPY")
     whisk.BatchVerifier(bytes.fromhex(case["crs"]), case["N"] - 4, fixed_window=4, lib=seam_lib).close()
+
+
+@pytest.mark.parametrize("ranks,on_device", [(2, False), (3, True), (8, False)])
+def test_one_proof_split_over_ranks(seam_lib, monkeypatch, ranks, on_device):
+    """every proof's MSM terms split over `ranks` blocks (emulated in-process), 2 partial sums per proof and block added
+    up: honest and corrupted variants still get the reference's verdicts"""
+    monkeypatch.setenv("CPG_TEST_VIRTUAL_RANKS", str(ranks))
+    vc.check_batch(seam_lib, "shuffle_N8_seed1234.json", transcript_on_device=on_device, fixed_window=4, sharded=True)

@@ -71,10 +71,10 @@ def variants(case):
     return out
 
 
-def check_batch(lib, name, copies=1, window=0, transcript_on_device=True, fixed_window=0, group=1):
+def check_batch(lib, name, copies=1, window=0, transcript_on_device=True, fixed_window=0, group=1, sharded=False):
     case = sc.load_case(name)
     ell = case["N"] - 4
-    ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), ell, fixed_window=fixed_window, lib=lib)
+    ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), ell, fixed_window=fixed_window, lib=lib, sharded=sharded)
     ver.set_transcript(transcript_on_device)
     ver.set_group(group)
     if window:

@@ -70,6 +70,17 @@ def worker(rank, world, port, n, q):
     lo, hi = sharding.shard_range(total, rank, world)
     full = sharding.gather_verdicts(bytes((i * 7 + 3) % 2 for i in range(lo, hi)), total, rank, world, lib=lib)
     assert full == bytes((i * 7 + 3) % 2 for i in range(total))
+    # ONE proof over all ranks (BASELINE config 5's decomposition): bytes equal the reference's golden proof, verdicts too
+    import prove_cases as prc
+    import verify_cases as vc
+    import large_cases as lc
+
+    prc.check_prove(lib, "shuffle_N128_seed4096.json", copies=2, sharded=True)
+    prc.check_prove(lib, "shuffle_N16_seed77.json", sharded=True, transcript="device")
+    vc.check_batch(lib, "shuffle_N128_seed4096.json", sharded=True, transcript_on_device=False)
+    vc.check_batch(lib, "shuffle_N16_seed77.json", sharded=True, transcript_on_device=True)
+    big = lc.check_large(lib, "large_N1024_seed6024.json", fixed_window=8, sharded=True)
+    times["large_N1024_prove"] = big["prove_s"] * 1e3
     slow = {k: sharding.max_over_ranks(v, lib=lib) for k, v in times.items()}
     lib.c.cpg_comm_free()
     q.put((rank, slow, int(lib.c.cpg_comm_nccl_version())))
@@ -92,7 +103,7 @@ def main():
         p.join(timeout=60)
         assert p.exitcode == 0
     print(json.dumps({"check": "cpg_g1_msm_sharded == single-GPU == oracle; allgather / max / verdict gather through libcpg's NCCL communicator",
-                      "gpus": a.gpus, "n": a.terms, "ms_single_gpu": res[0][1]["single"], "ms_sharded": res[0][1]["sharded"],
+                      "gpus": a.gpus, "n": a.terms, "ms_single_gpu": res[0][1]["single"], "ms_sharded": res[0][1]["sharded"], "sharded_proofs": "N128 / N16 golden bytes + verdicts, N1024 digests: equal the reference's", "ms_large_N1024_prove": res[0][1]["large_N1024_prove"],
                       "nccl_version": res[0][2], "wall_s": time.time() - t0}))
 
 
