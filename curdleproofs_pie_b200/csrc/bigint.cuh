@@ -11,8 +11,13 @@
 #pragma once
 #include <stdint.h>
 
-#if defined(__CUDACC__)
+// Forced inlining is for the DEVICE pass only.  nvcc's host pass compiles every __host__ __device__ functor as well;
+// with always_inline there gcc flattens whole point-arithmetic call trees into each of them (5.5 of the 7.5 minutes a
+// build of this library took), for code the host never runs hot.
+#if defined(__CUDACC__) && defined(__CUDA_ARCH__)
 #define CPG_HD __host__ __device__ __forceinline__
+#elif defined(__CUDACC__)
+#define CPG_HD __host__ __device__ inline
 #else
 #define CPG_HD inline
 #endif

@@ -672,6 +672,166 @@ struct FoldPoints {                // out[r][i] = L[r][i] + x[r] * R[r][i],  r <
     CPG_HD void operator()(uint64_t t) const { out[t] = jac_add(L[t], jac_mul(R[t], x + 8 * (t / m))); }
 };
 
+// ---- device-resident cache of decompressed points, keyed by their 48-byte encodings ----------------------------
+// In Whisk the pre-shuffle trackers of one shuffle proof are post-shuffle trackers of an earlier one
+// (cp/whisk_interface.py:96-100 decodes all 4 ell of them per call): a verifier that has seen a tracker already knows its
+// square root.  Open-addressing table, linear probing, 64-bit fingerprints backed by a full key comparison; it also
+// removes duplicates INSIDE a batch (the first thread to claim a slot decompresses, the others copy).
+//   CacheClaim       thread = cached point: hash, probe, claim an empty slot (OWN) or find the key's slot (FOLLOW)
+//   CacheResolve     thread = point: FOLLOW -> compare the key, settle HIT / wait-for-owner / decompress-uncached;
+//                    every point that must be decompressed is appended to a compact work list (warp-aggregated atomics)
+//   DecompressList   thread = work-list entry: square root; an owner also fills its slot and publishes it
+//   CacheFill        thread = cached point: hits and followers copy the slot's value
+// Several sub-batches run these on their own streams against the one table.  A slot is trusted only when `ready` is set
+// (published after the value) or when it was claimed by THIS launch sequence (owner == launch id: the owner's
+// DecompressList precedes our CacheFill in stream order); anything else - a torn key, a slot another stream is still
+// filling - falls back to decompressing the point uncached.  Verdicts never depend on who wins a race.
+#ifdef __CUDA_ARCH__
+CPG_HD unsigned long long atomic_cas_u64(unsigned long long* p, unsigned long long expect, unsigned long long v) { return atomicCAS(p, expect, v); }
+CPG_HD unsigned long long load_u64_volatile(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
+CPG_HD uint32_t load_u32_volatile(const uint32_t* p) { return *(const volatile uint32_t*)p; }
+CPG_HD void publish_u32(uint32_t* p, uint32_t v) { __threadfence(); *(volatile uint32_t*)p = v; }
+// index = counter++ for every thread with pred set, ONE atomic per warp
+CPG_HD uint32_t warp_agg_inc(uint32_t* counter, bool pred) {
+    const unsigned active = __activemask();
+    const unsigned m = __ballot_sync(active, pred);
+    if (!pred) return 0;
+    const int lane = (int)(threadIdx.x & 31), leader = __ffs((int)m) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+#else
+CPG_HD unsigned long long atomic_cas_u64(unsigned long long* p, unsigned long long expect, unsigned long long v) {
+    __atomic_compare_exchange_n(p, &expect, v, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE);
+    return expect;
+}
+CPG_HD unsigned long long load_u64_volatile(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+CPG_HD uint32_t load_u32_volatile(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+CPG_HD void publish_u32(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+CPG_HD uint32_t warp_agg_inc(uint32_t* counter, bool pred) { return pred ? __atomic_fetch_add(counter, 1u, __ATOMIC_RELAXED) : 0; }
+#endif
+
+struct PointCache {
+    uint32_t lg, max_probe;            // 2^lg slots
+    unsigned long long* tag;           // [slots] 0 = empty, else fingerprint | 1
+    unsigned long long* owner;         // [slots] launch id of the claimer
+    uint32_t* ready;                   // [slots] 1 once val / verr are valid
+    uint32_t* key;                     // [slots][12] the 48 encoded bytes
+    Aff* val;                          // [slots]
+    uint8_t* verr;                     // [slots] decode error code of the encoding (invalid encodings are cached too)
+    uint32_t* stats;                   // [0] slots claimed  [1] lookups  [2] lookups served from the table  (since the last reset)
+};
+enum { PC_NONE = 0, PC_OWN = 1, PC_FOLLOW = 2, PC_COPY = 3, PC_UNCACHED = 4 };
+
+struct PointSel {                      // which points of a [rows][row_pts] array of 48-byte encodings take part: the first `cached` of every row
+    uint64_t row_pts; uint32_t cached;
+    CPG_HD uint64_t index(uint64_t t) const { return (t / cached) * row_pts + t % cached; }
+};
+CPG_HD unsigned long long pc_hash(const uint32_t* w) {
+    unsigned long long h = 0x9e3779b97f4a7c15ULL;
+    for (int i = 0; i < 12; i += 2) {
+        unsigned long long v = (unsigned long long)w[i] | ((unsigned long long)w[i + 1] << 32);
+        h = (h ^ v) * 0xff51afd7ed558ccdULL;
+        h ^= h >> 32;
+    }
+    h *= 0xc4ceb9fe1a85ec53ULL;
+    h ^= h >> 29;
+    return h;
+}
+struct CacheClaim {
+    static constexpr const char* kName = "CacheClaim";
+    PointCache pc; PointSel sel; unsigned long long launch_id;
+    const uint32_t* in;                // encodings, 12 words each (16-byte aligned rows)
+    uint8_t* role; uint32_t* ref;      // per point (indexed like `in`)
+    CPG_HD void operator()(uint64_t t) const {
+        const uint64_t i = sel.index(t);
+        uint32_t w[12];
+        for (int k = 0; k < 12; k++) w[k] = in[12 * i + k];
+        const unsigned long long h = pc_hash(w), tg = h | 1ULL;
+        const uint32_t mask = (1u << pc.lg) - 1u;
+        uint32_t slot = (uint32_t)(h >> 20) & mask;
+        uint8_t r = PC_UNCACHED; uint32_t at = 0;
+        for (uint32_t p = 0; p < pc.max_probe; p++, slot = (slot + 1) & mask) {
+            unsigned long long cur = load_u64_volatile(pc.tag + slot);
+            if (cur == 0) {
+                cur = atomic_cas_u64(pc.tag + slot, 0ULL, tg);
+                if (cur == 0) {
+                    pc.owner[slot] = launch_id;
+                    for (int k = 0; k < 12; k++) pc.key[12 * (uint64_t)slot + k] = w[k];
+                    r = PC_OWN; at = slot;
+                    break;
+                }
+            }
+            if (cur == tg) { r = PC_FOLLOW; at = slot; break; }
+        }
+        role[i] = r; ref[i] = at;
+    }
+};
+struct CacheResolve {
+    static constexpr const char* kName = "CacheResolve";
+    PointCache pc; PointSel sel; unsigned long long launch_id;
+    uint32_t use_cache;                // 0: every point goes to the work list
+    uint32_t row_take;                 // points of every row that are decoded at all (the rest of the row is left alone)
+    const uint32_t* in; uint8_t* role; const uint32_t* ref;
+    uint32_t* todo; uint32_t* count;   // work list (out) and its length
+    CPG_HD void operator()(uint64_t t) const {
+        const uint64_t row = t / row_take, j = t % row_take, i = row * sel.row_pts + j;
+        bool need = true;
+        uint32_t claimed = 0, served = 0;
+        if (use_cache && j < sel.cached) {
+            uint8_t r = role[i];
+            if (r == PC_FOLLOW) {
+                const uint32_t slot = ref[i];
+                bool same = true;
+                for (int k = 0; k < 12; k++) same = same && pc.key[12 * (uint64_t)slot + k] == in[12 * i + k];
+                if (same && (load_u32_volatile(pc.ready + slot) != 0 || pc.owner[slot] == launch_id)) r = PC_COPY;
+                else r = PC_UNCACHED;                                    // fingerprint collision, or a slot another stream is still filling
+                role[i] = r;
+            }
+            need = r != PC_COPY;
+            claimed = r == PC_OWN; served = r == PC_COPY;
+        } else if (j < sel.cached) role[i] = PC_NONE;
+        const uint32_t at = warp_agg_inc(count, need);
+        if (need) todo[at] = (uint32_t)i;
+        if (use_cache) {                                                 // statistics (three warp-aggregated counters)
+            warp_agg_inc(pc.stats + 0, claimed != 0);
+            warp_agg_inc(pc.stats + 1, j < sel.cached);
+            warp_agg_inc(pc.stats + 2, served != 0);
+        }
+    }
+};
+struct DecompressList {                // launched over an upper bound of the list length; threads beyond *count leave at once
+    static constexpr const char* kName = "Decompress";                   // same work as Decompress: reported under its name
+    PointCache pc; uint32_t use_cache; uint32_t cached_per_row; uint64_t row_pts;
+    const uint8_t* in; const uint32_t* todo; const uint32_t* count;
+    const uint8_t* role; const uint32_t* ref;
+    Aff* out; uint8_t* err;
+    CPG_HD void operator()(uint64_t t) const {
+        if (t >= *count) return;
+        const uint64_t i = todo[t];
+        Aff a;
+        const int e = aff_decompress(in + 48 * i, false, &a);
+        out[i] = a; err[i] = (uint8_t)e;
+        if (use_cache && (i % row_pts) < cached_per_row && role[i] == PC_OWN) {
+            const uint32_t slot = ref[i];
+            pc.val[slot] = a; pc.verr[slot] = (uint8_t)e;
+            publish_u32(pc.ready + slot, 1u);
+        }
+    }
+};
+struct CacheFill {
+    static constexpr const char* kName = "CacheFill";
+    PointCache pc; PointSel sel; const uint8_t* role; const uint32_t* ref; Aff* out; uint8_t* err;
+    CPG_HD void operator()(uint64_t t) const {
+        const uint64_t i = sel.index(t);
+        if (role[i] != PC_COPY) return;
+        const uint32_t slot = ref[i];
+        out[i] = pc.val[slot]; err[i] = pc.verr[slot];
+    }
+};
+
 // ---- Fr vector ops on canonical little-endian words (K7) ------------------------------------
 struct FrBinary {                  // op 0 add, 1 sub, 2 mul
     static constexpr const char* kName = "FrBinary";

@@ -405,30 +405,28 @@ struct StreamScope {
 };
 
 struct Verifier {
+    // Sub-batch k owns three streams.  The transcript phases are one thread per proof: their duration is a LATENCY (a few
+    // hundred dependent Keccak permutations), the same for 2048 proofs as for 8192, and they need next to no issue slots.
+    // So they must never sit on the critical path of the integer-pipe kernels:
+    //   tstreams[k] (highest priority)  VerifyPhase1(k): needs only the wire bytes, starts right after the upload
+    //   streams[k]  (middle)            H2D(k) -> Decompress(k) -> [phase 1 done] -> D / A' -> VerifyPhase2(k)
+    //   mstreams[k] (lowest)            the MSM check of sub-batch k
+    // and the host enqueues EVERY sub-batch's first two rows before any check: all decompressions (and, under them, all
+    // transcript work) are through before the last MSM starts, so no MSM ever waits for a latency-bound kernel.
 #ifndef CPG_HOST_EMU
-    cudaStream_t streams[8] = {};
-    cudaEvent_t stream_done[8] = {};
+    cudaStream_t streams[8] = {}, tstreams[8] = {}, mstreams[8] = {};
+    cudaEvent_t stream_done[8] = {}, ev_up[8] = {}, ev_p1[8] = {}, ev_p2[8] = {};
 #else
-    void* streams[8] = {};
+    void *streams[8] = {}, *tstreams[8] = {}, *mstreams[8] = {};
 #endif
     int nstreams = 4;
-#ifndef CPG_HOST_EMU
-    cudaStream_t side_stream = nullptr;
-    cudaEvent_t side_ev[2] = {};
-    bool side_stream_ready() {
-        if (side_stream) return true;
-        if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess) { side_stream = nullptr; cudaGetLastError(); return false; }
-        for (int i = 0; i < 2; i++) if (cudaEventCreateWithFlags(&side_ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
-        return true;
-    }
-#else
-    bool side_stream_ready() { return false; }
-#endif
-    // make the caller's stream wait for every sub-batch stream (and vice versa at the start)
+    // make the caller's stream wait for every sub-batch (its check stream ends the chain)
     int join_streams(int rc) {
 #ifndef CPG_HOST_EMU
-        for (int i = 0; i < nstreams; i++) {
-            if (!streams[i]) continue;
+        for (int i = 0; i < 8; i++) {
+            if (!mstreams[i]) continue;
+            if (cudaEventRecord(stream_done[i], mstreams[i]) != cudaSuccess || cudaStreamWaitEvent(cur(), stream_done[i], 0) != cudaSuccess)
+                if (!rc) rc = fail("cpg_verify_batch: stream join failed");
             if (cudaEventRecord(stream_done[i], streams[i]) != cudaSuccess || cudaStreamWaitEvent(cur(), stream_done[i], 0) != cudaSuccess)
                 if (!rc) rc = fail("cpg_verify_batch: stream join failed");
         }
@@ -438,11 +436,17 @@ struct Verifier {
     int fork_streams() {
 #ifndef CPG_HOST_EMU
         // sub-batch streams start after whatever is already queued on the caller's stream
-        for (int i = 0; i < nstreams; i++) {
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);                 // numerically lower = more urgent
+        const int mid = greatest < least ? greatest + 1 : least;
+        for (int i = 0; i < 8 && i < (nstreams > 0 ? nstreams : 1); i++) {
             if (!streams[i]) {
-                if (cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&stream_done[i], cudaEventDisableTiming) != cudaSuccess)
+                if (cudaStreamCreateWithPriority(&streams[i], cudaStreamNonBlocking, mid) != cudaSuccess ||
+                    cudaStreamCreateWithPriority(&tstreams[i], cudaStreamNonBlocking, greatest) != cudaSuccess ||
+                    cudaStreamCreateWithPriority(&mstreams[i], cudaStreamNonBlocking, least) != cudaSuccess)
                     return fail("cpg_verify_batch: stream creation failed");
+                for (cudaEvent_t* e : {&stream_done[i], &ev_up[i], &ev_p1[i], &ev_p2[i]})
+                    if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return fail("cpg_verify_batch: event creation failed");
             }
             if (cudaEventRecord(stream_done[i], cur()) != cudaSuccess || cudaStreamWaitEvent(streams[i], stream_done[i], 0) != cudaSuccess)
                 return fail("cpg_verify_batch: stream fork failed");
@@ -484,12 +488,41 @@ struct Verifier {
     // pinned host staging (grown on demand)
     size_t hcap = 0;
     uint8_t *h_wire = nullptr, *h_psc = nullptr;
+    // cache of decompressed tracker points (cpg_verifier_set_cache; msm.cuh "PointCache"); off while pc.lg == 0
+    PointCache pc = {};
+    uint8_t* d_role = nullptr; uint32_t *d_ref = nullptr, *d_todo = nullptr, *d_count = nullptr;
+    unsigned long long launch_seq = 0;
+    uint64_t cache_total[3] = {0, 0, 0};   // lookups, lookups served from the table, slots claimed - since creation / cpg_verifier_cache_reset
+    void cache_free() {
+        for (void* q : {(void*)pc.tag, (void*)pc.owner, (void*)pc.ready, (void*)pc.key, (void*)pc.val, (void*)pc.verr, (void*)pc.stats}) cpg_free(q);
+        pc = PointCache{};
+    }
+    int cache_clear() {
+        if (!pc.lg) return 0;
+        const size_t slots = (size_t)1 << pc.lg;
+        if (int rc = cpg_memset(pc.tag, 0, slots * 8)) return rc;
+        if (int rc = cpg_memset(pc.ready, 0, slots * 4)) return rc;
+        return cpg_memset(pc.stats, 0, 3 * 4);
+    }
+    // before a batch: fold the device counters into the totals; start over with an empty table once it is half full
+    int cache_begin_batch() {
+        if (!pc.lg) return 0;
+        uint32_t st[3];
+        if (int rc = cpg_d2h(st, pc.stats, sizeof st)) return rc;
+        cache_total[0] += st[1]; cache_total[1] += st[2]; cache_total[2] += st[0];
+        cache_slots_used += st[0];
+        if (int rc = cpg_memset(pc.stats, 0, 3 * 4)) return rc;
+        if (cache_slots_used > ((size_t)1 << pc.lg) / 2) { cache_slots_used = 0; return cache_clear(); }
+        return 0;
+    }
+    size_t cache_slots_used = 0;
 
-    std::vector<void*> all() { return {d_wire, d_psc, d_err, d_derived, d_t0, d_vs, d_fs, d_ok, d_rej, d_chal, d_gok, d_gfs, d_bases, d_var, d_fix, d_gh, d_st, d_a, d_tmp}; }
+    std::vector<void*> all() { return {d_wire, d_psc, d_err, d_derived, d_t0, d_vs, d_fs, d_ok, d_rej, d_chal, d_gok, d_gfs, d_bases, d_var, d_fix, d_gh, d_st, d_a, d_tmp, d_role, d_ref, d_todo, d_count}; }
     void release() {
         for (void* q : all()) cpg_free(q);
         d_wire = d_psc = d_err = d_derived = d_t0 = d_vs = d_fs = d_ok = d_rej = d_chal = d_gok = d_gfs = nullptr;
         d_bases = nullptr; d_var = d_fix = d_gh = nullptr; d_st = nullptr; d_a = d_tmp = nullptr;
+        d_role = nullptr; d_ref = d_todo = d_count = nullptr;
         cap = 0;
     }
     int reserve(size_t B) {
@@ -513,6 +546,8 @@ struct Verifier {
         d_st = (VState*)cpg_malloc(sizeof(VState) * B);  d_a = (HFr*)cpg_malloc(sizeof(HFr) * B * sh.ell);
         d_tmp = (HFr*)cpg_malloc(sizeof(HFr) * B * 5 * sh.n);
         d_gok = (uint8_t*)cpg_malloc(B);                 d_gfs = (uint8_t*)cpg_malloc((B / 2 + 1) * NF * 32);
+        d_role = (uint8_t*)cpg_malloc(B * NV);           d_ref = (uint32_t*)cpg_malloc(B * NV * 4);
+        d_todo = (uint32_t*)cpg_malloc(B * NV * 4);      d_count = (uint32_t*)cpg_malloc(8 * 4);
         for (void* q : all()) if (!q) { release(); return fail("cpg_verify_batch: device allocation failed"); }
         cap = B;
         return 0;
@@ -526,8 +561,22 @@ struct Verifier {
         return vb;
     }
     // ---- the device side of proofs [b0, b0 + nb), in launch order (wire bytes already resident) ----
-    int device_decode(size_t b0, size_t nb) {
-        return cpg_g1_decompress(d_wire + b0 * sh.NV * 48, nb * sh.NV, 0, d_bases + b0 * sh.NV, d_err + b0 * sh.NV);
+    // `k` = which of the 8 work-list counters this sub-batch uses (its stream index)
+    int device_decode(size_t b0, size_t nb, size_t k = 0) {
+        if (!pc.lg) return cpg_g1_decompress(d_wire + b0 * sh.NV * 48, nb * sh.NV, 0, d_bases + b0 * sh.NV, d_err + b0 * sh.NV);
+        // cached path: the 4 ell tracker points of every proof go through the table, M and the proof's own points are
+        // decoded as they are (unique per proof); one compact work list holds everything that needs a square root
+        if (nb * (size_t)sh.NV >= 0xffffffffULL) return fail("cpg_verify_batch: sub-batch too large for the point cache");
+        const unsigned long long id = ++launch_seq;
+        const PointSel sel{sh.NV, 4 * sh.ell};
+        const uint32_t* in = (const uint32_t*)(d_wire + b0 * sh.NV * 48);
+        uint8_t* role = d_role + b0 * sh.NV; uint32_t* ref = d_ref + b0 * sh.NV; uint32_t* todo = d_todo + b0 * sh.NV; uint32_t* cnt = d_count + k;
+        Aff* out = d_bases + b0 * sh.NV; uint8_t* err = d_err + b0 * sh.NV;
+        if (int rc = cpg_memset(cnt, 0, 4)) return rc;
+        if (int rc = launch(CacheClaim{pc, sel, id, in, role, ref}, nb * sel.cached)) return rc;
+        if (int rc = launch(CacheResolve{pc, sel, id, 1u, sh.NV - 1, in, role, ref, todo, cnt}, nb * (size_t)(sh.NV - 1))) return rc;
+        if (int rc = launch_occ(DecompressList{pc, 1u, sel.cached, sh.NV, (const uint8_t*)in, todo, cnt, role, ref, out, err}, nb * (size_t)(sh.NV - 1))) return rc;
+        return launch(CacheFill{pc, sel, role, ref, out, err}, nb * sel.cached);
     }
     int device_derive(size_t b0, size_t nb, const Layout& L) {
         if (int rc = cpg_g1_msm_fixed_batched(table_gh, d_chal + b0 * 64, nb, 0, d_gh + b0)) return rc;
@@ -617,12 +666,10 @@ struct Verifier {
         if (int rc = launch(ScatterVerdicts{d_idx, var2, fix2, rej2, d_ok}, K)) return rc;
         return cpg_sync();                                               // idx (host) was read by an async copy
     }
-    // Transcript on the device: nothing crosses PCIe between the stages.  The batch is cut into
-    // sub-batches, each enqueued on its own stream, so the latency-bound kernels of one sub-batch
-    // (transcript phases, Horner, sort) run under the integer-pipe-bound kernels of the others.
-    // `upload` = also copy each sub-batch's wire bytes from the pinned staging buffers first; `stage` (optional)
-    // fills those buffers for proofs [b0, b0 + nb) right before their copy is enqueued, so the host stages
-    // sub-batch k + 1 while the GPU works on sub-batch k.
+    // Transcript on the device: nothing crosses PCIe between the stages.  The batch is cut into sub-batches on the
+    // three-stream scheme above.  `upload` = also copy each sub-batch's wire bytes from the pinned staging buffers first;
+    // `stage` (optional) fills those buffers for proofs [b0, b0 + nb) right before their copy is enqueued, so the host
+    // stages sub-batch k + 1 while the GPU works on sub-batch k.
     int device_all(size_t B, bool upload, const std::function<void(size_t, size_t)>& stage = nullptr) {
         const Layout L(sh.lg);
         VBuffers vb = device_buffers();
@@ -633,34 +680,41 @@ struct Verifier {
         size_t per = ((B + S - 1) / S + align - 1) / align * align;
         int rc = 0;
         size_t si = 0;
+        // rows 1 and 2 of every sub-batch
         for (size_t b0 = 0; b0 < B && !rc; b0 += per, si++) {
-            size_t nb = B - b0 < per ? B - b0 : per;
-            StreamScope scope(S > 1 ? streams[si % S] : nullptr);
+            const size_t nb = B - b0 < per ? B - b0 : per, k = si % 8;
+            StreamScope scope(streams[k]);
             if (upload && stage) stage(b0, nb);
             if (upload) {
                 rc = cpg_h2d(d_wire + b0 * sh.NV * 48, h_wire + b0 * sh.NV * 48, nb * sh.NV * 48);
                 if (!rc) rc = cpg_h2d(d_psc + b0 * 224, h_psc + b0 * 224, nb * 224);
             }
-            // phase 1 needs only the wire bytes: run it on a side stream under the decompression kernel
-            bool side = S == 1 && side_stream_ready();
 #ifndef CPG_HOST_EMU
-            if (!rc && side) {
-                if (cudaEventRecord(side_ev[0], cur()) != cudaSuccess || cudaStreamWaitEvent(side_stream, side_ev[0], 0) != cudaSuccess) side = false;
-            }
-            if (!rc && side) {
-                StreamScope sidescope(side_stream);
-                rc = launch<64>(VerifyPhase1{sh, L, vb, b0}, nb);
-                if (!rc && cudaEventRecord(side_ev[1], side_stream) != cudaSuccess) rc = fail("cpg_verify_batch: event record failed");
-            }
+            if (!rc && (cudaEventRecord(ev_up[k], cur()) != cudaSuccess || cudaStreamWaitEvent(tstreams[k], ev_up[k], 0) != cudaSuccess)) rc = fail("cpg_verify_batch: stream fork failed");
 #endif
-            if (!rc) rc = device_decode(b0, nb);
-            if (!rc && !side) rc = launch<64>(VerifyPhase1{sh, L, vb, b0}, nb);
+            if (!rc) {
+                StreamScope tscope(tstreams[k]);
+                rc = launch<64>(VerifyPhase1{sh, L, vb, b0}, nb);
 #ifndef CPG_HOST_EMU
-            if (!rc && side && cudaStreamWaitEvent(cur(), side_ev[1], 0) != cudaSuccess) rc = fail("cpg_verify_batch: stream join failed");
+                if (!rc && cudaEventRecord(ev_p1[k], cur()) != cudaSuccess) rc = fail("cpg_verify_batch: event record failed");
+#endif
+            }
+            if (!rc) rc = device_decode(b0, nb, k);
+#ifndef CPG_HOST_EMU
+            if (!rc && cudaStreamWaitEvent(cur(), ev_p1[k], 0) != cudaSuccess) rc = fail("cpg_verify_batch: stream join failed");
 #endif
             if (!rc) rc = device_derive(b0, nb, L);
             if (!rc) rc = launch<64>(VerifyPhase2{sh, L, vb, b0}, nb);
-            if (!rc) rc = device_check(b0, nb);
+#ifndef CPG_HOST_EMU
+            if (!rc && (cudaEventRecord(ev_p2[k], cur()) != cudaSuccess || cudaStreamWaitEvent(mstreams[k], ev_p2[k], 0) != cudaSuccess)) rc = fail("cpg_verify_batch: stream fork failed");
+#endif
+        }
+        // row 3: the checks
+        si = 0;
+        for (size_t b0 = 0; b0 < B && !rc; b0 += per, si++) {
+            const size_t nb = B - b0 < per ? B - b0 : per, k = si % 8;
+            StreamScope scope(mstreams[k]);
+            rc = device_check(b0, nb);
         }
         rc = join_streams(rc);
         if (!rc) rc = recheck_failed_groups(B);
@@ -813,11 +867,13 @@ int cpg_verifier_free(void* handle) {
     Verifier* v = (Verifier*)handle;
     v->release();
 #ifndef CPG_HOST_EMU
-    for (int i = 0; i < 8; i++) { if (v->streams[i]) cudaStreamDestroy(v->streams[i]); if (v->stream_done[i]) cudaEventDestroy(v->stream_done[i]); }
-    if (v->side_stream) cudaStreamDestroy(v->side_stream);
-    for (int i = 0; i < 2; i++) if (v->side_ev[i]) cudaEventDestroy(v->side_ev[i]);
+    for (int i = 0; i < 8; i++) {
+        for (cudaStream_t st : {v->streams[i], v->tstreams[i], v->mstreams[i]}) if (st) cudaStreamDestroy(st);
+        for (cudaEvent_t e : {v->stream_done[i], v->ev_up[i], v->ev_p1[i], v->ev_p2[i]}) if (e) cudaEventDestroy(e);
+    }
 #endif
     cpg_host_free(v->h_wire); cpg_host_free(v->h_psc);
+    v->cache_free();
     cpg_fixed_table_free(v->table);
     cpg_fixed_table_free(v->table_gh);
     for (void* t : v->shard_tables) cpg_fixed_table_free(t);
@@ -845,6 +901,44 @@ int cpg_verifier_set_group(void* handle, int group, int group_window) {
     v.group = group ? (uint32_t)group : 16; v.group_window = group_window;
     return 0;
 }
+/* Device-resident cache of decompressed tracker points (2^log2_slots entries of 160 B; 0 = off, the default). */
+int cpg_verifier_set_cache(void* handle, int log2_slots) {
+    if (!handle) return fail("cpg_verifier_set_cache: null verifier");
+    if (log2_slots != 0 && (log2_slots < 10 || log2_slots > 28)) return fail("cpg_verifier_set_cache: 0 (off) or 10..28");
+    Verifier& v = *(Verifier*)handle;
+    if (int rc = cpg_sync()) return rc;
+    v.cache_free();
+    v.cache_slots_used = 0;
+    if (!log2_slots) return 0;
+    const size_t slots = (size_t)1 << log2_slots;
+    PointCache pc{};
+    pc.lg = (uint32_t)log2_slots; pc.max_probe = 64;
+    pc.tag = (unsigned long long*)cpg_malloc(slots * 8); pc.owner = (unsigned long long*)cpg_malloc(slots * 8);
+    pc.ready = (uint32_t*)cpg_malloc(slots * 4); pc.key = (uint32_t*)cpg_malloc(slots * 48);
+    pc.val = (Aff*)cpg_malloc(slots * sizeof(Aff)); pc.verr = (uint8_t*)cpg_malloc(slots); pc.stats = (uint32_t*)cpg_malloc(3 * 4);
+    v.pc = pc;
+    if (!pc.tag || !pc.owner || !pc.ready || !pc.key || !pc.val || !pc.verr || !pc.stats) { v.cache_free(); return fail("cpg_verifier_set_cache: device allocation failed"); }
+    if (int rc = cpg_memset(pc.owner, 0, slots * 8)) return rc;
+    return v.cache_clear();
+}
+int cpg_verifier_cache_reset(void* handle) {
+    if (!handle) return fail("cpg_verifier_cache_reset: null verifier");
+    Verifier& v = *(Verifier*)handle;
+    if (int rc = cpg_sync()) return rc;
+    v.cache_slots_used = 0;
+    v.cache_total[0] = v.cache_total[1] = v.cache_total[2] = 0;
+    return v.cache_clear();
+}
+int cpg_verifier_cache_stats(void* handle, uint64_t* out3) {
+    if (!handle || !out3) return fail("cpg_verifier_cache_stats: null argument");
+    Verifier& v = *(Verifier*)handle;
+    out3[0] = v.cache_total[0]; out3[1] = v.cache_total[1]; out3[2] = v.cache_total[2];
+    if (!v.pc.lg) return 0;
+    uint32_t st[3];
+    if (int rc = cpg_d2h(st, v.pc.stats, sizeof st)) return rc;      // the batch in flight, not folded in yet
+    out3[0] += st[1]; out3[1] += st[2]; out3[2] += st[0];
+    return 0;
+}
 int cpg_verifier_group(const void* handle) { return handle ? (int)((const Verifier*)handle)->group : 0; }
 size_t cpg_verifier_rechecked(const void* handle) { return handle ? ((const Verifier*)handle)->rechecked : 0; }
 int cpg_verifier_set_transcript(void* handle, int mode) {
@@ -867,6 +961,7 @@ int cpg_verify_batch(void* handle, const uint8_t* inputs, const uint8_t* proofs,
     const Layout L(lg);
     const size_t in_len = (size_t)(NI - 1) * 48;
     if (int rc = v.reserve(B)) return rc;
+    if (int rc = v.cache_begin_batch()) return rc;
     v.lastB = B;
     v.transcript_on_device = v.device_transcript_for(B) ? 1 : 0;
 
@@ -929,6 +1024,7 @@ int cpg_verify_replay_device(void* handle, uint8_t* verdicts) {
     if (!handle) return fail("cpg_verify_replay_device: null verifier");
     Verifier& v = *(Verifier*)handle;
     if (!v.lastB) return fail("cpg_verify_replay_device: no batch resident");
+    if (int rc = v.cache_begin_batch()) return rc;
     if (v.transcript_on_device) {
         if (int rc = v.fork_streams()) return rc;
         if (int rc = v.device_all(v.lastB, false)) return rc;

@@ -97,6 +97,9 @@ _SIGS = {
     "cpg_verifier_set_transcript": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "cpg_verifier_set_streams": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "cpg_verifier_set_group": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int]),
+    "cpg_verifier_set_cache": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "cpg_verifier_cache_reset": (_c.c_int, [_c.c_void_p]),
+    "cpg_verifier_cache_stats": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_uint64)]),
     "cpg_verifier_rechecked": (_c.c_size_t, [_c.c_void_p]),
     "cpg_verifier_group": (_c.c_int, [_c.c_void_p]),
     "cpg_verify_batch": (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_char_p, _c.c_size_t, _c.c_char_p]),

@@ -57,6 +57,21 @@ class BatchVerifier:
     def rechecked(self):
         return int(self.lib.c.cpg_verifier_rechecked(self.handle))
 
+    def set_cache(self, log2_slots):
+        """Device-resident cache of decompressed tracker points keyed by their 48-byte encodings (0 = off): pre-shuffle
+        trackers of one Whisk shuffle are post-shuffle trackers of an earlier one, and duplicates inside a batch are
+        decompressed once.  2^log2_slots entries of 160 B."""
+        self.lib.check(self.lib.c.cpg_verifier_set_cache(self.handle, int(log2_slots)), "cpg_verifier_set_cache")
+
+    def cache_reset(self):
+        self.lib.check(self.lib.c.cpg_verifier_cache_reset(self.handle), "cpg_verifier_cache_reset")
+
+    def cache_stats(self):
+        """{lookups, served, claimed} since creation / cache_reset"""
+        out = (ctypes.c_uint64 * 3)()
+        self.lib.check(self.lib.c.cpg_verifier_cache_stats(self.handle, out), "cpg_verifier_cache_stats")
+        return {"lookups": int(out[0]), "served": int(out[1]), "claimed": int(out[2])}
+
     def verify_raw(self, inputs, proofs, B):
         """inputs: B*input_len bytes, proofs: B*proof_len bytes -> bytes of B verdicts."""
         out = ctypes.create_string_buffer(max(1, B))

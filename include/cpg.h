@@ -208,6 +208,16 @@ int cpg_verifier_set_streams(void* verifier, int nstreams);
 int cpg_verifier_set_group(void* verifier, int group, int group_window);
 size_t cpg_verifier_rechecked(const void* verifier);
 int cpg_verifier_group(const void* verifier);
+/* Device-resident cache of decompressed tracker points, keyed by their 48-byte encodings (default off).  In Whisk the
+ * pre-shuffle trackers of one shuffle proof are post-shuffle trackers of an earlier one (cp/whisk_interface.py:96-100
+ * decodes all 4*ell of them on every call): a verifier that has met a tracker already knows its square root, and a
+ * tracker that occurs several times in one batch is decompressed once.  Only the 4*ell tracker points of a proof go
+ * through the table (M and the proof's own points are unique per proof).  2^log2_slots entries of 160 bytes (10..28;
+ * 0 = off); open addressing, never evicts: the table starts over once it is half full.  Verdicts do not depend on it.
+ * cache_stats: out3 = {lookups, lookups served from the table, slots claimed} since creation / cache_reset. */
+int cpg_verifier_set_cache(void* verifier, int log2_slots);
+int cpg_verifier_cache_reset(void* verifier);
+int cpg_verifier_cache_stats(void* verifier, uint64_t* out3);
 int cpg_verify_batch(void* verifier, const uint8_t* inputs, const uint8_t* proofs, size_t B, uint8_t* verdicts);
 /* re-run the device side (decompress, D/A', MSM, test) of the last batch on its resident inputs */
 int cpg_verify_replay_device(void* verifier, uint8_t* verdicts_or_null);

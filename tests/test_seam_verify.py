@@ -25,6 +25,13 @@ def test_verify_batch_cross_proof_groups(seam_lib, on_device, group):
     vc.check_batch(seam_lib, "shuffle_N8_seed1234.json", transcript_on_device=on_device, fixed_window=4, group=group)
 
 
+@pytest.mark.parametrize("on_device,group", [(True, 1), (False, 1), (True, 2)])
+def test_tracker_cache_changes_no_verdict(seam_lib, on_device, group):
+    """decompressed trackers cached by their 48-byte encoding (hits, in-batch duplicates, malformed
+    encodings, table overflow) - verdicts equal the uncached ones lane by lane"""
+    vc.check_cache(seam_lib, "shuffle_N8_seed1234.json", transcript_on_device=on_device, group=group)
+
+
 def test_adaptive_group_size_follows_the_failure_rate(seam_lib):
     """group = 0: the library re-picks the group size after every batch (argmin of agg[G] + 1 - (1 - p)^G):
     all-valid batches drive it to 64, a batch where every second proof is bad drives it down to 2"""

@@ -98,3 +98,49 @@ def check_batch(lib, name, copies=1, window=0, transcript_on_device=True, fixed_
         assert ver.verify(ins, prs) == [i != group + 1 for i in range(nb)]
         assert ver.rechecked() == group
     ver.close()
+
+
+def check_cache(lib, name, log2_slots=12, transcript_on_device=True, group=1, streams=0, copies=3):
+    """The decompressed-tracker cache (cpg_verifier_set_cache) must not change a single verdict: the fixture's variants
+    (which share most trackers: duplicates inside the batch), a malformed tracker encoding (cached with its error code),
+    then the same batch again (served from the table), then a table so small that it overflows and starts over."""
+    case = sc.load_case(name)
+    ell = case["N"] - 4
+    ver = whisk.BatchVerifier(bytes.fromhex(case["crs"]), ell, lib=lib)
+    ver.set_transcript(transcript_on_device)
+    ver.set_group(group)
+    if streams:
+        ver.set_streams(streams)
+    vs = variants(case)
+    bad_enc = bytearray(vs[0][1]); bad_enc[48 * 3] &= 0x7F                      # vec_R[3]: compression flag missing
+    vs.append(("tracker:bad-encoding", bytes(bad_enc), vs[0][2], False))
+    vs = vs * copies
+    want = [v[3] for v in vs]
+    ins, prs = [v[1] for v in vs], [v[2] for v in vs]
+    assert ver.verify(ins, prs) == want                                          # cache off
+    ver.set_cache(log2_slots)
+    got = ver.verify(ins, prs)
+    assert got == want, [(v[0], g, w) for v, g, w in zip(vs, got, want) if g != w]
+    st1 = ver.cache_stats()
+    assert st1["lookups"] == len(vs) * 4 * ell and 0 < st1["claimed"] <= 5 * ell + 8, st1     # 4 ell distinct trackers + the few altered ones
+    # sub-batches on concurrent streams may meet a slot that another one is still filling: they decompress that point
+    # themselves (uncached) instead of waiting, so with several streams `served` is only bounded from above
+    if streams <= 1 or len(vs) < 64 * streams:
+        assert st1["served"] == st1["lookups"] - st1["claimed"], st1
+    else:
+        assert 0 < st1["served"] <= st1["lookups"] - st1["claimed"], st1
+    got = ver.verify(ins, prs)
+    assert got == want
+    st2 = ver.cache_stats()
+    assert st2["claimed"] == st1["claimed"] and st2["served"] - st1["served"] == len(vs) * 4 * ell, (st1, st2)   # all from the table
+    ver.cache_reset()
+    assert ver.cache_stats() == {"lookups": 0, "served": 0, "claimed": 0}
+    assert ver.verify(ins, prs) == want
+    # a table of 1024 slots with 4 ell = 496+ distinct keys per batch: more than half full after one batch -> it starts
+    # over before the next one, and probe sequences that run out fall back to plain decompression
+    ver.set_cache(10)
+    for _ in range(3):
+        assert ver.verify(ins, prs) == want
+    ver.set_cache(0)
+    assert ver.verify(ins, prs) == want
+    ver.close()
