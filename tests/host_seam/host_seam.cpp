@@ -13,6 +13,7 @@ void hs_fr_sqr(const uint32_t* a, uint32_t* r) { Fr x; memcpy(x.l, a, 32); Fr z 
 void hs_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fq x, y; memcpy(x.l, a, 48); memcpy(y.l, b, 48); Fq z = add(x, y); memcpy(r, z.l, 48); }
 void hs_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fq x, y; memcpy(x.l, a, 48); memcpy(y.l, b, 48); Fq z = sub(x, y); memcpy(r, z.l, 48); }
 void hs_fq_inv(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.l, a, 48); Fq z = fq_inv(x); memcpy(r, z.l, 48); }
+void hs_fq_inv_fermat(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.l, a, 48); Fq z = fq_inv_fermat(x); memcpy(r, z.l, 48); }
 void hs_fq_sqrt(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.l, a, 48); Fq z = fq_sqrt_candidate(x); memcpy(r, z.l, 48); }
 void hs_fq_to_mont(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.l, a, 48); Fq z = to_mont(x); memcpy(r, z.l, 48); }
 void hs_fq_from_mont(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.l, a, 48); Fq z = from_mont(x); memcpy(r, z.l, 48); }

@@ -73,3 +73,20 @@ def test_inverse_sqrt_montgomery_form(hs):
         assert y * y % P == sq
         k = rng.randrange(1, R)
         assert call(hs, "hs_fr_inv", 32, k * Rr % R) == pow(k, -1, R) * Rr % R
+
+
+def test_safegcd_inversion_matches_fermat_and_python(hs):
+    """fq_inv is the Bernstein-Yang division-step inversion on signed 30-bit limbs (field.cuh); cross-checked against
+    the Fermat exponentiation it replaced and against Python on carry-stressing limb patterns, 0 and the extremes"""
+    rng = random.Random(381)
+    Rq = pow(2, 384, P)
+    vals = patterns(P, 12, rng, 3000) + [P - 1, 1, 2, 3, (1 << 380), (1 << 381) % P, Rq, pow(Rq, -1, P)]
+    for am in vals:
+        got = call(hs, "hs_fq_inv", 48, am)
+        if am == 0:
+            assert got == 0
+            continue
+        a = am * pow(Rq, -1, P) % P                       # am is the Montgomery form of a
+        assert got == pow(a, -1, P) * Rq % P, hex(am)
+    for am in vals[:200]:
+        assert call(hs, "hs_fq_inv", 48, am) == call(hs, "hs_fq_inv_fermat", 48, am)
