@@ -31,6 +31,7 @@ thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 int g_device = -1;
 int g_msm_path = 0;          // cpg_msm_force_path: 0 = by shape, 1 = per-(msm, window) threads, 2 = per-term threads
+int g_msm_affine = 0;        // cpg_msm_set_accumulate: 0 = mixed XYZZ additions in the bucket accumulation (default: measured faster), 1 = batched affine additions
 std::mutex g_init_mu;
 Jac* g_generator = nullptr;  // device copy of the generator (Jacobian)
 
@@ -74,6 +75,13 @@ __global__ void __launch_bounds__(SORT_BLOCK) k_sort_digits_smem(SortDigits f, u
         uint16_t* grk = f.rank + t * (uint64_t)s.NB;
         for (uint32_t b = 0; b < s.NB; b++) grk[b] = rk[b];
     }
+}
+
+// BucketAccumulateAffine: every thread of the grid runs (the padding threads of the last block too, owning no buckets),
+// because its lanes vote on the loop exits (msm.cuh)
+__global__ void __launch_bounds__(128, 3) k_bucket_affine(const BucketAccumulateAffine f, uint64_t n) {
+    const uint64_t t = blockIdx.x * (uint64_t)128 + threadIdx.x;
+    f.run(t, t < n);
 }
 
 // ---- HornerJac for FEW MSMs: the 255 dependent doublings of one MSM's Horner pass on one thread are
@@ -199,6 +207,15 @@ int launch_sort_digits(const SortDigits& f, uint64_t n) {
     g_launches++;
     return ck(cudaGetLastError(), "kernel launch");
 }
+int launch_bucket_affine(const BucketAccumulateAffine& f, uint64_t n) {
+    if (!n) return 0;
+    ProfRec rec{BucketAccumulateAffine::kName, nullptr, nullptr, n};
+    if (g_prof_on) { cudaEventCreate(&rec.a); cudaEventCreate(&rec.b); cudaEventRecord(rec.a, cur()); }
+    k_bucket_affine<<<(unsigned)((n + 127) / 128), 128, 0, cur()>>>(f, n);
+    if (g_prof_on) { cudaEventRecord(rec.b, cur()); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back(rec); }
+    g_launches++;
+    return ck(cudaGetLastError(), "kernel launch");
+}
 int launch_horner_jac(const HornerJac& f, uint64_t n) {
     if (!n) return 0;
     if (n > 4096) return launch_occ(f, n);                 // many MSMs: throughput-bound, one thread each
@@ -227,6 +244,7 @@ int launch(const F& f, uint64_t n) {
 template <class F>
 int launch_occ(const F& f, uint64_t n) { return launch(f, n); }
 int launch_sort_digits(const SortDigits& f, uint64_t n) { return launch(f, n); }
+int launch_bucket_affine(const BucketAccumulateAffine& f, uint64_t n) { return launch(f, n); }
 int launch_horner_jac(const HornerJac& f, uint64_t n) { return launch(f, n); }
 void* scratch_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void scratch_free(void* p) { free(p); }
@@ -646,6 +664,11 @@ int cpg_msm_pick_window_batched(size_t B, size_t n) {
     const bool few = g_msm_path == 0 ? B * 32 < 8192 : g_msm_path == 2;
     return (int)((few || n > 2048) ? pick_window_large(n, B) : pick_window(n));
 }
+int cpg_msm_set_accumulate(int mode) {
+    if (mode < 0 || mode > 1) return fail("cpg_msm_set_accumulate: 0 (mixed XYZZ additions) or 1 (batched affine additions)");
+    g_msm_affine = mode;
+    return 0;
+}
 int cpg_msm_force_path(int path) {
     if (path < 0 || path > 2) return fail("cpg_msm_force_path: 0 (by shape), 1 (per-window threads) or 2 (per-term threads)");
     g_msm_path = path;
@@ -706,6 +729,23 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
     }
     // bound scratch to ~6 GiB per chunk of MSMs
     size_t per_msm = (size_t)s.wn * ((size_t)(s.NB + 1) * 8 + (size_t)n * 4 + (size_t)s.NB * (sizeof(Xyzz) + 6) + 2 * sizeof(Xyzz) * (lvl_elems + 1)) + (size_t)s.W * n * 2;
+    // batched affine accumulation: two scratch arrays of `cap` points per thread.  Per-window path: a thread owns a whole
+    // window, cap = (n + NB) / 2 always suffices.  Per-term path: a thread owns bpt buckets holding ~512 points at the
+    // density of the densest window (the top window has only tw bits: 2^tw non-empty buckets).
+    const bool affine = g_msm_affine != 0;
+    uint32_t bpt = s.NB, cap = (uint32_t)((n + s.NB) / 2 + 1);
+    if (affine && large) {
+        const int tw = 255 - (int)c * ((int)rc.W - 1);
+        const double top_buckets = tw >= (int)c - 1 ? (double)s.NB : (double)(1u << (tw > 0 ? tw : 0));
+        const double dens = (double)n / (slice && !(w0 + wn == rc.W) ? (double)s.NB : std::min((double)s.NB, top_buckets));
+        bpt = 1; while (bpt < s.NB && (double)(2 * bpt) * dens <= 512.0) bpt *= 2;
+        // ... but not so many that the launch cannot fill the GPU (two waves of 148 SMs x 3 blocks x 128 threads),
+        // as long as a thread keeps ~128 points (fewer, and the shared inversions stop paying)
+        while (bpt > 1 && (double)B * s.wn * (s.NB / bpt) < 2.0 * 148 * 3 * 128 && (double)(bpt / 2) * dens >= 128.0) bpt /= 2;
+        const double pts = (double)bpt * dens;
+        cap = (uint32_t)((pts + 6.0 * std::sqrt(pts) + 32.0 + bpt) / 2.0) + 1;
+    }
+    if (affine) per_msm += (size_t)s.wn * (s.NB / bpt) * cap * 2 * sizeof(Aff);
     size_t chunk = (size_t)6 << 30;
     chunk = chunk / per_msm; if (chunk < 1) chunk = 1; if (chunk > B) chunk = B;
     if (large) while (chunk > 1 && (uint64_t)chunk * s.wn * s.NB >= 0xffffffffULL) chunk /= 2;
@@ -717,7 +757,7 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
         Scratch sc;
         uint32_t* boff = sc.get<uint32_t>(BW * (s.NB + 1));
         uint32_t* sorted = sc.get<uint32_t>(BW * n);
-        const bool balanced = !large;
+        const bool balanced = !large && !affine;                    // length ranks: only the XYZZ accumulation (thread = bucket) uses them
         uint16_t* rank = balanced ? sc.get<uint16_t>(BW * s.NB) : nullptr;
         if (balanced && !rank) return fail("cpg_g1_msm_batched: scratch allocation failed");
         Xyzz* buckets = sc.get<Xyzz>(BW * s.NB);
@@ -731,8 +771,15 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
             Xyzz* wsum = sc.get<Xyzz>(BW);
             if (!wsum) return fail("cpg_g1_msm_batched: scratch allocation failed");
             if (int r = launch_sort_digits(SortDigits{s, dig, boff, sorted, rank}, BW)) return r;
-            uint64_t nthreads = (((uint64_t)nb + 31) / 32) * 32 * s.wn * s.NB;
-            if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, rank, nullptr, BW, buckets}, nthreads)) return r;
+            if (affine) {
+                const uint64_t T = (((uint64_t)nb + 31) / 32) * 32 * s.wn;
+                Aff* bufA = sc.get<Aff>(T * cap); Aff* bufB = sc.get<Aff>(T * cap);
+                if (!bufA || !bufB) return fail("cpg_g1_msm_batched: scratch allocation failed");
+                if (int r = launch_bucket_affine(BucketAccumulateAffine{s, bases, boff, sorted, BW, s.NB, 1u, cap, T, bufA, bufB, buckets}, T)) return r;
+            } else {
+                uint64_t nthreads = (((uint64_t)nb + 31) / 32) * 32 * s.wn * s.NB;
+                if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, rank, nullptr, BW, buckets}, nthreads)) return r;
+            }
             if (int r = launch_occ(WindowReduce{s, buckets, wsum}, BW)) return r;
             if (int r = launch_occ(Horner{s, wsum, (Jac*)d_out + b0}, nb)) return r;
             continue;
@@ -754,11 +801,18 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
         if (int r = launch(LargeScanTop{nsc, ctot}, BW)) return r;
         if (int r = launch(LargeScanApply{s, sch, nsc, cnt, ctot, boff}, BW * nsc)) return r;
         if (int r = launch(LargeScatter{s, dig, boff, cnt, sorted}, (uint64_t)nb * n)) return r;
-        // buckets by list length, longest first
-        if (int r = launch(LenHist{s, boff, hist}, BW * s.NB)) return r;
-        if (int r = launch(LenScan{hist}, 1)) return r;
-        if (int r = launch(LenScatter{s, boff, hist, order}, BW * s.NB)) return r;
-        if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, nullptr, order, BW, buckets}, BW * s.NB)) return r;
+        if (affine) {
+            const uint64_t T = BW * (s.NB / bpt);
+            Aff* bufA = sc.get<Aff>(T * cap); Aff* bufB = sc.get<Aff>(T * cap);
+            if (!bufA || !bufB) return fail("cpg_g1_msm_batched: scratch allocation failed");
+            if (int r = launch_bucket_affine(BucketAccumulateAffine{s, bases, boff, sorted, BW, bpt, 0u, cap, T, bufA, bufB, buckets}, T)) return r;
+        } else {
+            // buckets by list length, longest first
+            if (int r = launch(LenHist{s, boff, hist}, BW * s.NB)) return r;
+            if (int r = launch(LenScan{hist}, 1)) return r;
+            if (int r = launch(LenScatter{s, boff, hist, order}, BW * s.NB)) return r;
+            if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, nullptr, order, BW, buckets}, BW * s.NB)) return r;
+        }
         // level-wise window reduction
         const Xyzz* in = buckets; Xyzz* out = lvA;
         uint32_t len = s.NB;

@@ -280,7 +280,13 @@ CPG_HD Fq fq_inv_safegcd(const Fq& a) {               // a and the result in Mon
         int32_t nz = 0;
 #pragma unroll
         for (int i = 0; i < 13; i++) nz |= g.v[i];
+        // the lanes of a warp leave together (a lane whose g is already 0 idles through harmless extra rounds:
+        // t = diag(2^30, 1) leaves f and d as they are) - lanes that drift apart here rarely rejoin
+#ifdef __CUDA_ARCH__
+        if (!__any_sync(__activemask(), nz != 0)) break;
+#else
         if (nz == 0) break;
+#endif
     }
     fq_normalize30(d, f.v[12]);                         // d = +-(a R)^-1 with the sign of f = +-1
     Fq x;                                               // back to 12 x 32-bit words

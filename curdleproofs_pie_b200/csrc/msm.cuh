@@ -180,6 +180,163 @@ struct BucketAccumulate {
     }
 };
 
+// 2' -- the same bucket sums by BATCHED AFFINE additions ---------------------------------------------
+// An affine addition costs one division: lambda = (y2 - y1) / (x2 - x1), x3 = lambda^2 - x1 - x2,
+// y3 = lambda (x1 - x3) - y1.  With Montgomery's trick K independent additions share ONE inversion (field.cuh: ~4 k wide
+// multiplies) and each costs 5 products + 1 squaring (forward prefix product, two back-substitution products, lambda,
+// lambda^2, y3) instead of the 8 + 2 of the mixed XYZZ addition above.  The additions of a bucket are made independent
+// by summing it as a pairwise tree: round r pairs up neighbours inside every bucket, so a thread that owns a run of
+// buckets (~500 points: a whole window of a Whisk-size MSM, or a few buckets of a large one) has hundreds of
+// independent additions per round, K = BA_K of them per inversion.  Rounds ping-pong between two scratch arrays laid
+// out [slot][thread] (a warp's access to one slot is one contiguous run of records); round 0 reads the bases through
+// the sorted term list.  Exceptional pairs (P + P, P + (-P), an identity operand) are resolved by flag, they neither
+// divide nor stall the others.  A thread whose run would not fit its scratch slots (badly skewed digits) sums its
+// buckets with the XYZZ chain instead.  Buckets leave as XYZZ points with ZZ = ZZZ = 1: the reductions are unchanged.
+constexpr uint32_t BA_K = 32;        // additions per shared inversion
+constexpr uint32_t BA_MIN = 6;       // a round with fewer additions than this is not worth an inversion: finish with XYZZ chains
+struct BucketAccumulateAffine {
+    static constexpr const char* kName = "BucketAccumulateAffine";
+    MsmShape s;
+    const Aff* bases;
+    const uint32_t* boff;
+    const uint32_t* sorted;
+    uint64_t BW;                  // (msm, window) pairs of the launch
+    uint32_t bpt;                 // buckets per thread (divides NB)
+    uint32_t lane_msm;            // 1: bpt = NB and a warp is ONE window of 32 consecutive MSMs (lane = msm; T = ceil32(B) wn), 0: t = (mw, run of buckets)
+    uint32_t cap;                 // scratch slots per thread in each of the two arrays
+    uint64_t T;                   // threads of the launch (the scratch stride)
+    Aff* bufA; Aff* bufB;         // [cap][T]
+    Xyzz* buckets;                // [BW][NB] (out)
+    struct Src {                  // where round r reads its points
+        const Aff* P; const uint32_t* lst; const Aff* buf; uint64_t T, t;
+        CPG_HD Aff at(uint32_t i) const {
+            if (lst) { const uint32_t e = lst[i]; return cneg(P[e & 0x7fffffffu], (e >> 31) != 0); }
+            return buf[(uint64_t)i * T + t];
+        }
+    };
+    // Warp discipline (device): all 32 lanes run the round / batch loops the same number of times (votes decide when a
+    // batch is flushed and when a round or the whole tree ends) and meet again after every data-dependent stretch.  Left
+    // to themselves the lanes drift apart at the first bucket boundary and never rejoin: ncu showed 9.4 of 32 lanes
+    // active per issued instruction and the kernel 4x slower than the XYZZ one.  k_bucket_affine (cpg_api.cu) therefore
+    // calls run() for EVERY thread of the grid, `valid` = false for the padding threads, which own no buckets.
+#ifdef __CUDA_ARCH__
+    static __device__ __forceinline__ bool any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+    static __device__ __forceinline__ void rejoin() { __syncwarp(); }
+#else
+    static bool any(bool p) { return p; }
+    static void rejoin() {}
+#endif
+    CPG_HD void operator()(uint64_t t) const { run(t, true); }
+    CPG_HD void run(uint64_t t, bool valid) const {
+        uint64_t mw = 0; uint32_t b0 = 0;
+        if (lane_msm) {
+            const uint32_t lane = (uint32_t)(t % 32);
+            const uint64_t q = t / 32;
+            const uint32_t w = (uint32_t)(q % s.wn);
+            const uint64_t msm = (q / s.wn) * 32 + lane;
+            if (msm >= s.B) valid = false;
+            else mw = msm * s.wn + w;
+        } else if (valid) {
+            const uint32_t per = s.NB / bpt;
+            mw = t / per; b0 = (uint32_t)(t % per) * bpt;
+        }
+        const uint32_t nbk = valid ? bpt : 0;                                  // buckets of this thread
+        const uint32_t m = (uint32_t)(mw / s.wn);
+        const uint32_t* off = boff + mw * (uint64_t)(s.NB + 1) + b0;          // off[0 .. bpt]
+        const uint32_t* lst = sorted + mw * (uint64_t)s.n;
+        const Aff* P = bases + (valid ? (s.base_off ? (uint64_t)s.base_off[m] : (uint64_t)m * s.base_stride) : 0);
+        Xyzz* outb = buckets + mw * (uint64_t)s.NB + b0;
+        const uint32_t first = valid ? off[0] : 0;
+        uint32_t need = 0;
+        for (uint32_t b = 0; b < nbk; b++) need += (off[b + 1] - off[b] + 1) >> 1;
+        const bool fits = need <= cap;                                         // else: XYZZ chains for this thread's buckets
+        Src src{P, lst + first, nullptr, T, t};
+        uint32_t r = 0;                                                        // rounds done: bucket b now holds (len_b + 2^r - 1) >> r points
+        Aff* out = bufA; Aff* other = bufB;
+        for (;; r++) {
+            uint32_t adds = 0;
+            if (fits) for (uint32_t b = 0; b < nbk; b++) adds += ((off[b + 1] - off[b] + (1u << r) - 1) >> r) >> 1;
+            if (!any(adds >= BA_MIN)) break;                                   // the warp goes on while one lane still has a round worth an inversion
+            // one round: pairs inside every bucket, BA_K of them per inversion
+            Fq pre[BA_K]; uint32_t sa[BA_K], da[BA_K];                          // prefix products; source index of the pair; destination index | flag << 30
+            uint32_t cnt = 0, in_pos = 0, out_pos = 0;
+            Fq acc = fq_one();
+            const uint32_t nb_r = fits ? nbk : 0;
+            uint32_t b = 0, j = 0, L = nb_r ? (off[1] - off[0] + (1u << r) - 1) >> r : 0;
+            for (;;) {
+                // next pair of this lane (or the end of its round)
+                bool have = false;
+                while (b < nb_r) {
+                    if (j + 1 < L) { have = true; break; }
+                    if (j < L) out[(uint64_t)(out_pos + (j >> 1)) * T + t] = src.at(in_pos + j);      // odd one out: passes through
+                    in_pos += L; out_pos += (L + 1) >> 1;
+                    b++; j = 0;
+                    if (b < nb_r) L = (off[b + 1] - off[b] + (1u << r) - 1) >> r;
+                }
+                rejoin();
+                const bool anyhave = any(have);
+                if (have) {
+                    const Aff A = src.at(in_pos + j), B = src.at(in_pos + j + 1);
+                    uint32_t flag = 0;                                            // 0 generic, 1 doubling, 2 sum is the identity, 3 an operand is the identity
+                    Fq den = fq_one();
+                    if (is_inf(A) || is_inf(B)) flag = 3;
+                    else {
+                        den = sub(B.x, A.x);
+                        if (den.is_zero()) {
+                            if (A.y == B.y && !A.y.is_zero()) { flag = 1; den = dbl(A.y); }
+                            else { flag = 2; den = fq_one(); }
+                        }
+                    }
+                    pre[cnt] = acc;
+                    acc = mul(acc, den);
+                    sa[cnt] = in_pos + j; da[cnt] = (out_pos + (j >> 1)) | (flag << 30);
+                    cnt++; j += 2;
+                }
+                rejoin();
+                if (any(cnt == BA_K) || !anyhave) {                               // lanes still pairing all hold the same count; the others flush what they have
+                    Fq inv = fq_inv(acc);
+                    for (uint32_t k = BA_K; k-- > 0;) {
+                        if (!any(k < cnt)) continue;
+                        if (k < cnt) {
+                            const Aff A = src.at(sa[k]), B = src.at(sa[k] + 1);
+                            const uint32_t flag = da[k] >> 30;
+                            Aff R;
+                            if (flag == 3) R = is_inf(A) ? B : A;
+                            else if (flag == 2) R = aff_inf();
+                            else {
+                                Fq den, num;
+                                if (flag == 0) { den = sub(B.x, A.x); num = sub(B.y, A.y); }
+                                else { den = dbl(A.y); Fq xx = sqr(A.x); num = add(dbl(xx), xx); }
+                                const Fq li = mul(inv, pre[k]);
+                                inv = mul(inv, den);
+                                const Fq lam = mul(num, li);
+                                R.x = sub(sub(sqr(lam), A.x), B.x);
+                                R.y = sub(mul(lam, sub(A.x, R.x)), A.y);
+                            }
+                            out[(uint64_t)(da[k] & 0x3fffffffu) * T + t] = R;
+                        }
+                        rejoin();
+                    }
+                    cnt = 0; acc = fq_one();
+                }
+                if (!anyhave) break;
+            }
+            if (fits) { src.lst = nullptr; src.buf = out; }
+            Aff* tmp = out; out = other; other = tmp;
+        }
+        // what is left of every bucket (one point after enough rounds; everything if the run did not fit): XYZZ chain
+        uint32_t in_pos = 0;
+        const uint32_t rr = fits ? r : 0;
+        for (uint32_t b = 0; b < nbk; b++) {
+            const uint32_t L = (off[b + 1] - off[b] + (1u << rr) - 1) >> rr;
+            Xyzz acc = xyzz_inf();
+            for (uint32_t j = 0; j < L; j++) acc = xyzz_add_mixed(acc, src.at(in_pos + j));
+            outb[b] = acc;
+            in_pos += L;
+        }
+    }
+};
+
 // 3 --- one window: sum_b (b+1) * S_b by running sums ---------------------------------------
 struct WindowReduce {
     static constexpr const char* kName = "WindowReduce";

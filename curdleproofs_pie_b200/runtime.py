@@ -61,6 +61,7 @@ _SIGS = {
     "cpg_g1_msm_batched_off": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_void_p]),
     "cpg_msm_pick_window": (_c.c_int, [_c.c_size_t]),
     "cpg_msm_force_path": (_c.c_int, [_c.c_int]),
+    "cpg_msm_set_accumulate": (_c.c_int, [_c.c_int]),
     "cpg_msm_pick_window_batched": (_c.c_int, [_c.c_size_t, _c.c_size_t]),
     "cpg_msm_window_count": (_c.c_int, [_c.c_size_t, _c.c_int]),
     "cpg_g1_msm_window_sums": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),

@@ -106,6 +106,12 @@ int cpg_g1_msm_batched_off(const void* d_bases_aff, const uint32_t* d_base_off, 
  * thread per (msm, window) for the sort/reduce stages, few or large MSMs run one thread per term with
  * atomics, length-ordered buckets and a level-wise window reduction; 1 / 2 force either (tests, tuning). */
 int cpg_msm_force_path(int path);
+/* How the bucket accumulation adds: 0 (default) = one mixed XYZZ addition per term (8 products + 2 squarings), one thread
+ * per bucket; 1 = batched affine additions - a thread sums a run of buckets as pairwise trees, 32 independent additions
+ * sharing one Fq inversion (5 products + 1 squaring per addition: 39 % fewer multiply-accumulates).  Results are
+ * identical.  Measured on B200 the affine kernel is SLOWER (it issues more instructions per addition and stalls on its
+ * gathers: DESIGN.md section 4, profiles/r02_ncu_bucket_affine_*), so it is kept as a tested alternative, not the default. */
+int cpg_msm_set_accumulate(int mode);
 /* Window split of ONE large MSM (BASELINE configs 2 and 5): the W = cpg_msm_window_count
  * windows are independent; a rank computes the Jacobian window sums S_w of its slice, the slices are
  * exchanged by one small all-gather (W * 144 B in total), and every rank finishes with

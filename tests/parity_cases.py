@@ -202,3 +202,21 @@ def case_msm_large(lib, cref, n, window, seed=8, slices=3):
     res = lib.alloc(rt.JAC)
     lib.check(lib.c.cpg_g1_msm_combine_windows(wsums.ptr, c, res.ptr), "cpg_g1_msm_combine_windows")
     assert split48(lib.compress_jac(res, 1)) == [want]
+
+
+def case_msm_skewed(lib, cref, n, window, seed=9):
+    """Every term carries the same scalar: each window has ONE non-empty bucket holding all n terms - the run of a
+    batched-affine thread overflows its scratch slots and must fall back to the XYZZ chain; a second instance uses two
+    scalars (half / half), and identical bases throughout a bucket (doubling at every level of the pairwise tree)."""
+    rng = random.Random(seed * 31 + n)
+    blobs, enc = rand_points(cref, rng, 8, with_identity=False)
+    k1, k2 = rng.randrange(R), rng.randrange(R)
+    for bases_idx, ks in (([i % 8 for i in range(n)], [k1] * n),
+                          ([i % 8 for i in range(n)], [k1 if i < n // 2 else k2 for i in range(n)]),
+                          ([0] * n, [k1] * n)):
+        aff, _ = upload_points(lib, [enc[i] for i in bases_idx])
+        out = lib.msm_batched(aff, 0, lib.upload(rt.scalars_to_bytes(ks)), 1, n, window)
+        agg = [0] * 8
+        for i, k in zip(bases_idx, ks):
+            agg[i] = (agg[i] + k) % R
+        assert split48(lib.compress_jac(out, 1)) == [cref.compress(cref.msm(blobs, agg))], (n, window)

@@ -51,6 +51,33 @@ def test_msm_edges(gpu_lib, cref):
     pc.case_msm(gpu_lib, cref, 5, 128, 0, shared=True, edge=True)
 
 
+@pytest.mark.parametrize("accumulate", [0, 1])
+@pytest.mark.parametrize("path,n,window", [(2, 5000, 0), (1, 600, 7), (2, 20000, 12), (2, 64, 0)])
+def test_msm_skewed_digits(gpu_lib, cref, path, n, window, accumulate):
+    gpu_lib.check(gpu_lib.c.cpg_msm_force_path(path))
+    gpu_lib.check(gpu_lib.c.cpg_msm_set_accumulate(accumulate))
+    try:
+        pc.case_msm_skewed(gpu_lib, cref, n, window)
+    finally:
+        gpu_lib.check(gpu_lib.c.cpg_msm_force_path(0))
+        gpu_lib.check(gpu_lib.c.cpg_msm_set_accumulate(0))
+
+
+@pytest.mark.parametrize("B,n,window,shared", [(64, 128, 0, False), (8, 627, 7, False), (2, 3000, 9, False), (1, 40000, 0, False)])
+def test_msm_batched_affine_accumulation_matches(gpu_lib, cref, B, n, window, shared):
+    """cpg_msm_set_accumulate(1): bucket sums by batched affine additions (pairwise trees, 32 additions per shared
+    inversion, warp-converged) - an alternative to the default mixed-XYZZ accumulation, same bytes"""
+    gpu_lib.check(gpu_lib.c.cpg_msm_set_accumulate(1))
+    try:
+        if n > 5000:
+            pc.case_msm_large(gpu_lib, cref, n, window)
+        else:
+            pc.case_msm(gpu_lib, cref, B, n, window, shared)
+            pc.case_msm(gpu_lib, cref, 6, 40, 4, shared=False, edge=True)
+    finally:
+        gpu_lib.check(gpu_lib.c.cpg_msm_set_accumulate(0))
+
+
 def test_msm_empty(gpu_lib):
     out = gpu_lib.msm_batched(gpu_lib.alloc(96), 0, gpu_lib.alloc(32), 2, 0)
     assert gpu_lib.is_identity(out, 2) == [1, 1]

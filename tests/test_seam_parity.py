@@ -23,19 +23,24 @@ def test_msm(seam_lib, cref, B, n, window, shared):
     pc.case_msm(seam_lib, cref, B, n, window, shared)
 
 
+@pytest.mark.parametrize("accumulate", [0, 1])
 @pytest.mark.parametrize("path", [1, 2])
-@pytest.mark.parametrize("B,n,window,shared", [(3, 16, 0, False), (2, 33, 5, True), (2, 7, 2, False), (1, 40, 8, False)])
-def test_msm_both_pipelines(seam_lib, cref, B, n, window, shared, path):
+@pytest.mark.parametrize("B,n,window,shared", [(3, 16, 0, False), (2, 33, 5, True), (2, 7, 2, False), (1, 40, 8, False), (2, 200, 3, False)])
+def test_msm_both_pipelines(seam_lib, cref, B, n, window, shared, path, accumulate):
     """path 1 = one thread per (msm, window) (the batched-proofs pipeline), 2 = per-term threads with the
-    level-wise reduction (single / large MSMs); by shape these small batches would all take path 2"""
+    level-wise reduction (single / large MSMs); by shape these small batches would all take path 2.
+    accumulate 0 = mixed XYZZ additions, 1 = batched affine additions (pairwise trees, shared inversions)"""
     seam_lib.check(seam_lib.c.cpg_msm_force_path(path))
+    seam_lib.check(seam_lib.c.cpg_msm_set_accumulate(accumulate))
     try:
         pc.case_msm(seam_lib, cref, B, n, window, shared)
         # zero scalars, k = r - 1, identity bases, P and -P / the same base twice in one bucket
         pc.case_msm(seam_lib, cref, 4, 12, 4, shared=False, edge=True)
         pc.case_msm(seam_lib, cref, 3, 12, 3, shared=True, edge=True)
+        pc.case_msm(seam_lib, cref, 2, 90, 2, shared=True, edge=True)        # 2 buckets per window: long lists of equal / opposite points
     finally:
         seam_lib.check(seam_lib.c.cpg_msm_force_path(0))
+        seam_lib.check(seam_lib.c.cpg_msm_set_accumulate(0))
 
 
 def test_msm_edges(seam_lib, cref):
@@ -60,6 +65,23 @@ def test_fr(seam_lib):
     pc.case_fr(seam_lib, 16)
 
 
+@pytest.mark.parametrize("accumulate", [0, 1])
 @pytest.mark.parametrize("n,window", [(2100, 5), (300, 10), (2500, 9), (600, 16), (3000, 0)])
-def test_msm_large_and_window_slices(seam_lib, cref, n, window):
-    pc.case_msm_large(seam_lib, cref, n, window)
+def test_msm_large_and_window_slices(seam_lib, cref, n, window, accumulate):
+    seam_lib.check(seam_lib.c.cpg_msm_set_accumulate(accumulate))
+    try:
+        pc.case_msm_large(seam_lib, cref, n, window)
+    finally:
+        seam_lib.check(seam_lib.c.cpg_msm_set_accumulate(0))
+
+
+@pytest.mark.parametrize("accumulate", [0, 1])
+@pytest.mark.parametrize("path,n,window", [(2, 700, 6), (1, 300, 4), (2, 64, 0)])
+def test_msm_skewed_digits(seam_lib, cref, path, n, window, accumulate):
+    seam_lib.check(seam_lib.c.cpg_msm_force_path(path))
+    seam_lib.check(seam_lib.c.cpg_msm_set_accumulate(accumulate))
+    try:
+        pc.case_msm_skewed(seam_lib, cref, n, window)
+    finally:
+        seam_lib.check(seam_lib.c.cpg_msm_force_path(0))
+        seam_lib.check(seam_lib.c.cpg_msm_set_accumulate(0))

@@ -133,7 +133,7 @@ def main():
             if bm["wide"] >= 100:
                 lines.append("    sub @0x%04x  called from %3d sites  %5d instrs  wide %4d  narrow %3d  iadd %3d  mem %d   %s" % (
                     t, ncalls, bm["total"], bm["wide"], bm["imad_narrow"], bm["iadd"], bm["global_mem"] + bm["local_mem"], classify(bm)))
-                if k.startswith("BucketAccumulate"):
+                if k == "BucketAccumulate<128,3>":
                     sub_dump.append((t, ncalls, body, bm))
     lines.append("%-28s %8d %8d %6.1f%% %7d %7d %7d %7d %7d %6d %6d %6d" % (
         "ALL", tot["total"], tot["wide"], 100.0 * tot["wide"] / max(1, tot["total"]), tot["imad_narrow"], tot["iadd"], tot["global_mem"], tot["local_mem"], tot["shared_mem"], tot["shfl"], tot["call"], tot["tensor_or_tma"]))
