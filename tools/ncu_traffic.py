@@ -2,7 +2,10 @@
 """DRAM traffic per launch of the kernels in an `ncu --set full` capture -> profiles/r02_ncu_traffic.json, the file
 bench.py's `roofline.traffic` reads (no hard-coded constant).
 
-    python tools/ncu_traffic.py gpurun_out/<capture>.ncu-rep [more.ncu-rep ...] [--points-per-launch N]
+    python tools/ncu_traffic.py gpurun_out/<capture>.ncu-rep [more.ncu-rep ...] [--units Kernel=N ...]
+
+--units Decompress=2097152 records how many units (points, additions) ONE captured launch processed, so that bench.py can
+scale the measured bytes to the size of its own launches (bytes per unit x its units per launch).
 
 For every captured launch: dram__bytes_read.sum + dram__bytes_write.sum, its duration, the SM-busy / pipe metrics that
 the DESIGN's layout decision cites (LSU utilisation, long-scoreboard stalls), keyed by the functor name
@@ -57,7 +60,14 @@ def read(rep):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    args, units = [], {}
+    it = iter(sys.argv[1:])
+    for a in it:
+        if a == "--units":
+            k, v = next(it).split("=")
+            units[k] = float(v)
+        else:
+            args.append(a)
     launches = []
     for rep in args:
         for ent in read(rep):
@@ -78,6 +88,9 @@ def main():
                 a[key] /= n
         a["dram_bytes_per_launch"] = a.get("dram_read_bytes", 0.0) + a.get("dram_write_bytes", 0.0)
         a["note"] = "ncu --set full, mean of %d captured launch(es) in %s" % (n, a["capture"])
+        if k in units:
+            a["units_per_launch"] = units[k]
+            a["dram_bytes_per_unit"] = a["dram_bytes_per_launch"] / units[k]
     prev = {}
     if os.path.exists(OUT):
         with open(OUT) as f:
