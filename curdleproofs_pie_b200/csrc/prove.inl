@@ -644,7 +644,7 @@ struct ProverLane {
         return 0;
     }
 };
-constexpr int P_MAX_LANES = 4;
+constexpr int P_MAX_LANES = 8;
 
 struct Prover {
     PShape sh;
@@ -1008,7 +1008,7 @@ int cpg_prover_set_transcript(void* handle, int mode) {
 }
 int cpg_prover_set_lanes(void* handle, int nlanes, size_t min_proofs_per_lane) {
     if (!handle) return fail("cpg_prover_set_lanes: null prover");
-    if (nlanes < 1 || nlanes > P_MAX_LANES) return fail("cpg_prover_set_lanes: 1..4 lanes");
+    if (nlanes < 1 || nlanes > P_MAX_LANES) return fail("cpg_prover_set_lanes: 1..8 lanes");
     ((Prover*)handle)->nlanes = nlanes;
     ((Prover*)handle)->lane_min = min_proofs_per_lane ? min_proofs_per_lane : 256;
     return 0;

@@ -199,8 +199,10 @@ int cpg_verifier_set_window(void* verifier, int var_window);
  * few, or large, proofs - a CPU core runs the sequential Keccak chain ~20x faster than one GPU thread),
  * 2 (default) = by batch size */
 int cpg_verifier_set_transcript(void* verifier, int mode);
-/* sub-batches in flight on separate CUDA streams (1..8, default 4; device transcript only); the host stages the wire
- * bytes of sub-batch k + 1 while the GPU works on sub-batch k */
+/* at most this many sub-batches in flight, each on its own set of CUDA streams (1..8, default 8; device transcript only;
+ * a sub-batch holds at least 1024 proofs): the host stages the wire bytes of sub-batch k + 1 while the GPU works on
+ * sub-batch k, the transcript kernels run on high-priority side streams, and every sub-batch's decompression is enqueued
+ * before any MSM check */
 int cpg_verifier_set_streams(void* verifier, int nstreams);
 /* Cross-proof aggregation: `group` (a power of two, default 1 = off) consecutive proofs
  * are accepted by ONE MSM over their group*NV variable bases and ONE fixed-base MSM over their summed
@@ -259,7 +261,7 @@ int cpg_prover_set_window(void* prover, int var_window);
  * prover builds, per batch, a table of the 2^(window-1) multiples of each of them and evaluates those MSMs
  * as table look-ups + Horner instead of the bucket method; 0 = bucket method for every variable-base MSM */
 int cpg_prover_set_table_window(void* prover, int window);
-/* sub-batches ("lanes", 1..4, default 2) whose rounds are issued alternately on separate streams: the
+/* sub-batches ("lanes", 1..8, default 2) whose rounds are issued alternately on separate streams: the
  * one-thread-per-proof transcript kernels of one lane run under the MSM kernels of the other */
 int cpg_prover_set_lanes(void* prover, int nlanes, size_t min_proofs_per_lane /* 0 = 256: smaller batches are not split */);
 /* where a proof's Fiat-Shamir transcript runs (its Fr vector work is always GPU kernels, one thread per element):

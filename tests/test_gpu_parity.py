@@ -170,8 +170,8 @@ def test_verify_batch_cross_proof_groups(gpu_lib, name, copies, group):
         vc.check_batch(gpu_lib, name, copies=2, transcript_on_device=False, group=group)
 
 
-@pytest.mark.parametrize("name,lg,group,streams,copies", [("shuffle_N8_seed1234.json", 12, 1, 0, 3), ("shuffle_N128_seed4096.json", 16, 1, 4, 6),
-                                                          ("shuffle_N128_seed4096.json", 14, 8, 4, 6), ("shuffle_N64_seed2024.json", 16, 1, 1, 3)])
+@pytest.mark.parametrize("name,lg,group,streams,copies", [("shuffle_N8_seed1234.json", 12, 1, 0, 3), ("shuffle_N128_seed4096.json", 16, 1, 4, 36),
+                                                          ("shuffle_N128_seed4096.json", 14, 8, 4, 36), ("shuffle_N64_seed2024.json", 16, 1, 1, 3)])
 def test_tracker_cache_changes_no_verdict(gpu_lib, name, lg, group, streams, copies):
     vc.check_cache(gpu_lib, name, log2_slots=lg, group=group, streams=streams, copies=copies)
     vc.check_cache(gpu_lib, name, log2_slots=lg, transcript_on_device=False, group=group)
