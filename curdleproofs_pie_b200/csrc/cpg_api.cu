@@ -886,22 +886,24 @@ static int msm_fixed_impl(const void* table, const uint8_t* d_scalars, size_t B,
     if (!row_stride) row_stride = t->s.nb;
     Recode rc = make_recode(t->s.c);
     Scratch sc;
-    // few MSMs over many bases (a single large proof): split the bases so that no thread walks thousands of them
+    // few MSMs over many bases (a single large proof): <= 64 bases per thread, then a tree over the partial sums
+    // (fan-in 8) - every stage is a short chain instead of one thread walking hundreds of bases / partials
     uint32_t nchunk = 1;
-    if ((uint64_t)B * t->s.W < 8192 && t->s.nb >= 1024) { nchunk = t->s.nb / 256; if (nchunk > 64) nchunk = 64; }
+    if ((uint64_t)B * t->s.W < 8192 && t->s.nb >= 128) nchunk = (t->s.nb + 63) / 64;
     Xyzz* partial = sc.get<Xyzz>((uint64_t)B * t->s.W * nchunk);
     if (!partial) return fail("cpg_g1_msm_fixed_batched: scratch allocation failed");
 #ifndef CPG_HOST_EMU
     if (g_prof_on && g_d_counters) if (int r = launch(CountNonZero{(const uint32_t*)d_scalars, g_d_counters, t->s.nb, row_stride, row_off}, (uint64_t)B * t->s.nb)) return r;
 #endif
-    if (int r = launch<128, 3>(FixedMsmWindow{t->s, rc, (uint32_t)B, nchunk, t->table, (const uint32_t*)d_scalars, row_stride, row_off, partial}, (((uint64_t)B + 31) / 32) * 32 * t->s.W * nchunk)) return r;
+    const uint64_t nthreads = nchunk > 1 ? (uint64_t)B * t->s.W * nchunk : (((uint64_t)B + 31) / 32) * 32 * t->s.W;
+    if (int r = launch<128, 3>(FixedMsmWindow{t->s, rc, (uint32_t)B, nchunk, t->table, (const uint32_t*)d_scalars, row_stride, row_off, partial}, nthreads)) return r;
     uint32_t np = t->s.W * nchunk;
-    if (np > 256) {                                                      // long partial lists: two stages of short serial sums
-        const uint32_t per = nchunk;                                     // np = W * nchunk: W groups of nchunk
-        Xyzz* stage = sc.get<Xyzz>((uint64_t)B * t->s.W);
+    while (np > (nchunk > 1 ? 8u : 64u)) {
+        const uint32_t per = nchunk > 1 ? 8 : 16, np_out = (np + per - 1) / per;
+        Xyzz* stage = sc.get<Xyzz>((uint64_t)B * np_out);
         if (!stage) return fail("cpg_g1_msm_fixed_batched: scratch allocation failed");
-        if (int r = launch_occ(SumPartials{per, partial, stage}, (uint64_t)B * t->s.W)) return r;
-        partial = stage; np = t->s.W;
+        if (int r = launch_occ(SumPartialsRagged{np, per, np_out, partial, stage}, (uint64_t)B * np_out)) return r;
+        partial = stage; np = np_out;
     }
     return launch_occ(SumWindows{np, partial, (Jac*)d_out, accumulate}, B);
 }

@@ -638,15 +638,21 @@ struct FixedMsmWindow {            // sum_i +-T[i][w][|d|-1] for one (msm, windo
     const uint32_t* scalars;       // [B][row_stride][8]; the table's nb bases take entries row_off .. row_off + nb of every row
     uint64_t row_stride, row_off;
     Xyzz* partial;                 // [B*W*nchunk]
-    // A warp = one window of 32 consecutive MSMs (lane = msm): all lanes walk the same bases of the same
-    // table segment, and callers that order their MSMs by kind (the prover: output-major) give every
+    // Thousands of MSMs (nchunk = 1): a warp = one window of 32 consecutive MSMs (lane = msm) - all lanes walk the same
+    // bases of the same table segment, and callers that order their MSMs by kind (the prover: output-major) give every
     // lane the same pattern of structurally zero coefficients, so the zero skips do not diverge.
+    // A few MSMs over many bases (nchunk > 1: a lone large proof): thread = (msm, window, chunk of <= 64 bases), lanes =
+    // consecutive chunks - with lane = msm a warp would hold ONE working lane and the launch is a pure latency chain.
     CPG_HD void operator()(uint64_t t) const {
-        uint32_t lane = (uint32_t)(t % 32);
-        uint64_t q = t / 32;
-        uint32_t ch = (uint32_t)(q % nchunk), w = (uint32_t)((q / nchunk) % s.W);
-        uint64_t m = (q / ((uint64_t)nchunk * s.W)) * 32 + lane;
-        if (m >= B) return;
+        uint32_t ch, w; uint64_t m;
+        if (nchunk > 1) {
+            ch = (uint32_t)(t % nchunk); w = (uint32_t)((t / nchunk) % s.W); m = t / ((uint64_t)nchunk * s.W);
+        } else {
+            const uint32_t lane = (uint32_t)(t % 32);
+            const uint64_t q = t / 32;
+            ch = 0; w = (uint32_t)(q % s.W); m = (q / s.W) * 32 + lane;
+            if (m >= B) return;
+        }
         const uint32_t per = (s.nb + nchunk - 1) / nchunk;
         const uint32_t i0 = ch * per, i1 = i0 + per < s.nb ? i0 + per : s.nb;
         const uint32_t* ks = scalars + (m * row_stride + row_off) * 8;
@@ -663,6 +669,18 @@ struct FixedMsmWindow {            // sum_i +-T[i][w][|d|-1] for one (msm, windo
             acc = xyzz_add_mixed(acc, cneg(q2, d < 0));
         }
         partial[(m * s.W + w) * nchunk + ch] = acc;
+    }
+};
+struct SumPartialsRagged {         // thread = (msm, group): sum of up to `per` consecutive partials of that MSM's np_in (one level of a reduction tree)
+    static constexpr const char* kName = "SumPartials";
+    uint32_t np_in, per, np_out; const Xyzz* partial; Xyzz* out;
+    CPG_HD void operator()(uint64_t t) const {
+        const uint64_t m = t / np_out; const uint32_t g = (uint32_t)(t % np_out);
+        const uint32_t lo = g * per, hi = lo + per < np_in ? lo + per : np_in;
+        const Xyzz* ps = partial + m * (uint64_t)np_in;
+        Xyzz acc = ps[lo];
+        for (uint32_t k = lo + 1; k < hi; k++) acc = xyzz_add(acc, ps[k]);
+        out[t] = acc;
     }
 };
 struct CountNonZero {              // thread = scalar: *count += 1 for every non-zero one (work model of the table MSMs, profiling only)

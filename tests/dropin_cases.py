@@ -7,6 +7,8 @@ import pytest
 
 GEN_HEX = "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
 G99_HEX = "aa10e1055b14a89cc3261699524998732fddc4f30c76c1057eb83732a01416643eb015a932e4080c86f42e485973d240"
+G2_HEX = "a572cbea904d67468808c8eb50a9450c9721db309128012543902d0ac358a62ae28f75bb8f1c7c42c39a8c5529bf0f4e"   # 2 G, 3 G: Ethereum consensus BLS
+G3_HEX = "89ece308f9d1f0131765212deca99697b112d61f9be9a5f1f3780a51335b3ff981747a0b2ca2179b96d2c0c9024e5224"   # vectors (tests/test_oracle_kat.py)
 CURVE_ORDER = 52435875175126190479447740508185965837690552500527637822603658699938581184513
 
 REQUIRED_G1 = {"__add__", "__sub__", "__neg__", "__mul__", "__eq__", "__ne__", "__radd__", "__rmul__", "__rsub__", "__str__",
@@ -27,6 +29,8 @@ def surface_kats(mod):
     assert G1Point.from_compressed_bytes(cb) == G1Point.from_compressed_bytes_unchecked(cb) == gen
     assert str(gen) == GEN_HEX
     assert bytes((gen * Scalar(99)).to_compressed_bytes()).hex() == G99_HEX
+    assert bytes((gen + gen).to_compressed_bytes()).hex() == G2_HEX and bytes((gen * Scalar(3)).to_compressed_bytes()).hex() == G3_HEX
+    assert G1Point.from_compressed_bytes(bytes.fromhex(G3_HEX)) - G1Point.from_compressed_bytes(bytes.fromhex(G2_HEX)) == gen
     assert bytes(ident.to_compressed_bytes()) == bytes([0xC0]) + bytes(47)
     assert (gen * Scalar(0)) == ident and (ident * Scalar(5)) == ident
     with pytest.raises(TypeError):
