@@ -123,8 +123,10 @@ def trackers_to_input(pre_trackers, post_trackers):
 _CACHE = {}
 
 
-def IsValidWhiskShuffleProofBatch(crs, pre_shuffle_trackers, post_shuffle_trackers, whisk_shuffle_proofs):
-    """crs: object with to_bytes()/vec_G/vec_H (the reference's CurdleproofsCrs) or (crs_bytes, ell)."""
+def IsValidWhiskShuffleProofBatch(crs, pre_shuffle_trackers, post_shuffle_trackers, whisk_shuffle_proofs, cache_log2=None):
+    """crs: object with to_bytes()/vec_G/vec_H (the reference's CurdleproofsCrs) or (crs_bytes, ell).
+    cache_log2: None leaves the (per-CRS, process-wide) verifier's tracker cache as it is (off unless set before);
+    k > 0 gives it 2^k slots (BatchVerifier.set_cache: trackers met in earlier calls are not decompressed again); 0 = off."""
     if isinstance(crs, tuple):
         crs_bytes, ell = crs
         nbl = 4
@@ -134,6 +136,10 @@ def IsValidWhiskShuffleProofBatch(crs, pre_shuffle_trackers, post_shuffle_tracke
     ver = _CACHE.get(key)
     if ver is None:
         ver = _CACHE[key] = BatchVerifier(crs_bytes, ell, nbl)
+        ver._cache_log2 = 0
+    if cache_log2 is not None and int(cache_log2) != ver._cache_log2:
+        ver.set_cache(int(cache_log2))
+        ver._cache_log2 = int(cache_log2)
     inputs = []
     for pre, post in zip(pre_shuffle_trackers, post_shuffle_trackers):
         try:
