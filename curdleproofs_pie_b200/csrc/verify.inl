@@ -81,7 +81,7 @@ struct VBuffers {
     uint64_t nonce;               // per-call counter: identical (proof, lane) pairs do not reuse weights across calls
 };
 
-CPG_HD void verify_phase1(const VShape& sh, const Layout& L, const VBuffers& vb, size_t b) {
+CPG_HD void verify_phase1(const VShape& sh, const Layout& L, const VBuffers& vb, size_t b, uint32_t warp = 0) {
     using namespace cpgh;
     VState& s = vb.st[b];
     const uint32_t ell = sh.ell;
@@ -97,6 +97,7 @@ CPG_HD void verify_phase1(const VShape& sh, const Layout& L, const VBuffers& vb,
     // the STROBE state is worked on in thread-local storage (registers / coalesced local memory) and
     // written back once: per-thread structs in global memory make every byte XOR an uncoalesced RMW
     Transcript tr;
+    tr.s.warp = (uint8_t)warp;
     tr.init("curdleproofs");
     for (uint32_t i = 0; i < 4 * ell; i++) tr.append_point("curdleproofs_step1", row + 48 * (size_t)i);
     const uint8_t* M = row + 48 * (size_t)(4 * ell);
@@ -125,7 +126,7 @@ CPG_HD void verify_phase1(const VShape& sh, const Layout& L, const VBuffers& vb,
     s.tr = tr;
 }
 
-CPG_HD void verify_phase2(const VShape& sh, const Layout& L, const VBuffers& vb, size_t b) {
+CPG_HD void verify_phase2(const VShape& sh, const Layout& L, const VBuffers& vb, size_t b, uint32_t warp = 0) {
     using namespace cpgh;
     VState& s = vb.st[b];
     const uint32_t ell = sh.ell, n = sh.n, lg = sh.lg, NV = sh.NV, NF = sh.NF, NI = sh.NI;
@@ -151,6 +152,7 @@ CPG_HD void verify_phase2(const VShape& sh, const Layout& L, const VBuffers& vb,
     // transcript step for sm_100a - the appended bytes were not the identity's - while the same source was right on the host)
     const uint8_t* INF = CPGH_SEL(INF48);
     Transcript tr = s.tr;
+    tr.s.warp = (uint8_t)warp;
     // grand product -> IPA statement
     HFr beta_l = fr_pow_u64(s.beta_gp, ell), beta_l1 = fr_mul(beta_l, s.beta_gp);
     HFr z = fr_sub(fr_add(fr_mul(s.r_p, beta_l1), fr_mul(s.gprod, beta_l)), fr_one());
@@ -291,21 +293,23 @@ CPG_HD void verify_phase2(const VShape& sh, const Layout& L, const VBuffers& vb,
     fr_to_bytes(vrow + 32 * (size_t)(NV - 1), fr_mul(rho3, alpha_ipa));                                  // D
 }
 
-struct VerifyPhase1 {             // thread = proof
+// thread = proof (warp = 0), or WARP = proof (warp = 1: launched over 32 threads per proof; the 32 lanes run the same
+// code on the same data in lock-step - identical loads, identical stores - and share the Keccak permutations)
+struct VerifyPhase1 {
     static constexpr const char* kName = "VerifyPhase1";
-    VShape sh; Layout L; VBuffers vb; uint64_t b0;
-    CPG_HD void operator()(uint64_t b) const { verify_phase1(sh, L, vb, (size_t)(b0 + b)); }
+    VShape sh; Layout L; VBuffers vb; uint64_t b0; uint32_t warp;
+    CPG_HD void operator()(uint64_t t) const { verify_phase1(sh, L, vb, (size_t)(b0 + (warp ? t / 32 : t)), warp); }
 };
 struct VerifyPhase2 {
     static constexpr const char* kName = "VerifyPhase2";
-    VShape sh; Layout L; VBuffers vb; uint64_t b0;
-    CPG_HD void operator()(uint64_t b) const { verify_phase2(sh, L, vb, (size_t)(b0 + b)); }
+    VShape sh; Layout L; VBuffers vb; uint64_t b0; uint32_t warp;
+    CPG_HD void operator()(uint64_t t) const { verify_phase2(sh, L, vb, (size_t)(b0 + (warp ? t / 32 : t)), warp); }
 };
 
-struct MerlinScript {             // one thread: the whole script (cpg_merlin_script with on_device = 1)
+struct MerlinScript {             // the whole script on one thread (cpg_merlin_script with on_device = 1) or on one warp in lock-step (= 2)
     static constexpr const char* kName = "MerlinScript";
-    const uint8_t* script; size_t len; uint8_t* out; size_t cap; uint64_t* out_len;
-    CPG_HD void operator()(uint64_t) const { *out_len = (uint64_t)cpgh::merlin_run_script(script, len, out, cap); }
+    const uint8_t* script; size_t len; uint8_t* out; size_t cap; uint64_t* out_len; uint32_t warp;
+    CPG_HD void operator()(uint64_t) const { *out_len = (uint64_t)cpgh::merlin_run_script(script, len, out, cap, warp); }
 };
 
 struct VerifyDerived {            // thread = proof: D = gh + B, A' = A + T_1 + U_1, their encodings
@@ -461,7 +465,13 @@ struct Verifier {
     int transcript_mode = 2;      // 0 host threads, 1 one GPU thread per proof, 2 by batch size (cpg_verifier_set_transcript)
     int transcript_on_device = 1; // placement of the batch in flight (begin of cpg_verify_batch)
     // A CPU core runs one proof's Keccak chain ~20x faster than a lone GPU thread; the GPU runs thousands at once.
-    bool device_transcript_for(size_t B) const { return transcript_mode == 1 || (transcript_mode == 2 && B > 16 * (size_t)threads); }
+    // Mode 2 (default): every host thread gets at most one proof -> host; else the device: one WARP per proof while the
+    // batch is a single sub-batch (nothing else to hide the one-thread-per-proof latency behind: phase 1 17.8 -> 9.5 ms at
+    // B = 1024, the step 34.7 -> 30.3 ms), one THREAD per proof from two sub-batches on (the warp form only shares the
+    // Keccak permutations - absorbing and the Fr loops still run on every lane - and costs 32x the issue slots: at
+    // B = 4096 it is slower, 107 vs 70 ms).  Mode 3 forces warp per proof.
+    bool device_transcript_for(size_t B) const { return transcript_mode == 1 || transcript_mode == 3 || (transcript_mode == 2 && B > (size_t)threads); }
+    bool warp_transcript_for(size_t B) const { return transcript_mode == 3 || (transcript_mode == 2 && B <= 1024); }
     std::vector<uint8_t> crs48;   // vec_G | vec_H | H | G_t | G_u | G_sum | H_sum  (n + 5 points)
     Aff* d_crs = nullptr;         // n + 5 affine points
     uint8_t* d_crs48 = nullptr;   // the same as wire bytes (device transcript appends H)
@@ -680,6 +690,11 @@ struct Verifier {
         size_t per = ((B + S - 1) / S + align - 1) / align * align;
         int rc = 0;
         size_t si = 0;
+#ifndef CPG_HOST_EMU
+        const uint32_t wp = warp_transcript_for(B) ? 1u : 0u;
+#else
+        const uint32_t wp = 0;
+#endif
         // rows 1 and 2 of every sub-batch
         for (size_t b0 = 0; b0 < B && !rc; b0 += per, si++) {
             const size_t nb = B - b0 < per ? B - b0 : per, k = si % 8;
@@ -694,7 +709,7 @@ struct Verifier {
 #endif
             if (!rc) {
                 StreamScope tscope(tstreams[k]);
-                rc = launch<64>(VerifyPhase1{sh, L, vb, b0}, nb);
+                rc = launch<64>(VerifyPhase1{sh, L, vb, b0, wp}, wp ? nb * 32 : nb);
 #ifndef CPG_HOST_EMU
                 if (!rc && cudaEventRecord(ev_p1[k], cur()) != cudaSuccess) rc = fail("cpg_verify_batch: event record failed");
 #endif
@@ -704,7 +719,7 @@ struct Verifier {
             if (!rc && cudaStreamWaitEvent(cur(), ev_p1[k], 0) != cudaSuccess) rc = fail("cpg_verify_batch: stream join failed");
 #endif
             if (!rc) rc = device_derive(b0, nb, L);
-            if (!rc) rc = launch<64>(VerifyPhase2{sh, L, vb, b0}, nb);
+            if (!rc) rc = launch<64>(VerifyPhase2{sh, L, vb, b0, wp}, wp ? nb * 32 : nb);
 #ifndef CPG_HOST_EMU
             if (!rc && (cudaEventRecord(ev_p2[k], cur()) != cudaSuccess || cudaStreamWaitEvent(mstreams[k], ev_p2[k], 0) != cudaSuccess)) rc = fail("cpg_verify_batch: stream fork failed");
 #endif
@@ -770,7 +785,8 @@ int cpg_merlin_script(const uint8_t* script, size_t len, int on_device, uint8_t*
         if (!d_sc || !d_out || !d_len) return fail("cpg_merlin_script: scratch allocation failed");
         if (int rc = cpg_h2d(d_sc, script, len)) return rc;
         if (int rc = cpg_sync()) return rc;                                  // pageable source
-        if (int rc = launch(MerlinScript{d_sc, len, d_out, out_cap, d_len}, 1)) return rc;
+        const uint32_t wp = on_device == 2 ? 1u : 0u;
+        if (int rc = launch(MerlinScript{d_sc, len, d_out, out_cap, d_len, wp}, wp ? 32 : 1)) return rc;
         uint64_t g = 0;
         if (int rc = cpg_d2h(&g, d_len, 8)) return rc;
         got = (size_t)g;
@@ -943,7 +959,7 @@ int cpg_verifier_group(const void* handle) { return handle ? (int)((const Verifi
 size_t cpg_verifier_rechecked(const void* handle) { return handle ? ((const Verifier*)handle)->rechecked : 0; }
 int cpg_verifier_set_transcript(void* handle, int mode) {
     if (!handle) return fail("cpg_verifier_set_transcript: null verifier");
-    if (mode < 0 || mode > 2) return fail("cpg_verifier_set_transcript: 0 (host threads), 1 (GPU thread per proof) or 2 (by batch size)");
+    if (mode < 0 || mode > 3) return fail("cpg_verifier_set_transcript: 0 (host threads), 1 (GPU thread per proof), 2 (by batch size) or 3 (GPU warp per proof)");
     ((Verifier*)handle)->transcript_mode = mode;
     return 0;
 }

@@ -321,7 +321,7 @@ class CpgLib:
                 blob += bytes(data)
         out = ctypes.create_string_buffer(cap)
         got = ctypes.c_size_t()
-        self.check(self.c.cpg_merlin_script(bytes(blob), len(blob), 1 if on_device else 0, out, cap, ctypes.byref(got)), "cpg_merlin_script")
+        self.check(self.c.cpg_merlin_script(bytes(blob), len(blob), int(on_device), out, cap, ctypes.byref(got)), "cpg_merlin_script")
         return out.raw[:got.value]
 
     def bench_int_pipe(self, kind, iters):

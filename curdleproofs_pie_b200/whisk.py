@@ -38,9 +38,10 @@ class BatchVerifier:
         self.lib.check(self.lib.c.cpg_verifier_set_window(self.handle, int(c)), "cpg_verifier_set_window")
 
     def set_transcript(self, mode):
-        """True / "device": transcript + coefficients per proof on the GPU; False / "host": on host threads;
-        "auto" (the default): by batch size."""
-        mode = {"host": 0, "device": 1, "auto": 2, True: 1, False: 0}.get(mode, mode)
+        """True / "device": transcript + coefficients per proof on the GPU, one thread per proof; "warp": one warp per
+        proof (shorter, for tens to a few thousand proofs); False / "host": on host threads; "auto" (the default): by
+        batch size."""
+        mode = {"host": 0, "device": 1, "auto": 2, "warp": 3, True: 1, False: 0}.get(mode, mode)
         self.lib.check(self.lib.c.cpg_verifier_set_transcript(self.handle, int(mode)), "cpg_verifier_set_transcript")
 
     def set_streams(self, n):

@@ -162,8 +162,9 @@ int cpg_fr_inverse(const uint8_t* d_a, size_t k, uint8_t* d_out);   /* inverse(0
  * (the two output ops carry no data; n = bytes wanted):
  *   0 STROBE init(data = protocol label)   1 meta_ad(data, more)   2 ad(data, more)   3 prf(n, more) -> n bytes
  *   4 key(data, more)   5 MerlinTranscript(data = label)   6 append_message(label, data)   7 challenge_bytes(label, n)
- * Outputs are concatenated into `out`.  on_device = 1 runs the script in a one-thread kernel, 0 on the calling thread
- * (host-only; needs no cpg_init). */
+ * Outputs are concatenated into `out`.  on_device = 0 runs the script on the calling thread (host-only; needs no
+ * cpg_init), 1 in a one-thread kernel, 2 on one warp in lock-step with the warp-cooperative Keccak permutation (the two
+ * placements the batched verifier uses per proof). */
 int cpg_merlin_script(const uint8_t* script, size_t len, int on_device, uint8_t* out, size_t out_cap, size_t* out_len);
 
 /* stateful host-side form: MerlinTranscript(label) / append_message / challenge_bytes (merlin_transcript.py:6-24);
@@ -194,10 +195,13 @@ int cpg_verifier_free(void* verifier);
 size_t cpg_verifier_proof_bytes(const void* verifier);
 size_t cpg_verifier_input_bytes(const void* verifier);
 int cpg_verifier_set_window(void* verifier, int var_window);
-/* where the Fiat-Shamir transcript + coefficient algebra run: 1 = one proof per GPU thread (only wire bytes cross
- * PCIe: right for thousands of proofs), 0 = on `host_threads` host threads (the reference's placement: right for a
- * few, or large, proofs - a CPU core runs the sequential Keccak chain ~20x faster than one GPU thread),
- * 2 (default) = by batch size */
+/* where the Fiat-Shamir transcript + coefficient algebra run: 0 = on `host_threads` host threads (the reference's
+ * placement: right when every thread gets at most one proof - a CPU core runs the sequential Keccak chain ~20x faster
+ * than one GPU thread); 1 = one proof per GPU THREAD (only wire bytes cross PCIe; fewest issue slots, but a latency of
+ * ~31 ms at n = 128 whatever the batch size: right when other sub-batches' kernels hide it, i.e. thousands of proofs);
+ * 3 = one proof per GPU WARP (the 32 lanes share every Keccak permutation through shuffles; 32x the issue slots: right
+ * for tens to ~1000 proofs); 2 (default) = by batch size: host while every host thread gets at most one proof, warp per
+ * proof up to 1024 proofs, thread per proof beyond */
 int cpg_verifier_set_transcript(void* verifier, int mode);
 /* at most this many sub-batches in flight, each on its own set of CUDA streams (1..8, default 8; device transcript only;
  * a sub-batch holds at least 1024 proofs): the host stages the wire bytes of sub-batch k + 1 while the GPU works on

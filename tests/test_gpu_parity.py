@@ -177,6 +177,26 @@ def test_tracker_cache_changes_no_verdict(gpu_lib, name, lg, group, streams, cop
     vc.check_cache(gpu_lib, name, log2_slots=lg, transcript_on_device=False, group=group)
 
 
+@pytest.mark.parametrize("on_device", [1, 2])
+def test_transcript_kats_on_device(gpu_lib, on_device):
+    """The product's STROBE / Merlin / Keccak in a real kernel - on one thread (1) and on one warp in lock-step with the
+    warp-cooperative permutation (2) - against the reference's known answers (mt/test_merlin.py:18,29,40) and the oracle"""
+    import test_host_transcript as tht
+
+    tht.strobe_conformance(gpu_lib, on_device)
+    tht.merlin_simple(gpu_lib, on_device)
+    for seed in range(6):
+        tht.merlin_random_scripts(gpu_lib, on_device, seed, rounds=20)
+
+
+@pytest.mark.parametrize("name,copies,group", [("shuffle_N8_seed1234.json", 1, 1), ("shuffle_N16_seed77.json", 3, 2), ("shuffle_N64_seed2024.json", 2, 1),
+                                               ("shuffle_N128_seed4096.json", 20, 1), ("shuffle_N128_seed4096.json", 40, 8)])
+def test_verify_batch_warp_per_proof_transcript(gpu_lib, name, copies, group):
+    """cpg_verifier_set_transcript(3): one WARP per proof (what mode 2 picks for tens to a few thousand proofs)"""
+    vc.check_batch(gpu_lib, name, copies=copies, transcript_on_device="warp", group=group)
+    vc.check_cache(gpu_lib, name, log2_slots=14, transcript_on_device="warp", group=group)
+
+
 def test_verify_replay_matches(gpu_lib):
     import ctypes
 
