@@ -17,11 +17,91 @@ every IPA/SameMSM fold and every commitment of the reference becomes a real MSM 
 the reference's code.  Group elements are never computed on the host: the only host arithmetic
 is the Fr bookkeeping of the coefficients k_i (Python ints mod r), as SURVEY 8b assigns.
 Results are canonical (affine, fully reduced), so bytes and equality match arkworks exactly.
+
+Observation is BATCHED over everything that is pending.  The reference observes its points one at a time
+(``transcript.append(point_projective_to_bytes(P))`` per point, cp/curdleproofs.py:100-125, cp/same_msm.py:60-70 ...),
+and a lone scalar multiplication on a GPU is a latency chain of 255 dependent doublings (~2 ms whatever the batch size).
+So the first observation of ANY lazy point evaluates every lazy point that is still alive (a weak registry; loop
+temporaries of ``compute_MSM`` die at once and are never evaluated) in one launch sequence - scalar multiples through
+cpg_g1_mul, longer combinations through cpg_g1_msm_batched per size class - and converts, compresses and downloads them
+together: n = 128 ``CurdleProofsProof.new`` makes ~25 launch sequences instead of ~550.  Early evaluation cannot change a
+value: leaves are immutable and a combination is a pure function of them.
+
+Encodings met before are not decompressed again: a bounded host-side map  48-byte encoding -> affine bytes  is filled by
+every decompression and every compression (cp/msm_accumulator.py:65 decodes, per verification, ~620 bases the very
+process encoded a moment earlier; Whisk's pre-shuffle trackers are an earlier shuffle's post-shuffle trackers).  An
+entry remembers whether the subgroup check was run, and ``from_compressed_bytes`` (checked) only trusts checked ones.
 """
+import weakref as _weakref
+
 from curdleproofs_pie_b200 import runtime as _rt
 
 _R = _rt.R_ORDER
 _ZERO_AFF = bytes(_rt.AFF)
+_INF48 = bytes([0xC0]) + bytes(47)
+
+_pending = _weakref.WeakValueDictionary()      # id -> lazy point nobody has observed yet (G1Point is unhashable, like the wheel's)
+_BATCH_MAX_TERMS = 1024            # a pending combination longer than this waits for its own observation
+_BATCH_MAX_POINTS = 1 << 14
+_decoded = {}                      # 48-byte encoding -> (affine bytes, subgroup-checked)
+_DECODED_MAX = 1 << 17             # ~25 MB of host memory; emptied when full
+_SIZE_CLASSES = (2, 4, 8, 16, 32, 64, 128, 256, 512, 1024)
+
+
+def _remember(comp, aff, checked):
+    if len(_decoded) >= _DECODED_MAX:
+        _decoded.clear()
+    cur = _decoded.get(comp)
+    if cur is None or (checked and not cur[1]):
+        _decoded[comp] = (aff, checked)
+
+
+def _evaluate(points):
+    """All of `points` (lazy, non-empty) in one launch sequence; fills _aff and _comp of each."""
+    lib = _rt.get_lib()
+    ones = [p for p in points if len(p._terms) == 1]
+    outs = []                      # (list of points, DevBuf of their Jacobian values)
+    if ones:
+        leaves = [next(iter(p._terms.values())) for p in ones]
+        jac = lib.aff_to_jac(lib.upload(b"".join(leaf._aff for leaf, _ in leaves)), len(ones))
+        sc = lib.upload(b"".join(k.to_bytes(32, "little") for _, k in leaves))
+        outs.append((ones, lib.mul(jac, sc, len(ones))))
+    rest = [p for p in points if len(p._terms) > 1]
+    if rest:
+        by_class = {}
+        for p in rest:
+            n = len(p._terms)
+            cls = next((c for c in _SIZE_CLASSES if n <= c), n)
+            by_class.setdefault(cls, []).append(p)
+        zero32 = bytes(32)
+        for cls, grp in by_class.items():
+            if cls > _SIZE_CLASSES[-1] or len(grp) == 1:         # its own length, no padding
+                for p in grp:
+                    leaves = list(p._terms.values())
+                    bases = lib.upload(b"".join(leaf._aff for leaf, _ in leaves))
+                    sc = lib.upload(b"".join(k.to_bytes(32, "little") for _, k in leaves))
+                    outs.append(([p], lib.msm_batched(bases, 0, sc, 1, len(leaves))))
+                continue
+            width = max(len(p._terms) for p in grp)
+            bl, sl = [], []
+            for p in grp:
+                leaves = list(p._terms.values())
+                pad = width - len(leaves)
+                bl.append(b"".join(leaf._aff for leaf, _ in leaves) + _ZERO_AFF * pad)
+                sl.append(b"".join(k.to_bytes(32, "little") for _, k in leaves) + zero32 * pad)
+            bases, sc = lib.upload(b"".join(bl)), lib.upload(b"".join(sl))
+            outs.append((grp, lib.msm_batched(bases, width, sc, len(grp), width)))
+    for grp, jac in outs:
+        k = len(grp)
+        aff = lib.jac_to_aff(jac, k)
+        comp = lib.compress_aff(aff, k)
+        raw = lib.download(aff, k * _rt.AFF)
+        for i, p in enumerate(grp):
+            p._aff = raw[i * _rt.AFF:(i + 1) * _rt.AFF]
+            p._comp = comp[i * 48:(i + 1) * 48]
+            p._terms = None
+            _pending.pop(id(p), None)
+            _remember(p._comp, p._aff, False)
 
 __all__ = ["G1Point", "Scalar"]
 
@@ -133,7 +213,7 @@ class Scalar:
 class G1Point:
     """BLS12-381 G1 element (stub :5-30).  ``G1Point()`` is the generator."""
 
-    __slots__ = ("_aff", "_terms", "_comp")
+    __slots__ = ("_aff", "_terms", "_comp", "__weakref__")
 
     def __init__(self):
         lib = _rt.get_lib()
@@ -157,6 +237,8 @@ class G1Point:
         p._aff = None
         p._terms = terms
         p._comp = None
+        if terms:
+            _pending[id(p)] = p
         return p
 
     @staticmethod
@@ -214,22 +296,18 @@ class G1Point:
 
     __rmul__ = __mul__
 
-    # -- observation: one GPU MSM --
+    # -- observation: one launch sequence for everything pending --
     def _force(self):
         if self._aff is not None:
             return self._aff
-        terms = self._terms
-        n = len(terms)
-        if n == 0:
-            self._aff = _ZERO_AFF
-        else:
-            lib = _rt.get_lib()
-            leaves = list(terms.values())
-            bases = lib.upload(b"".join(leaf._aff for leaf, _ in leaves))
-            scalars = lib.upload(b"".join(k.to_bytes(32, "little") for _, k in leaves))
-            jac = lib.msm_batched(bases, 0, scalars, 1, n)
-            self._aff = lib.download(lib.jac_to_aff(jac, 1), _rt.AFF)
-        self._terms = None
+        if not self._terms:
+            self._aff, self._comp, self._terms = _ZERO_AFF, _INF48, None
+            return self._aff
+        batch = [self]
+        for p in list(_pending.values()):
+            if p is not self and p._aff is None and p._terms and len(p._terms) <= _BATCH_MAX_TERMS and len(batch) < _BATCH_MAX_POINTS:
+                batch.append(p)
+        _evaluate(batch)
         return self._aff
 
     def __eq__(self, o):
@@ -246,9 +324,11 @@ class G1Point:
 
     def to_compressed_bytes(self):
         if self._comp is None:
+            self._force()
+        if self._comp is None:                       # a concrete point that was never encoded (the generator)
             lib = _rt.get_lib()
-            aff = lib.upload(self._force())
-            self._comp = lib.compress_aff(aff, 1)
+            self._comp = lib.compress_aff(lib.upload(self._aff), 1)
+            _remember(self._comp, self._aff, False)
         return self._comp
 
     def __str__(self):
@@ -261,12 +341,18 @@ class G1Point:
         data = bytes(data)
         if len(data) != 48:
             raise ValueError("serialised data seems to be invalid")
+        known = _decoded.get(data)
+        if known is not None and (known[1] or not check):
+            p = G1Point._concrete(known[0])
+            p._comp = data
+            return p
         lib = _rt.get_lib()
         aff, err = lib.decompress(data, check_subgroup=check)
         if err[0]:
             raise ValueError("serialised data seems to be invalid")
         p = G1Point._concrete(lib.download(aff, _rt.AFF))
         p._comp = data
+        _remember(data, p._aff, bool(check))
         return p
 
     @staticmethod

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--case", default="shuffle_N128_seed4096.json")
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--python-merlin", action="store_true", help="keep the reference's own pure-Python merlin_transcripts (0.7 ms per Keccak-f)")
+    ap.add_argument("--stats", action="store_true", help="also report where the time of .new / .verify goes: count and seconds of every observation (MSM by size class), decompression, compression and transcript call of the drop-ins")
     ap.add_argument("--test-seam", action="store_true", help="CPU test tier only: run on the host emulation of the kernels (tests/conftest.py::build_seam)")
     args = ap.parse_args()
     if not os.path.isdir(os.path.join(REF, "curdleproofs")):
@@ -66,8 +67,34 @@ def main():
         case = json.load(f)
     N = case["N"]
     ell = N - N_BLINDERS
+    stats, phase = {}, ["setup"]
+    if args.stats:
+        def timed(owner, name, label, static=False):
+            fn = getattr(owner, name)
+
+            def wrap(*a, **kw):
+                lab = label(*a) if callable(label) else label
+                t0 = time.perf_counter()
+                try:
+                    return fn(*a, **kw)
+                finally:
+                    e = stats.setdefault(phase[0], {}).setdefault(lab, [0, 0.0])
+                    e[0] += 1
+                    e[1] += time.perf_counter() - t0
+            setattr(owner, name, staticmethod(wrap) if static else wrap)
+
+        def force_label(p):
+            if p._aff is not None:
+                return "force(cached)"
+            n = len(p._terms)
+            return "force n=%s" % (n if n <= 2 else "3-8" if n <= 8 else "9-64" if n <= 64 else "65-256" if n <= 256 else ">256")
+        timed(ark.G1Point, "_force", force_label)
+        timed(ark.G1Point, "_decompress", "decompress", static=True)
+        timed(ark.G1Point, "to_compressed_bytes", "to_compressed_bytes (incl. force)")
+        timed(merlin_transcripts.MerlinTranscript, "append_message", "merlin.append_message")
+        timed(merlin_transcripts.MerlinTranscript, "challenge_bytes", "merlin.challenge_bytes")
     launches0 = lib.launch_count()
-    t_new, t_verify, t_whisk_v, t_whisk_p = [], [], [], []
+    t_new, t_verify, t_verify_warm, t_whisk_v, t_whisk_p, t_whisk_v_cold = [], [], [], [], [], []
     for rep in range(args.repeat):
         # the fixture's construction order (oracle/gen_golden.py; cp/test_curdleproofs.py:576-593)
         random.seed(case["seed"])
@@ -78,10 +105,12 @@ def main():
         vec_R = [get_random_point() for _ in range(ell)]
         vec_S = [get_random_point() for _ in range(ell)]
         vec_T, vec_U, M, bl = shuffle_permute_and_commit_input(crs, vec_R, vec_S, perm, k)
+        phase[0] = "new"
         t0 = time.perf_counter()
         proof = CurdleProofsProof.new(crs=crs, vec_R=vec_R, vec_S=vec_S, vec_T=vec_T, vec_U=vec_U, M=M, permutation=perm, k=k, vec_m_blinders=bl)
         wire = proof.to_bytes()
         t_new.append(time.perf_counter() - t0)
+        phase[0] = "other"
         assert crs.to_bytes().hex() == case["crs"], "CRS bytes differ from the fixture"
         enc = lambda pts: [point_projective_to_bytes(p).hex() for p in pts]  # noqa: E731
         assert enc(vec_T) == case["vec_T"] and enc(vec_U) == case["vec_U"] and point_projective_to_bytes(M).hex() == case["M"], "shuffle outputs differ"
@@ -94,9 +123,18 @@ def main():
             except AssertionError:
                 return False
 
+        # cold: no encoding of this proof is in the drop-in's decode cache (a verifier that never saw these bytes);
+        # warm: the same call again (the inputs and the proof were decoded once already)
+        getattr(ark, "_decoded", {}).clear()
+        phase[0] = "verify"
         t0 = time.perf_counter()
         honest = verdict(vec_R, vec_S, vec_T, vec_U, M)
         t_verify.append(time.perf_counter() - t0)
+        phase[0] = "verify_warm"
+        t0 = time.perf_counter()
+        assert verdict(vec_R, vec_S, vec_T, vec_U, M) == honest
+        t_verify_warm.append(time.perf_counter() - t0)
+        phase[0] = "other"
         got = {"honest": honest, "swap_R_S": verdict(vec_S, vec_R, vec_T, vec_U, M), "swap_T_U": verdict(vec_R, vec_S, vec_U, vec_T, M),
                "wrong_M": verdict(vec_R, vec_S, vec_T, vec_U, M + M), "rotated_T": verdict(vec_R, vec_S, vec_T[1:] + vec_T[:1], vec_U, M)}
         assert got == case["verdicts"], (got, case["verdicts"])
@@ -104,6 +142,11 @@ def main():
         pre = [WhiskTracker(bytes.fromhex(r), bytes.fromhex(s)) for r, s in zip(case["vec_R"], case["vec_S"])]
         post = [WhiskTracker(bytes.fromhex(t), bytes.fromhex(u)) for t, u in zip(case["vec_T"], case["vec_U"])]
         whisk_wire = bytes.fromhex(case["M"]) + wire
+        getattr(ark, "_decoded", {}).clear()
+        t0 = time.perf_counter()
+        ok = IsValidWhiskShuffleProof(crs, pre, post, whisk_wire)
+        t_whisk_v_cold.append(time.perf_counter() - t0)
+        assert ok is True
         t0 = time.perf_counter()
         ok = IsValidWhiskShuffleProof(crs, pre, post, whisk_wire)
         t_whisk_v.append(time.perf_counter() - t0)
@@ -114,12 +157,14 @@ def main():
         t_whisk_p.append(time.perf_counter() - t0)
         assert IsValidWhiskShuffleProof(crs, pre, post2, wire2) is True
     lib.sync()
-    print(json.dumps({
+    extra = {"stats": {ph: {k: [v[0], round(v[1], 4)] for k, v in sorted(d.items(), key=lambda kv: -kv[1][1])} for ph, d in stats.items()}} if args.stats else {}
+    print(json.dumps({**extra, 
         "what": "the UNMODIFIED reference (baseline/_ref) on the B200 drop-in; proof bytes and 5 verdicts equal tests/golden/%s" % args.case,
         "n": N, "merlin": "reference pure-Python" if args.python_merlin else "dropin/merlin_transcripts (libcpg.so STROBE/Keccak)",
         "merlin_module": os.path.relpath(merlin_transcripts.__file__, ROOT),
-        "CurdleProofsProof_new_s": min(t_new), "CurdleProofsProof_verify_s": min(t_verify),
-        "IsValidWhiskShuffleProof_s": min(t_whisk_v), "GenerateWhiskShuffleProof_s": min(t_whisk_p),
+        "CurdleProofsProof_new_s": min(t_new), "CurdleProofsProof_verify_s": min(t_verify), "CurdleProofsProof_verify_warm_s": min(t_verify_warm),
+        "IsValidWhiskShuffleProof_s": min(t_whisk_v_cold), "IsValidWhiskShuffleProof_warm_s": min(t_whisk_v),
+        "cache_note": "verify / IsValid: the drop-in's encoding -> point map emptied before the call (all 4 ell trackers and the proof's points are decompressed on the GPU); _warm: the same call again", "GenerateWhiskShuffleProof_s": min(t_whisk_p),
         "repeat": args.repeat, "gpu_launches": lib.launch_count() - launches0, "backend": lib.backend}))
 
 
