@@ -104,7 +104,10 @@ CPG_HD void mul_wide(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
 }
 
 // r = a * b / 2^(32N) mod p, all operands < p, result < p.  r may alias a or b.
-template <int N>
+// LAZY = true leaves out the final conditional subtraction: for p < 2^(32N-3) (Fq) operands < 2p give
+// t = (ab + mp) / R < p (4p/R + 1) < 1.41 p and every interleaved partial sum stays < 3p < 2^(32N), so a chain of
+// products / squarings can run on values in [0, 2p) and reduce ONCE at its end (reduce_once_n).
+template <int N, bool LAZY = false>
 CPG_HD void mont_mul_n(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* p, uint32_t inv) {
     uint32_t e[N], o[N];
 #pragma unroll
@@ -129,6 +132,11 @@ CPG_HD void mont_mul_n(uint32_t* r, const uint32_t* a, const uint32_t* b, const 
 #pragma unroll
     for (int j = 1; j < N - 1; j++) t[j] = addc_cc(o[j + 1], e[j]);
     t[N - 1] = addc(e[N - 1], 0);
+    if (LAZY) {
+#pragma unroll
+        for (int j = 0; j < N; j++) r[j] = t[j];
+        return;
+    }
     // t < 2p: one conditional subtraction
     uint32_t s[N];
     s[0] = sub_cc(t[0], p[0]);
@@ -215,7 +223,9 @@ struct SqrSteps<N, N> {
     static CPG_HD void run(uint32_t*, uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t) {}
 };
 // r = a * a / 2^(32N) mod p, a < p < 2^(32N-3), result < p.  r may alias a.
-template <int N>
+// LAZY = true: a < 2p allowed (d = 2a < 4p < 2^(32N-1) is still exact, the look-ahead partial sums are < 2a + p < 5p
+// < 2^(32N)), no final subtraction, result < 1.41 p.
+template <int N, bool LAZY = false>
 CPG_HD void mont_sqr_n(uint32_t* r, const uint32_t* a, const uint32_t* p, uint32_t inv) {
     uint32_t d[N];
     d[0] = a[0] << 1;
@@ -241,6 +251,22 @@ CPG_HD void mont_sqr_n(uint32_t* r, const uint32_t* a, const uint32_t* p, uint32
 #pragma unroll
     for (int j = 1; j < N - 1; j++) t[j] = addc_cc(o[j + 1], e[j]);
     t[N - 1] = addc(e[N - 1], 0);
+    if (LAZY) {
+#pragma unroll
+        for (int j = 0; j < N; j++) r[j] = t[j];
+        return;
+    }
+    uint32_t s[N];
+    s[0] = sub_cc(t[0], p[0]);
+#pragma unroll
+    for (int j = 1; j < N; j++) s[j] = subc_cc(t[j], p[j]);
+    uint32_t borrow = subc(0, 0);
+#pragma unroll
+    for (int j = 0; j < N; j++) r[j] = borrow ? t[j] : s[j];
+}
+// t in [0, 2p) -> [0, p)
+template <int N>
+CPG_HD void reduce_once_n(uint32_t* r, const uint32_t* t, const uint32_t* p) {
     uint32_t s[N];
     s[0] = sub_cc(t[0], p[0]);
 #pragma unroll

@@ -189,6 +189,13 @@ int launch(const F& f, uint64_t n) {
 bool occ1() { static const bool v = getenv("CPG_OCC1") != nullptr; return v; }
 template <class F>
 int launch_occ(const F& f, uint64_t n) { return occ1() ? launch<128, 1>(f, n) : launch<128, 3>(f, n); }
+// The unchecked Decompress is a chain of 376 squarings + ~100 products on ONE value (the 16-entry window table lives in
+// local memory): 96 registers, 5 resident blocks per SM instead of the 3 of a point addition.  Measured on 4.8 M points
+// (profiles/r02_ab_decomp_occ.txt): 71.2 ms at 168 registers / 3 blocks (when the kernel still carried the subgroup
+// check's code), 68.4 at 108 / 4, 67.4 at 96 / 5, 67.5 at 80 / 6, 67.7 at 64 / 8.  CPG_DECOMP_MINB=3 keeps the old launch.
+int decomp_minb() { static const int v = getenv("CPG_DECOMP_MINB") ? atoi(getenv("CPG_DECOMP_MINB")) : 5; return v; }
+template <class F>
+int launch_decomp(const F& f, uint64_t n) { return decomp_minb() == 5 ? launch<128, 5>(f, n) : launch_occ(f, n); }
 int launch_sort_digits(const SortDigits& f, uint64_t n) {
     const MsmShape& s = f.s;
     size_t smem = (size_t)(s.NB + 1) * SORT_BLOCK * 4 + (size_t)s.NB * SORT_BLOCK * 2;
@@ -243,6 +250,8 @@ int launch(const F& f, uint64_t n) {
 }
 template <class F>
 int launch_occ(const F& f, uint64_t n) { return launch(f, n); }
+template <class F>
+int launch_decomp(const F& f, uint64_t n) { return launch(f, n); }
 int launch_sort_digits(const SortDigits& f, uint64_t n) { return launch(f, n); }
 int launch_bucket_affine(const BucketAccumulateAffine& f, uint64_t n) { return launch(f, n); }
 int launch_horner_jac(const HornerJac& f, uint64_t n) { return launch(f, n); }
@@ -572,7 +581,8 @@ int cpg_profile_report(char* buf, size_t cap) {
 /* ---- serialisation ---- */
 int cpg_g1_decompress(const uint8_t* d_in, size_t k, int check, void* d_out, uint8_t* d_err) {
     NEED_INIT();
-    return launch_occ(Decompress{d_in, check, (Aff*)d_out, d_err}, k);
+    if (check) return launch_occ(DecompressChecked{d_in, (Aff*)d_out, d_err}, k);
+    return launch_decomp(Decompress{d_in, (Aff*)d_out, d_err}, k);
 }
 int cpg_g1_compress(const void* d_jac, size_t k, uint8_t* d_out) {
     NEED_INIT();

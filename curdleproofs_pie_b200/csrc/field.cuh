@@ -102,16 +102,35 @@ template <class C> CPG_HD Fp<C> from_mont(const Fp<C>& a) { Fp<C> o = Fp<C>::zer
 // true iff the plain integer a is < p
 template <class C> CPG_HD bool is_canonical(const Fp<C>& a) { return !geq_n<C::N>(a.l, C::p()); }
 
+// Lazy forms for exponentiation chains of Fq (values in [0, 2p), bigint.cuh mont_mul_n<N, true>): LZ = false is the
+// plain product.  Only for fields with three spare bits (FAST_SQR).
+template <bool LZ, class C> CPG_HD Fp<C> mul_lz(const Fp<C>& a, const Fp<C>& b) {
+    if constexpr (!LZ) return mul(a, b);
+    else { Fp<C> r; mont_mul_n<C::N, true>(r.l, a.l, b.l, C::p(), C::INV); return r; }
+}
+template <bool LZ, class C> CPG_HD Fp<C> sqr_n_lz(Fp<C> a, int n) {
+    if constexpr (!LZ) return sqr_n(a, n);
+    else {
+        for (int i = 0; i < n; i++) mont_sqr_n<C::N, true>(a.l, a.l, C::p(), C::INV);
+        return a;
+    }
+}
+template <class C> CPG_HD Fp<C> reduce_once(const Fp<C>& a) { Fp<C> r; reduce_once_n<C::N>(r.l, a.l, C::p()); return r; }
+
 // a^e for a public exponent given as little-endian u32 words: left-to-right sliding window of 5 bits over
 // the 16 odd powers a, a^3 .. a^31.  For the 379-bit sqrt / inversion exponents of Fq that is 376 squarings +
 // 81 products (a fixed 4-bit window needs 105 products).  The exponent is uniform across the warp, so
 // neither the window scan nor the table index diverges.
-template <class C, int EW>
+// LZ = true (Fq only): every intermediate stays in [0, 2p) without its conditional subtraction (24 + 12 of the ~380
+// instructions of a product / squaring, which on B200 do NOT hide under the IMAD.WIDE stream - profiles/r02_pipe_probe.txt),
+// one reduction at the end.
+template <class C, int EW, bool LZ = false>
 CPG_HD Fp<C> pow_public(const Fp<C>& a, const uint32_t (&e)[EW]) {
+    static_assert(!LZ || C::FAST_SQR, "lazy chains need the field's three spare bits");
     Fp<C> tbl[16];
     tbl[0] = a;
-    Fp<C> a2 = sqr(a);
-    for (int i = 1; i < 16; i++) tbl[i] = mul(tbl[i - 1], a2);
+    Fp<C> a2 = sqr_n_lz<LZ>(a, 1);
+    for (int i = 1; i < 16; i++) tbl[i] = mul_lz<LZ>(tbl[i - 1], a2);
     Fp<C> acc = Fp<C>::one();
     bool started = false;
     int i = EW * 32 - 1;
@@ -119,7 +138,7 @@ CPG_HD Fp<C> pow_public(const Fp<C>& a, const uint32_t (&e)[EW]) {
         if (!((e[i >> 5] >> (i & 31)) & 1u)) {                // a run of clear bits: that many squarings in one call
             int z = 1;
             while (i - z >= 0 && !((e[(i - z) >> 5] >> ((i - z) & 31)) & 1u)) z++;
-            if (started) acc = sqr_n(acc, z);
+            if (started) acc = sqr_n_lz<LZ>(acc, z);
             i -= z;
             continue;
         }
@@ -128,14 +147,15 @@ CPG_HD Fp<C> pow_public(const Fp<C>& a, const uint32_t (&e)[EW]) {
         uint32_t v = 0;
         for (int k = 0; k < l; k++) v = (v << 1) | ((e[(i - k) >> 5] >> ((i - k) & 31)) & 1u);
         if (started) {
-            acc = mul(sqr_n(acc, l), tbl[v >> 1]);
+            acc = mul_lz<LZ>(sqr_n_lz<LZ>(acc, l), tbl[v >> 1]);
         } else {
             acc = tbl[v >> 1];
             started = true;
         }
         i -= l;
     }
-    return acc;
+    if constexpr (LZ) return reduce_once(acc);
+    else return acc;
 }
 
 typedef Fp<FqCfg> Fq;
@@ -157,6 +177,14 @@ static __device__ __noinline__ Fq fq_sqr_n_call(Fq a, int n) {
     return a;
 }
 __device__ __forceinline__ Fq sqr_n(Fq a, int n) { return fq_sqr_n_call(a, n); }
+static __device__ __noinline__ Fq fq_mul_lz_call(Fq a, Fq b) { Fq r; mont_mul_n<12, true>(r.l, a.l, b.l, FqCfg::p(), FqCfg::INV); return r; }
+static __device__ __noinline__ Fq fq_sqr_n_lz_call(Fq a, int n) {
+#pragma unroll 1
+    for (int i = 0; i < n; i++) mont_sqr_n<12, true>(a.l, a.l, FqCfg::p(), FqCfg::INV);
+    return a;
+}
+template <> __device__ __forceinline__ Fq mul_lz<true, FqCfg>(const Fq& a, const Fq& b) { return fq_mul_lz_call(a, b); }
+template <> __device__ __forceinline__ Fq sqr_n_lz<true, FqCfg>(Fq a, int n) { return fq_sqr_n_lz_call(a, n); }
 #endif
 
 // Fq inversion, two ways.
@@ -313,7 +341,7 @@ CPG_HD Fq fq_inv(const Fq& a) { return fq_inv_safegcd(a); }
 CPG_HD Fq fq_sqrt_candidate(const Fq& a) {
     const uint32_t e[12] = {0xffffeaabu, 0xee7fbfffu, 0xac54ffffu, 0x07aaffffu, 0x3dac3d89u, 0xd9cc34a8u,
                             0x3ce144afu, 0xd91dd2e1u, 0x90d2eb35u, 0x92c6e9edu, 0x8e5ff9a6u, 0x0680447au};
-    return pow_public<FqCfg, 12>(a, e);
+    return pow_public<FqCfg, 12, true>(a, e);
 }
 CPG_HD Fr fr_inv(const Fr& a) {
     const uint32_t e[8] = {0xffffffffu, 0xfffffffeu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};

@@ -796,12 +796,24 @@ struct VarTableMsmWindow {         // sum_i +-tab[base i of msm m][|d_w| - 1] fo
 };
 
 // ---- element-wise kernels (vector scalar-mul, fold, group law, serialisation) ---------------
+// Two kernels, not a runtime flag: the subgroup check is a scalar multiplication, and merely carrying its code makes the
+// kernel need 168+ registers; the unchecked decoder (every tracker and proof point, cp/util.py:35-36) fits 96.
 struct Decompress {
     static constexpr const char* kName = "Decompress";
-    const uint8_t* in; int check; Aff* out; uint8_t* err;
+    const uint8_t* in; Aff* out; uint8_t* err;
     CPG_HD void operator()(uint64_t t) const {
         Aff a;
-        int e = aff_decompress(in + 48 * t, check != 0, &a);
+        int e = aff_decompress(in + 48 * t, false, &a);
+        out[t] = a;
+        err[t] = (uint8_t)e;
+    }
+};
+struct DecompressChecked {
+    static constexpr const char* kName = "Decompress";
+    const uint8_t* in; Aff* out; uint8_t* err;
+    CPG_HD void operator()(uint64_t t) const {
+        Aff a;
+        int e = aff_decompress(in + 48 * t, true, &a);
         out[t] = a;
         err[t] = (uint8_t)e;
     }

@@ -585,7 +585,7 @@ struct Verifier {
         if (int rc = cpg_memset(cnt, 0, 4)) return rc;
         if (int rc = launch(CacheClaim{pc, sel, id, in, role, ref}, nb * sel.cached)) return rc;
         if (int rc = launch(CacheResolve{pc, sel, id, 1u, sh.NV - 1, in, role, ref, todo, cnt}, nb * (size_t)(sh.NV - 1))) return rc;
-        if (int rc = launch_occ(DecompressList{pc, 1u, sel.cached, sh.NV, (const uint8_t*)in, todo, cnt, role, ref, out, err}, nb * (size_t)(sh.NV - 1))) return rc;
+        if (int rc = launch_decomp(DecompressList{pc, 1u, sel.cached, sh.NV, (const uint8_t*)in, todo, cnt, role, ref, out, err}, nb * (size_t)(sh.NV - 1))) return rc;
         return launch(CacheFill{pc, sel, role, ref, out, err}, nb * sel.cached);
     }
     int device_derive(size_t b0, size_t nb, const Layout& L) {

@@ -75,6 +75,26 @@ def test_inverse_sqrt_montgomery_form(hs):
         assert call(hs, "hs_fr_inv", 32, k * Rr % R) == pow(k, -1, R) * Rr % R
 
 
+def test_lazy_chain_forms(hs):
+    """mont_mul_n / mont_sqr_n with LAZY = true (the square-root chain of Decompress): operands anywhere in [0, 2p),
+    no final subtraction, result congruent to a b / R and below 2p again (in fact < 1.41 p); reduce_once ends a chain.
+    The whole sliding-window exponentiation on top of them equals Python's pow for residues, non-residues and 0."""
+    rng = random.Random(77)
+    Ri = pow(pow(2, 384, P), -1, P)
+    vals = patterns(2 * P, 12, rng, 6000) + [P, P + 1, P - 1, 2 * P - 1, 2 * P - 2]
+    for i, a in enumerate(vals):
+        b = vals[(i * 11 + 5) % len(vals)]
+        m = call(hs, "hs_fq_mul_lazy", 48, a, b)
+        assert m < 2 * P and m % P == a * b * Ri % P
+        q = call(hs, "hs_fq_sqr_lazy", 48, a)
+        assert q < 2 * P and q % P == a * a * Ri % P
+        assert call(hs, "hs_fq_reduce_once", 48, a) == a % P
+    Rq = pow(2, 384, P)
+    for a in patterns(P, 12, rng, 300):
+        want = pow(a * pow(Rq, -1, P) % P, (P + 1) // 4, P) * Rq % P          # a is a Montgomery form
+        assert call(hs, "hs_fq_sqrt", 48, a) == want
+
+
 def test_safegcd_inversion_matches_fermat_and_python(hs):
     """fq_inv is the Bernstein-Yang division-step inversion on signed 30-bit limbs (field.cuh); cross-checked against
     the Fermat exponentiation it replaced and against Python on carry-stressing limb patterns, 0 and the extremes"""
