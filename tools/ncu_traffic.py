@@ -2,7 +2,7 @@
 """DRAM traffic per launch of the kernels in an `ncu --set full` capture -> profiles/r02_ncu_traffic.json, the file
 bench.py's `roofline.traffic` reads (no hard-coded constant).
 
-    python tools/ncu_traffic.py gpurun_out/<capture>.ncu-rep [more.ncu-rep ...] [--units Kernel=N ...]
+    python tools/ncu_traffic.py gpurun_out/<capture>.ncu-rep [more.ncu-rep ...] [--units Kernel=N ...] [--min-ms T]
 
 --units Decompress=2097152 records how many units (points, additions) ONE captured launch processed, so that bench.py can
 scale the measured bytes to the size of its own launches (bytes per unit x its units per launch).
@@ -60,10 +60,12 @@ def read(rep):
 
 
 def main():
-    args, units = [], {}
+    args, units, min_ns = [], {}, 0.0
     it = iter(sys.argv[1:])
     for a in it:
-        if a == "--units":
+        if a == "--min-ms":                  # leave out launches shorter than this (the 1-point self-test of cpg_init)
+            min_ns = float(next(it)) * 1e6
+        elif a == "--units":
             k, v = next(it).split("=")
             units[k] = float(v)
         else:
@@ -71,6 +73,8 @@ def main():
     launches = []
     for rep in args:
         for ent in read(rep):
+            if ent.get("duration_ns", 0.0) < min_ns:
+                continue
             ent["capture"] = os.path.basename(rep)
             launches.append(ent)
     agg = {}
