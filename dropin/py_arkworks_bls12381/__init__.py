@@ -31,7 +31,18 @@ Encodings met before are not decompressed again: a bounded host-side map  48-byt
 every decompression and every compression (cp/msm_accumulator.py:65 decodes, per verification, ~620 bases the very
 process encoded a moment earlier; Whisk's pre-shuffle trackers are an earlier shuffle's post-shuffle trackers).  An
 entry remembers whether the subgroup check was run, and ``from_compressed_bytes`` (checked) only trusts checked ones.
+
+Deferred decoding (OPT-IN: ``defer_decoding(True)`` or CPG_DROPIN_DEFER_DECODE=1).  The reference decodes one point per
+call (cp/whisk_interface.py:96-100: 4 ell trackers, then the proof's points), and one point on a GPU is the latency of a
+single thread's 457-product square-root chain (0.46 ms): 715 such calls are 0.33 s of a 0.35 s ``.verify``.  With
+deferral on, ``from_compressed_bytes[_unchecked]`` only records the 48 bytes; the first point whose VALUE is needed
+decodes everything recorded so far in one launch.  The price is where a malformed encoding is reported: the same
+``ValueError``, but raised by the first use of that point (arithmetic that gets observed, ``==``,
+``to_compressed_bytes``) instead of by the decoding call - a point that is decoded and never used raises nothing.
+``IsValidWhiskShuffleProof`` turns any exception into ``False`` (cp/whisk_interface.py:84-87), so its verdicts do not
+change; the default stays eager, the wheel's exact behaviour.
 """
+import os as _os
 import weakref as _weakref
 
 from curdleproofs_pie_b200 import runtime as _rt
@@ -46,6 +57,48 @@ _BATCH_MAX_POINTS = 1 << 14
 _decoded = {}                      # 48-byte encoding -> (affine bytes, subgroup-checked)
 _DECODED_MAX = 1 << 17             # ~25 MB of host memory; emptied when full
 _SIZE_CLASSES = (2, 4, 8, 16, 32, 64, 128, 256, 512, 1024)
+_undecoded = _weakref.WeakValueDictionary()    # id -> point whose 48 bytes are recorded but not decoded yet
+_defer = _os.environ.get("CPG_DROPIN_DEFER_DECODE", "") not in ("", "0")
+_BAD = -1                          # G1Point._dec: None = nothing pending, 0 / 1 = decode pending (subgroup check flag), _BAD = malformed
+_INVALID = "serialised data seems to be invalid"
+
+
+def defer_decoding(on=True):
+    """Switch deferred decoding (module docstring) on or off; returns the previous setting."""
+    global _defer
+    prev, _defer = _defer, bool(on)
+    return prev
+
+
+def _flush_decodes():
+    """Decode every recorded encoding in one launch per check flag; malformed ones are marked, not raised here."""
+    if not _undecoded:
+        return
+    lib = _rt.get_lib()
+    todo = [p for p in list(_undecoded.values()) if p._aff is None and p._dec in (0, 1)]
+    _undecoded.clear()
+    for flag in (0, 1):
+        grp = [p for p in todo if p._dec == flag]
+        if not grp:
+            continue
+        aff, err = lib.decompress(b"".join(p._comp for p in grp), check_subgroup=bool(flag))
+        raw = lib.download(aff, len(grp) * _rt.AFF)
+        for i, p in enumerate(grp):
+            if err[i]:
+                p._dec = _BAD
+            else:
+                p._aff, p._dec = raw[i * _rt.AFF:(i + 1) * _rt.AFF], None
+                _remember(p._comp, p._aff, bool(flag))
+
+
+def _value(p):
+    """Affine bytes of a concrete (possibly not yet decoded) point."""
+    if p._aff is None:
+        if p._dec in (0, 1):
+            _flush_decodes()
+        if p._dec == _BAD:
+            raise ValueError(_INVALID)
+    return p._aff
 
 
 def _remember(comp, aff, checked):
@@ -59,6 +112,10 @@ def _remember(comp, aff, checked):
 def _evaluate(points):
     """All of `points` (lazy, non-empty) in one launch sequence; fills _aff and _comp of each."""
     lib = _rt.get_lib()
+    for p in points:
+        for leaf, _ in p._terms.values():
+            if leaf._aff is None:
+                _value(leaf)                                        # decodes everything recorded; raises for a malformed leaf
     ones = [p for p in points if len(p._terms) == 1]
     outs = []                      # (list of points, DevBuf of their Jacobian values)
     if ones:
@@ -213,7 +270,7 @@ class Scalar:
 class G1Point:
     """BLS12-381 G1 element (stub :5-30).  ``G1Point()`` is the generator."""
 
-    __slots__ = ("_aff", "_terms", "_comp", "__weakref__")
+    __slots__ = ("_aff", "_terms", "_comp", "_dec", "__weakref__")
 
     def __init__(self):
         lib = _rt.get_lib()
@@ -221,6 +278,7 @@ class G1Point:
         self._aff = lib.download(aff, _rt.AFF)
         self._terms = None
         self._comp = None
+        self._dec = None
 
     # -- construction helpers --
     @staticmethod
@@ -229,6 +287,7 @@ class G1Point:
         p._aff = aff_bytes
         p._terms = None
         p._comp = None
+        p._dec = None
         return p
 
     @staticmethod
@@ -237,6 +296,7 @@ class G1Point:
         p._aff = None
         p._terms = terms
         p._comp = None
+        p._dec = None
         if terms:
             _pending[id(p)] = p
         return p
@@ -249,6 +309,8 @@ class G1Point:
         """{id(leaf): (leaf, coefficient)} view of this point."""
         if self._aff is not None:
             return {} if self._aff == _ZERO_AFF else {id(self): (self, 1)}
+        if self._dec is not None:                    # recorded, not decoded: never the identity (that encoding is decoded at once)
+            return {id(self): (self, 1)}
         return self._terms
 
     # -- lazy group law --
@@ -300,12 +362,14 @@ class G1Point:
     def _force(self):
         if self._aff is not None:
             return self._aff
+        if self._dec is not None:
+            return _value(self)
         if not self._terms:
             self._aff, self._comp, self._terms = _ZERO_AFF, _INF48, None
             return self._aff
         batch = [self]
         for p in list(_pending.values()):
-            if p is not self and p._aff is None and p._terms and len(p._terms) <= _BATCH_MAX_TERMS and len(batch) < _BATCH_MAX_POINTS:
+            if p is not self and p._aff is None and p._dec is None and p._terms and len(p._terms) <= _BATCH_MAX_TERMS and len(batch) < _BATCH_MAX_POINTS:
                 batch.append(p)
         _evaluate(batch)
         return self._aff
@@ -323,7 +387,7 @@ class G1Point:
     __hash__ = None
 
     def to_compressed_bytes(self):
-        if self._comp is None:
+        if self._comp is None or self._dec is not None:
             self._force()
         if self._comp is None:                       # a concrete point that was never encoded (the generator)
             lib = _rt.get_lib()
@@ -340,11 +404,16 @@ class G1Point:
     def _decompress(data, check):
         data = bytes(data)
         if len(data) != 48:
-            raise ValueError("serialised data seems to be invalid")
+            raise ValueError(_INVALID)
         known = _decoded.get(data)
         if known is not None and (known[1] or not check):
             p = G1Point._concrete(known[0])
             p._comp = data
+            return p
+        if _defer and not (data[0] & 0x40):          # infinity encodings (and their malformed variants) are settled at once
+            p = G1Point._concrete(None)
+            p._comp, p._dec = data, 1 if check else 0
+            _undecoded[id(p)] = p
             return p
         lib = _rt.get_lib()
         aff, err = lib.decompress(data, check_subgroup=check)

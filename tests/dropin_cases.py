@@ -65,3 +65,59 @@ def multiexp_matches_oracle(mod, cref, n, seed=11):
     for p, s in zip(pts, ss):
         acc = acc + p * Scalar(s)
     assert acc == got
+
+
+def deferred_decoding(mod, cref, n=40, seed=21):
+    """Opt-in deferred decoding (dropin docstring): decoding calls only record the bytes, the first use decodes everything
+    recorded in one launch; values, bytes and equality are those of the eager mode, and a malformed encoding raises the
+    same ValueError - at its first use instead of at the decoding call."""
+    from oracle import bls12381_py as bp
+
+    rng = random.Random(seed)
+    G1Point, Scalar = mod.G1Point, mod.Scalar
+    ks = [rng.randrange(1, bp.R) for _ in range(n)]
+    ss = [rng.randrange(bp.R) for _ in range(n)]
+    blobs = cref.mul_batch([cref.generator()] * n, ks)
+    enc = cref.compress_batch(blobs)
+    want = cref.compress(cref.msm(blobs, ss))
+    x_off = next(x for x in range(1, 200) if pow((x**3 + 4) % bp.P, (bp.P - 1) // 2, bp.P) != 1)     # x^3 + 4 a non-residue
+    off_curve = bytes([0x80]) + x_off.to_bytes(48, "big")[1:]
+    getattr(mod, "_decoded", {}).clear()
+    prev = mod.defer_decoding(True)
+    try:
+        launches0 = mod._rt.get_lib().launch_count()
+        pts = [G1Point.from_compressed_bytes_unchecked(e) for e in enc]
+        chk = [G1Point.from_compressed_bytes(e) for e in enc[:5]]
+        assert mod._rt.get_lib().launch_count() == launches0                 # nothing ran yet
+        assert all(p._aff is None for p in pts)
+        got = G1Point.multiexp_unchecked(pts, [Scalar(s) for s in ss])
+        assert bytes(got.to_compressed_bytes()) == want
+        assert all(p._aff is not None for p in pts + chk)                     # one flush decoded every recorded point
+        assert [bytes(p.to_compressed_bytes()) for p in pts] == [bytes(e) for e in enc]
+        assert chk[0] == pts[0] and chk[1] != pts[0]
+        # identity encodings and wrong lengths are settled at once, as in eager mode
+        assert G1Point.from_compressed_bytes_unchecked(bytes([0xC0]) + bytes(47)) == G1Point.identity()
+        with pytest.raises(ValueError):
+            G1Point.from_compressed_bytes_unchecked(bytes([0xC0]) + bytes(46) + b"\x01")
+        with pytest.raises(ValueError):
+            G1Point.from_compressed_bytes_unchecked(bytes(47))
+        # malformed encodings: recorded silently, reported by the first use - and only by uses of THAT point
+        getattr(mod, "_decoded", {}).clear()
+        bad = G1Point.from_compressed_bytes_unchecked(off_curve)
+        good = G1Point.from_compressed_bytes_unchecked(enc[0])
+        assert bytes((good * Scalar(3)).to_compressed_bytes()) == cref.compress(cref.mul_batch([blobs[0]], [3])[0])
+        for use in (lambda: bad.to_compressed_bytes(), lambda: bad == good, lambda: (bad * Scalar(2) + good).to_compressed_bytes()):
+            with pytest.raises(ValueError):
+                use()
+        # a point off the r-order subgroup passes the unchecked decoder and fails the checked one, deferred or not
+        h = next(bytes([0x80]) + x.to_bytes(48, "big")[1:] for x in range(1, 400)
+                 if pow((x**3 + 4) % bp.P, (bp.P - 1) // 2, bp.P) == 1 and x != x_off)
+        G1Point.from_compressed_bytes_unchecked(h).to_compressed_bytes()
+        with pytest.raises(ValueError):
+            G1Point.from_compressed_bytes(h).to_compressed_bytes()
+    finally:
+        mod.defer_decoding(prev)
+    # eager again: the same malformed encoding raises in the decoding call
+    getattr(mod, "_decoded", {}).clear()
+    with pytest.raises(ValueError):
+        G1Point.from_compressed_bytes_unchecked(off_curve)

@@ -29,6 +29,19 @@ def test_multiexp(dropin, cref):
     dc.multiexp_matches_oracle(dropin, cref, 24)
 
 
+def test_deferred_decoding(dropin, cref):
+    dc.deferred_decoding(dropin, cref)
+
+
+def test_verify_verdicts_equal_reference_with_deferred_decoding(dropin):
+    prev = dropin.defer_decoding(True)
+    try:
+        getattr(dropin, "_decoded", {}).clear()
+        sc.check_verify_matches_golden(dropin, sc.load_case("shuffle_N8_seed1234.json"))
+    finally:
+        dropin.defer_decoding(prev)
+
+
 @pytest.mark.parametrize("name", ["shuffle_N8_seed1234.json", "shuffle_N16_seed77.json"])
 def test_prove_bytes_equal_reference(dropin, name):
     sc.check_prove_matches_golden(dropin, sc.load_case(name))

@@ -136,6 +136,10 @@ def test_dropin_surface(dropin):
     dc.surface_kats(dropin)
 
 
+def test_dropin_deferred_decoding(dropin, cref):
+    dc.deferred_decoding(dropin, cref, n=300)
+
+
 def test_dropin_multiexp(dropin, cref):
     dc.multiexp_matches_oracle(dropin, cref, 128)
     dc.multiexp_matches_oracle(dropin, cref, 1024, seed=12)

@@ -42,19 +42,25 @@ def test_reference_replays_golden_on_host_emulation(seam_lib):
 
 
 @pytest.mark.gpu
-def test_reference_replays_golden_n128_on_gpu(gpu_lib):
-    out = _replay(["--case", "shuffle_N128_seed4096.json", "--repeat", "1"], 900)
+@pytest.mark.parametrize("defer", [[], ["--defer-decode"]], ids=["eager-decode", "deferred-decode"])
+def test_reference_replays_golden_n128_on_gpu(gpu_lib, defer):
+    out = _replay(["--case", "shuffle_N128_seed4096.json", "--repeat", "1"] + defer, 900)
     assert out["backend"] == "cuda-sm_100a" and out["gpu_launches"] > 1000 and out["merlin_module"].startswith("dropin")
     print("unmodified reference on the B200 drop-in, n = 128: new %.2f s, verify %.2f s" % (out["CurdleProofsProof_new_s"], out["CurdleProofsProof_verify_s"]))
 
 
 @pytest.mark.gpu
-def test_reference_whole_test_file_on_gpu(gpu_lib):
+@pytest.mark.parametrize("defer", ["", "1"], ids=["eager-decode", "deferred-decode"])
+def test_reference_whole_test_file_on_gpu(gpu_lib, defer):
+    """Both decoding modes of the drop-in: the reference's tests expect no ValueError at a decoding call, so the whole
+    file must pass with deferral on as well (CPG_DROPIN_DEFER_DECODE=1)."""
+    env = _env()
+    env["CPG_DROPIN_DEFER_DECODE"] = defer
     r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider", "--rootdir", "/tmp",
                         os.path.join(REF, "curdleproofs", "test_curdleproofs.py"), os.path.join(REF, "merlin_transcripts", "test_merlin.py"),
                         "-k", "not test_py_arkworks_bls12381_api",
                         "--durations", "0"],
-                       env=_env(), cwd="/tmp", capture_output=True, text=True, timeout=2400)
+                       env=env, cwd="/tmp", capture_output=True, text=True, timeout=2400)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout and "deselected" in r.stdout, tail

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--repeat", type=int, default=2)
     ap.add_argument("--python-merlin", action="store_true", help="keep the reference's own pure-Python merlin_transcripts (0.7 ms per Keccak-f)")
     ap.add_argument("--stats", action="store_true", help="also report where the time of .new / .verify goes: count and seconds of every observation (MSM by size class), decompression, compression and transcript call of the drop-ins")
+    ap.add_argument("--defer-decode", action="store_true", help="drop-in: deferred decoding (from_compressed_bytes* only records the bytes; one batched decode at first use; a malformed encoding raises at its first use instead)")
     ap.add_argument("--test-seam", action="store_true", help="CPU test tier only: run on the host emulation of the kernels (tests/conftest.py::build_seam)")
     args = ap.parse_args()
     if not os.path.isdir(os.path.join(REF, "curdleproofs")):
@@ -54,6 +55,7 @@ def main():
     from curdleproofs_pie_b200 import runtime as rt
 
     lib = rt.get_lib()
+    ark.defer_decoding(args.defer_decode)
     assert lib.backend == ("host-emulation-test-seam" if args.test_seam else "cuda-sm_100a"), lib.backend
     assert os.path.dirname(ark.__file__).startswith(dropin), ark.__file__
     import curdleproofs
@@ -86,6 +88,8 @@ def main():
         def force_label(p):
             if p._aff is not None:
                 return "force(cached)"
+            if getattr(p, "_dec", None) is not None:
+                return "force (flush of the recorded decodes)"
             n = len(p._terms)
             return "force n=%s" % (n if n <= 2 else "3-8" if n <= 8 else "9-64" if n <= 64 else "65-256" if n <= 256 else ">256")
         timed(ark.G1Point, "_force", force_label)
@@ -165,7 +169,7 @@ def main():
         "CurdleProofsProof_new_s": min(t_new), "CurdleProofsProof_verify_s": min(t_verify), "CurdleProofsProof_verify_warm_s": min(t_verify_warm),
         "IsValidWhiskShuffleProof_s": min(t_whisk_v_cold), "IsValidWhiskShuffleProof_warm_s": min(t_whisk_v),
         "cache_note": "verify / IsValid: the drop-in's encoding -> point map emptied before the call (all 4 ell trackers and the proof's points are decompressed on the GPU); _warm: the same call again", "GenerateWhiskShuffleProof_s": min(t_whisk_p),
-        "repeat": args.repeat, "gpu_launches": lib.launch_count() - launches0, "backend": lib.backend}))
+        "deferred_decoding": bool(args.defer_decode), "repeat": args.repeat, "gpu_launches": lib.launch_count() - launches0, "backend": lib.backend}))
 
 
 if __name__ == "__main__":
