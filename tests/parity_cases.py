@@ -37,6 +37,29 @@ def edge_scalars(rng, k):
     return (base + [rng.randrange(R) for _ in range(max(0, k - len(base)))])[:k]
 
 
+def case_empty(lib, crs_hex, ell):
+    """Zero-length calls through every batch entry point: no launch is needed, nothing is written, nothing fails
+    (the reference's list comprehensions over empty sequences, cp/whisk_interface.py:96-100, simply produce [])."""
+    from curdleproofs_pie_b200 import whisk
+
+    buf, _ = lib.decompress(b"")
+    assert lib.decompress(b"")[1] == []
+    assert lib.compress_jac(lib.alloc(144), 0) == b"" and lib.compress_aff(lib.alloc(96), 0) == b""
+    lib.mul(lib.alloc(144), lib.alloc(32), 0)
+    lib.jac_to_aff(lib.alloc(144), 0)
+    lib.aff_to_jac(lib.alloc(96), 0)
+    lib.add(lib.alloc(144), lib.alloc(144), 0)
+    assert lib.eq(lib.alloc(144), lib.alloc(144), 0) == [] and lib.is_identity(lib.alloc(144), 0) == []
+    crs = bytes.fromhex(crs_hex)
+    ver = whisk.BatchVerifier(crs, ell, lib=lib)
+    assert ver.verify([], []) == [] and ver.verify_raw(b"", b"", 0) == b""
+    ver.close()
+    prover = whisk.BatchProver(crs, ell, lib=lib)
+    assert list(prover.prove_drawn([], random.Random(1))) == []
+    prover.close()
+    lib.sync()
+
+
 def case_roundtrip(lib, cref, k, seed=1):
     rng = random.Random(seed)
     blobs, enc = rand_points(cref, rng, k, with_identity=True)

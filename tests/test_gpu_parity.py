@@ -2,6 +2,7 @@
 (include/cpg.h) and compares compressed bytes with the CPU oracle on the same seeded inputs;
 full-size shapes are covered by size-independent properties (linearity, splitting, round trips).
 Run on a B200: python -m pytest tests -m gpu"""
+import os
 import importlib
 import random
 
@@ -130,6 +131,14 @@ def test_msm_full_size_properties(gpu_lib, cref):
 @pytest.fixture(scope="module")
 def dropin(gpu_lib):
     return importlib.import_module("py_arkworks_bls12381")
+
+
+def test_empty_batches(gpu_lib):
+    import json
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shuffle_N8_seed1234.json")) as f:
+        case = json.load(f)
+    pc.case_empty(gpu_lib, case["crs"], case["N"] - 4)
 
 
 def test_dropin_surface(dropin):

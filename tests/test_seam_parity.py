@@ -1,6 +1,7 @@
 """CPU tier: the kernels' per-thread code (host-emulated, see tests/conftest.py::build_seam) driven
 through the same C ABI and launch logic as on the GPU, checked bit-for-bit against the oracle.
 Sizes are small; the GPU tier (tests/test_gpu_parity.py) repeats the cases at full size."""
+import os
 import pytest
 
 import parity_cases as pc
@@ -46,6 +47,14 @@ def test_msm_both_pipelines(seam_lib, cref, B, n, window, shared, path, accumula
 def test_msm_edges(seam_lib, cref):
     pc.case_msm(seam_lib, cref, 4, 12, 4, shared=False, edge=True)
     pc.case_msm(seam_lib, cref, 3, 12, 3, shared=True, edge=True)
+
+
+def test_empty_batches(seam_lib):
+    import json
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "shuffle_N8_seed1234.json")) as f:
+        case = json.load(f)
+    pc.case_empty(seam_lib, case["crs"], case["N"] - 4)
 
 
 def test_msm_empty(seam_lib, cref):
