@@ -43,6 +43,10 @@ thread_local cudaStream_t t_stream = nullptr;
 thread_local bool t_stream_set = false;
 cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 cudaStream_t cur() { return t_stream_set ? t_stream : g_stream; }
+// hooks of the pipelined single MSM (msm_large_pipelined): the per-term MSM pipeline waits on t_pipe_wait before its first
+// kernel and records t_pipe_signal right after its bucket accumulation
+thread_local cudaEvent_t t_pipe_signal = nullptr;
+thread_local cudaStream_t t_pipe_tail = nullptr;      // high-priority stream the window reduction moves to (pipelined MSM)
 
 int ck(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return 0;
@@ -145,8 +149,11 @@ __global__ void __launch_bounds__(32) k_horner_jac_coop(HornerJac f, uint64_t n_
     if (m >= n_msm) return;
     const int lane = threadIdx.x;
     const Jac* ws = f.wsum + m * (uint64_t)f.W;
-    Jac acc = ws[f.W - 1];
-    for (uint32_t w = f.W - 1; w-- > 0;) {
+    uint32_t w = f.hi();
+    Jac acc;
+    if (f.cont) acc = f.out[m];
+    else acc = ws[--w];
+    while (w-- > f.w_lo) {
         for (uint32_t j = 0; j < f.c; j++) acc = coop_dbl(acc, lane);
         acc = coop_add(acc, ws[w], lane);
     }
@@ -382,6 +389,14 @@ int cpg_init(int device) {
     CK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = ~0ULL;
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    // A block freed on one stream may be handed to an allocation on another stream by making that stream WAIT for the
+    // free (an "internal dependency").  For pipelines that run on several streams at once that wait is a hidden
+    // serialisation.  CPG_POOL_INTERNAL_DEPS=0 forbids it (measured: no effect on the verifier's 24 streams, and the pool then
+    // has to grow - allocation spikes of 10+ ms in the pipelined MSM experiment), so the driver's default stays.
+    if (const char* e = getenv("CPG_POOL_INTERNAL_DEPS")) {
+        int on = atoi(e) != 0;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &on));
+    }
 #endif
     g_device = device;
     // device-resident generator: decompress its wire encoding once
@@ -555,6 +570,18 @@ int cpg_profile_report(char* buf, size_t cap) {
         if (i == agg.size()) agg.push_back(Agg{r.name, 0.0, 0, 0});
         agg[i].ms += ms; agg[i].launches++; agg[i].threads += r.threads;
     }
+    // CPG_PROFILE_TRACE=<file>: also a timeline, one line per launch - name, start and end in ms since the first recorded
+    // launch (event timestamps are comparable across streams): shows what overlaps what
+    if (const char* path = getenv("CPG_PROFILE_TRACE")) {
+        if (FILE* tf = fopen(path, "w")) {
+            for (auto& r : g_prof) {
+                float t0 = 0.f, t1 = 0.f;
+                if (cudaEventElapsedTime(&t0, g_prof[0].a, r.a) != cudaSuccess || cudaEventElapsedTime(&t1, g_prof[0].a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+                fprintf(tf, "%-22s %10.4f %10.4f  %llu threads\n", r.name, t0, t1, (unsigned long long)r.threads);
+            }
+            fclose(tf);
+        }
+    }
     std::string out = "{";
     if (g_d_counters) {
         unsigned long long c[2] = {0, 0};
@@ -702,6 +729,59 @@ int cpg_g1_msm_combine_windows(const void* d_wsums_jac, int window, void* d_out_
     if (window <= 0) return fail("cpg_g1_msm_combine_windows: bad window");
     return launch_horner_jac(HornerJac{windows_for((uint32_t)window), (uint32_t)window, (const Jac*)d_wsums_jac, (Jac*)d_out_jac}, 1);
 }
+#ifndef CPG_HOST_EMU
+// ONE large MSM, pipelined over slices of its windows (top slice first) - EXPERIMENT, off by default (CPG_MSM_SLICES > 1
+// turns it on).  The tail of the plain pipeline is pure latency: 8 reduction levels + the 255 dependent doublings of the
+// Horner pass = 2.6 of the 9.3 ms of an n = 2^20 MSM, during which the GPU is nearly idle.  Here the GPU-filling stages
+// of all slices (digit sort, bucket accumulation) run back to back on one stream, and each slice's level-wise
+// reduction + its segment of the Horner pass run on a second, high-priority stream under the next slice's
+// accumulation.  Results are bit-identical (same window sums, same Horner order) - and it is NOT faster
+// (profiles/r02_ab_msm_pipeline.txt, r02_msm_trace_slices4.txt): the overlap happens, but a latency chain that shares
+// the SMs with 12 accumulating warps each runs 2-3x slower (a reduction level 0.10 -> 0.2-0.7 ms, a Horner segment
+// 0.32 -> 0.87 ms), the per-slice sort costs 0.44 ms four times instead of 0.94 ms once, and the sliced accumulations
+// add up to 6.4 instead of 5.7 ms: n = 2^20 9.36 ms plain, 9.2 ms in 2 slices, 9.8-10.8 in 4, 13-15 in 8.
+int msm_pipe_slices() { static const int v = getenv("CPG_MSM_SLICES") ? atoi(getenv("CPG_MSM_SLICES")) : 1; return v; }
+size_t msm_pipe_min_n() { static const size_t v = getenv("CPG_MSM_PIPE_MIN_N") ? (size_t)atoll(getenv("CPG_MSM_PIPE_MIN_N")) : ((size_t)1 << 18); return v; }
+static int msm_large_pipelined(const void* d_bases, const uint8_t* d_scalars, size_t n, uint32_t c, void* d_out, int slices) {
+    const uint32_t W = windows_for(c), per = (W + (uint32_t)slices - 1) / (uint32_t)slices;
+    thread_local cudaStream_t st_low = nullptr, st_high = nullptr;
+    if (!st_low) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));                       // lo = least, hi = greatest priority
+        CK(cudaStreamCreateWithPriority(&st_low, cudaStreamNonBlocking, lo));
+        CK(cudaStreamCreateWithPriority(&st_high, cudaStreamNonBlocking, hi));
+    }
+    const cudaStream_t main_stream = cur();
+    const bool saved_set = t_stream_set; const cudaStream_t saved = t_stream;
+    Jac* wsum = (Jac*)scratch_alloc((size_t)W * sizeof(Jac));
+    if (!wsum) return fail("cpg_g1_msm_batched: scratch allocation failed");
+    std::vector<cudaEvent_t> evs;
+    auto new_event = [&]() { cudaEvent_t e = nullptr; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); evs.push_back(e); return e; };
+    cudaEvent_t fork = new_event();
+    int rc = ck(cudaEventRecord(fork, main_stream), "cudaEventRecord");
+    if (!rc) rc = ck(cudaStreamWaitEvent(st_low, fork, 0), "cudaStreamWaitEvent");
+    if (!rc) rc = ck(cudaStreamWaitEvent(st_high, fork, 0), "cudaStreamWaitEvent");
+    int k = 0;
+    for (uint32_t w_end = W; w_end > 0 && !rc; k++) {
+        const uint32_t w_begin = w_end > per ? w_end - per : 0;
+        t_stream = st_low; t_stream_set = true;
+        t_pipe_signal = new_event(); t_pipe_tail = st_high;
+        rc = msm_batched_impl(d_bases, 0, nullptr, d_scalars, 1, n, (int)c, wsum + w_begin, w_begin, w_end - w_begin);
+        t_pipe_signal = nullptr; t_pipe_tail = nullptr;
+        t_stream = st_high; t_stream_set = true;                             // (the call left it there after its accumulation)
+        if (!rc) { HornerJac hj{W, c, wsum, (Jac*)d_out}; hj.w_lo = w_begin; hj.w_hi = w_end; hj.cont = k > 0 ? 1u : 0u; rc = launch_horner_jac(hj, 1); }
+        w_end = w_begin;
+    }
+    // join: the caller's stream continues after both
+    cudaEvent_t e_low = new_event(), e_high = new_event();
+    if (cudaEventRecord(e_low, st_low) == cudaSuccess) cudaStreamWaitEvent(main_stream, e_low, 0);
+    if (cudaEventRecord(e_high, st_high) == cudaSuccess) cudaStreamWaitEvent(main_stream, e_high, 0);
+    t_stream = saved; t_stream_set = saved_set;
+    scratch_free(wsum);
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    return rc;
+}
+#endif
 // wn = 0: all windows and the final Horner; wn > 0: only windows [w0, w0+wn), output = their sums (B must be 1)
 // sc_stride / sc_off: the scalar of (msm m, term i) is d_scalars[m*sc_stride + sc_off + i] (sc_stride = 0: rows of n, no offset)
 static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint32_t* d_base_off, const uint8_t* d_scalars,
@@ -726,6 +806,10 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
     s.sc_stride = sc_stride ? sc_stride : n; s.sc_off = sc_off;
     const bool large = few || n > 2048 || s.NB > 256;
     if (g_msm_path == 1 && large) return fail("cpg_g1_msm_batched: the per-window path handles n <= 2048 and windows <= 9 bits");
+#ifndef CPG_HOST_EMU
+    if (B == 1 && !slice && large && !d_base_off && !sc_stride && !sc_off && n >= msm_pipe_min_n() && msm_pipe_slices() > 1 && rc.W >= 2u * (uint32_t)msm_pipe_slices())
+        return msm_large_pipelined(d_bases, d_scalars, n, c, d_out, msm_pipe_slices());
+#endif
     // reduction levels: NB = prod ch_j
     uint32_t nlev = 0; uint8_t lg_ch[16]; uint32_t chs[16];
     size_t lvl_elems = 0;                                          // largest level output, in points per (msm, window)
@@ -823,6 +907,15 @@ static int msm_batched_impl(const void* d_bases, size_t base_stride, const uint3
             if (int r = launch(LenScatter{s, boff, hist, order}, BW * s.NB)) return r;
             if (int r = launch<128, 3>(BucketAccumulate{s, bases, boff, sorted, nullptr, order, BW, buckets}, BW * s.NB)) return r;
         }
+#ifndef CPG_HOST_EMU
+        if (t_pipe_signal && t_pipe_tail) {
+            // pipelined single MSM: everything after the accumulation - and the stream-ordered release of this call's
+            // scratch - continues on the high-priority tail stream; the caller's stream is free for the next slice
+            CK(cudaEventRecord(t_pipe_signal, cur()));
+            CK(cudaStreamWaitEvent(t_pipe_tail, t_pipe_signal, 0));
+            t_stream = t_pipe_tail; t_stream_set = true;
+        }
+#endif
         // level-wise window reduction
         const Xyzz* in = buckets; Xyzz* out = lvA;
         uint32_t len = s.NB;

@@ -521,10 +521,17 @@ struct XyzzToJac {
 struct HornerJac {                 // thread = msm: combine W Jacobian window sums (window-split MSMs)
     static constexpr const char* kName = "HornerJac";
     uint32_t W, c; const Jac* wsum; Jac* out;
+    // a SEGMENT of the pass: windows [w_lo, w_hi) from the top down (w_hi = 0 means W); cont != 0 continues from the
+    // partial result of the windows above, read from out[m] (the pipelined single MSM, cpg_api.cu)
+    uint32_t w_lo = 0, w_hi = 0, cont = 0;
+    CPG_HD uint32_t hi() const { return w_hi ? w_hi : W; }
     CPG_HD void operator()(uint64_t m) const {
         const Jac* ws = wsum + m * (uint64_t)W;
-        Jac acc = ws[W - 1];
-        for (uint32_t w = W - 1; w-- > 0;) {
+        uint32_t w = hi();
+        Jac acc;
+        if (cont) acc = out[m];
+        else acc = ws[--w];
+        while (w-- > w_lo) {
             for (uint32_t j = 0; j < c; j++) acc = jac_dbl(acc);
             acc = jac_add(acc, ws[w]);
         }

@@ -133,6 +133,22 @@ def dropin(gpu_lib):
     return importlib.import_module("py_arkworks_bls12381")
 
 
+def test_msm_pipelined_slices_bit_exact(gpu_lib):
+    """The opt-in pipelined single MSM (CPG_MSM_SLICES window slices on a low- and a high-priority stream, Horner pass in
+    segments that continue from the partial result): same bytes as the oracle (tools/msm_trace.py asserts it)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for slices in ("2", "4"):
+        env = dict(os.environ, CPG_MSM_SLICES=slices, CPG_MSM_PIPE_MIN_N="1")
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "msm_trace.py"), "17", "/tmp/msm_trace_test.txt"], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "timeline in" in r.stdout, (r.stdout + r.stderr)[-1500:]
+        with open("/tmp/msm_trace_test.txt") as f:
+            names = [ln.split()[0] for ln in f if ln.strip()]
+        assert names.count("BucketAccumulate") == int(slices) and names.count("HornerJacCoop") == int(slices), names
+
+
 def test_empty_batches(gpu_lib):
     import json
 
