@@ -390,8 +390,11 @@ void parallel_for(int threads, size_t n, F f) {
     std::atomic<size_t> next{0};
     std::vector<std::thread> pool;
     int nt = (int)std::min<size_t>((size_t)threads, n);
+    // items per grab: 8 for big batches; ONE when there are only a few items per thread (a 16-proof batch on 16 threads
+    // was run by two of them, 8 transcripts each: 3.2 ms instead of 0.4)
+    const size_t grab = std::max<size_t>(1, std::min<size_t>(8, n / ((size_t)nt * 4)));
     for (int t = 0; t < nt; t++)
-        pool.emplace_back([&]() { for (;;) { size_t i = next.fetch_add(8); if (i >= n) break; for (size_t k = i; k < n && k < i + 8; k++) f(k); } });
+        pool.emplace_back([&]() { for (;;) { size_t i = next.fetch_add(grab); if (i >= n) break; for (size_t k = i; k < n && k < i + grab; k++) f(k); } });
     for (auto& th : pool) th.join();
 }
 
@@ -420,6 +423,8 @@ struct Verifier {
 #ifndef CPG_HOST_EMU
     cudaStream_t streams[8] = {}, tstreams[8] = {}, mstreams[8] = {};
     cudaEvent_t stream_done[8] = {}, ev_up[8] = {}, ev_p1[8] = {}, ev_p2[8] = {};
+    cudaStream_t side_stream = nullptr;                    // fixed-base MSM of a small sub-batch, beside its variable-base MSM
+    cudaEvent_t side_fork = nullptr, side_join = nullptr;
 #else
     void *streams[8] = {}, *tstreams[8] = {}, *mstreams[8] = {};
 #endif
@@ -618,9 +623,42 @@ struct Verifier {
             if (int rc = launch_occ(SumRanks{(uint32_t)shard.world, cnt, nb, d_gather, d_var + b0, d_fix + b0}, cnt)) return rc;
             return launch(AddFixedAndTest{d_var + b0, d_fix + b0, d_rej + b0, d_ok + b0}, nb);
         }
-        if (int rc = cpg_g1_msm_batched(d_bases + b0 * sh.NV, sh.NV, d_vs + b0 * sh.NV * 32, nb, sh.NV, var_window, d_var + b0)) return rc;
-        if (int rc = cpg_g1_msm_fixed_batched(table, d_fs + b0 * sh.NF * 32, nb, 0, d_fix + b0)) return rc;
+        if (int rc = beside(nb <= 64,
+                            [&]() { return cpg_g1_msm_fixed_batched(table, d_fs + b0 * sh.NF * 32, nb, 0, d_fix + b0); },
+                            [&]() { return cpg_g1_msm_batched(d_bases + b0 * sh.NV, sh.NV, d_vs + b0 * sh.NV * 32, nb, sh.NV, var_window, d_var + b0); })) return rc;
         return launch(AddFixedAndTest{d_var + b0, d_fix + b0, d_rej + b0, d_ok + b0}, nb);
+    }
+    // fixed() and variable(): the two independent MSMs of a check.  A handful of proofs (one shuffle per block) makes both
+    // latency chains - the 255 doublings of the variable-base Horner pass (1.3 ms) and the CRS table look-ups with their
+    // partial-sum tree (0.75 ms) - so with `small` the fixed-base one runs BESIDE the other on a side stream; big
+    // sub-batches fill the GPU either way and keep the single stream.
+    template <class FX, class VA>
+    int beside(bool small, FX fixed, VA variable) {
+#ifndef CPG_HOST_EMU
+        if (small) {
+            if (!side_stream) {
+                if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&side_fork, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&side_join, cudaEventDisableTiming) != cudaSuccess)
+                    return fail("cpg_verify_batch: stream creation failed");
+            }
+            if (cudaEventRecord(side_fork, cur()) != cudaSuccess || cudaStreamWaitEvent(side_stream, side_fork, 0) != cudaSuccess)
+                return fail("cpg_verify_batch: stream fork failed");
+            int rc = 0;
+            {
+                StreamScope scope(side_stream);
+                rc = fixed();
+            }
+            if (!rc) rc = variable();
+            if (cudaEventRecord(side_join, side_stream) != cudaSuccess || cudaStreamWaitEvent(cur(), side_join, 0) != cudaSuccess)
+                if (!rc) rc = fail("cpg_verify_batch: stream join failed");
+            return rc;
+        }
+#else
+        (void)small;
+#endif
+        if (int rc = variable()) return rc;
+        return fixed();
     }
     // proofs [b0, b0 + nb), b0 a multiple of `group`: whole groups through one aggregated check each
     // (provisional verdicts; recheck_failed_groups settles the failing ones), the tail proof by proof
@@ -628,9 +666,12 @@ struct Verifier {
         const size_t G = cur_group;
         const size_t ng = G > 1 ? nb / G : 0, g0 = G > 1 ? b0 / G : 0;
         if (ng) {
-            if (int rc = cpg_g1_msm_batched(d_bases + b0 * sh.NV, G * sh.NV, d_vs + b0 * sh.NV * 32, ng, G * sh.NV, group_window, d_var + g0)) return rc;
-            if (int rc = launch(GroupSumFixed{(uint32_t)G, sh.NF, d_fs + b0 * sh.NF * 32, d_gfs + g0 * sh.NF * 32}, ng * sh.NF)) return rc;
-            if (int rc = cpg_g1_msm_fixed_batched(table, d_gfs + g0 * sh.NF * 32, ng, 0, d_fix + g0)) return rc;
+            if (int rc = beside(ng <= 64,
+                                [&]() {
+                                    if (int r = launch(GroupSumFixed{(uint32_t)G, sh.NF, d_fs + b0 * sh.NF * 32, d_gfs + g0 * sh.NF * 32}, ng * sh.NF)) return r;
+                                    return cpg_g1_msm_fixed_batched(table, d_gfs + g0 * sh.NF * 32, ng, 0, d_fix + g0);
+                                },
+                                [&]() { return cpg_g1_msm_batched(d_bases + b0 * sh.NV, G * sh.NV, d_vs + b0 * sh.NV * 32, ng, G * sh.NV, group_window, d_var + g0); })) return rc;
             if (int rc = launch(GroupTest{(uint32_t)G, d_var + g0, d_fix + g0, d_rej + b0, d_gok + g0, d_ok + b0}, ng)) return rc;
         }
         // the tail's scratch points share d_var/d_fix with the group results: indices >= b0 + ng*G > g0 + ng
@@ -887,6 +928,8 @@ int cpg_verifier_free(void* handle) {
         for (cudaStream_t st : {v->streams[i], v->tstreams[i], v->mstreams[i]}) if (st) cudaStreamDestroy(st);
         for (cudaEvent_t e : {v->stream_done[i], v->ev_up[i], v->ev_p1[i], v->ev_p2[i]}) if (e) cudaEventDestroy(e);
     }
+    if (v->side_stream) cudaStreamDestroy(v->side_stream);
+    for (cudaEvent_t e : {v->side_fork, v->side_join}) if (e) cudaEventDestroy(e);
 #endif
     cpg_host_free(v->h_wire); cpg_host_free(v->h_psc);
     v->cache_free();
