@@ -583,6 +583,7 @@ bool glv_split(const uint8_t* k32, uint32_t* out) {
 constexpr size_t TAB_CHUNK = 148 * 3 * 128 * 2;   // bases per VarTableBuild launch (bounds the scratch): two full waves of 3 blocks x 148 SMs
 struct ProverLane {
     size_t cap = 0, B = 0;
+    SideLane side;                // a few proofs: the round's fixed-base MSMs beside its variable-base ones (verify.inl)
     uint8_t *d_in48 = nullptr, *d_tu48 = nullptr, *d_k = nullptr, *d_rand = nullptr, *d_outs = nullptr, *d_fs = nullptr, *d_vs = nullptr, *d_proof = nullptr, *d_err = nullptr;
     uint32_t *d_perm = nullptr, *d_off = nullptr; Aff* d_bases = nullptr; HFr* d_vec = nullptr; Jac *d_fix = nullptr, *d_var = nullptr;
     Jac* d_gather = nullptr;      // [world][B * (P_MAX_OUT + P_MAX_VAR)] partial sums of a sharded proof's round
@@ -830,8 +831,10 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
             if (int rc = shard_exchange(sd, p.d_gather, cnt)) return rc;
             if (int rc = launch_occ(SumRanks{(uint32_t)sd.world, cnt, nfix, p.d_gather, p.d_fix, p.d_var}, cnt)) return rc;
         } else {
-        // fixed-base part of every output of the round: B*nout MSMs over the CRS table (rows are output-major)
-        if (int rc = cpg_g1_msm_fixed_batched(pr.table, p.d_fs, B * pl.nout, 0, p.d_fix)) return rc;
+        // fixed-base part of every output of the round: B*nout MSMs over the CRS table (rows are output-major); for a
+        // few proofs (B * nout <= 64 MSMs: both parts are latency chains) beside the variable-base part, not before it
+        auto fixed_part = [&]() { return cpg_g1_msm_fixed_batched(pr.table, p.d_fs, B * pl.nout, 0, p.d_fix); };
+        auto variable_part = [&]() -> int {
         if (pl.nvar) {                                  // variable-base parts: ONE batched MSM over all B*nvar instances
             VarOffsets vo; vo.B = B; vo.ell = ell; vo.off = p.d_off;
             for (uint32_t v = 0; v < P_MAX_VAR; v++) vo.set[v] = v < pl.nvar ? pl.var_set[v] : 0;
@@ -854,6 +857,9 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
                 if (int rc = launch_occ(Horner{hs, partial, p.d_var}, M)) return rc;
             } else if (int rc = cpg_g1_msm_batched_off(p.d_bases, p.d_off, p.d_vs, B * pl.nvar, ell, pr.var_window, p.d_var)) return rc;
         }
+        return 0;
+        };
+        if (int rc = p.side.beside(B * pl.nout <= 64 && pl.nvar != 0, fixed_part, variable_part)) return rc;
         }
         ProveCombine pc;
         pc.nout = pl.nout; pc.NOUT = O.NOUT; pc.B = B; pc.fixed = p.d_fix; pc.var = p.d_var; pc.outs48 = p.d_outs;
@@ -974,7 +980,7 @@ int cpg_prover_free(void* handle) {
     Prover* p = (Prover*)handle;
     p->release();
 #ifndef CPG_HOST_EMU
-    for (ProverLane& L : p->lanes) { if (L.stream) cudaStreamDestroy(L.stream); if (L.done) cudaEventDestroy(L.done); }
+    for (ProverLane& L : p->lanes) { if (L.stream) cudaStreamDestroy(L.stream); if (L.done) cudaEventDestroy(L.done); L.side.destroy(); }
     if (p->fork) cudaEventDestroy(p->fork);
 #endif
     cpg_fixed_table_free(p->table);

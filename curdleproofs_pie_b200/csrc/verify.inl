@@ -411,6 +411,53 @@ struct StreamScope {
 #endif
 };
 
+// A second stream for one of two INDEPENDENT latency chains.  fixed() and variable() are the two MSMs of a check (or of
+// a prover round).  A handful of proofs (one shuffle per block) makes both of them latency chains - the 255 doublings of
+// the variable-base Horner pass (1.3 ms) and the CRS table look-ups with their partial-sum tree (0.75 ms) - so with
+// `small` the fixed-base one runs BESIDE the other on the side stream; big batches fill the GPU either way and keep
+// the single stream.
+struct SideLane {
+#ifndef CPG_HOST_EMU
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    void destroy() {
+        if (stream) cudaStreamDestroy(stream);
+        for (cudaEvent_t e : {fork, join}) if (e) cudaEventDestroy(e);
+        stream = nullptr; fork = join = nullptr;
+    }
+#else
+    void destroy() {}
+#endif
+    template <class FX, class VA>
+    int beside(bool small, FX fixed, VA variable) {
+#ifndef CPG_HOST_EMU
+        if (small) {
+            if (!stream) {
+                if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess)
+                    return fail("side stream creation failed");
+            }
+            if (cudaEventRecord(fork, cur()) != cudaSuccess || cudaStreamWaitEvent(stream, fork, 0) != cudaSuccess)
+                return fail("side stream fork failed");
+            int rc = 0;
+            {
+                StreamScope scope(stream);
+                rc = fixed();
+            }
+            if (!rc) rc = variable();
+            if (cudaEventRecord(join, stream) != cudaSuccess || cudaStreamWaitEvent(cur(), join, 0) != cudaSuccess)
+                if (!rc) rc = fail("side stream join failed");
+            return rc;
+        }
+#else
+        (void)small;
+#endif
+        if (int rc = variable()) return rc;
+        return fixed();
+    }
+};
+
 struct Verifier {
     // Sub-batch k owns three streams.  The transcript phases are one thread per proof: their duration is a LATENCY (a few
     // hundred dependent Keccak permutations), the same for 2048 proofs as for 8192, and they need next to no issue slots.
@@ -423,12 +470,12 @@ struct Verifier {
 #ifndef CPG_HOST_EMU
     cudaStream_t streams[8] = {}, tstreams[8] = {}, mstreams[8] = {};
     cudaEvent_t stream_done[8] = {}, ev_up[8] = {}, ev_p1[8] = {}, ev_p2[8] = {};
-    cudaStream_t side_stream = nullptr;                    // fixed-base MSM of a small sub-batch, beside its variable-base MSM
-    cudaEvent_t side_fork = nullptr, side_join = nullptr;
+
 #else
     void *streams[8] = {}, *tstreams[8] = {}, *mstreams[8] = {};
 #endif
     int nstreams = 8;
+    SideLane side;                 // fixed-base MSM of a small sub-batch, beside its variable-base MSM
     // make the caller's stream wait for every sub-batch (its check stream ends the chain)
     int join_streams(int rc) {
 #ifndef CPG_HOST_EMU
@@ -623,42 +670,10 @@ struct Verifier {
             if (int rc = launch_occ(SumRanks{(uint32_t)shard.world, cnt, nb, d_gather, d_var + b0, d_fix + b0}, cnt)) return rc;
             return launch(AddFixedAndTest{d_var + b0, d_fix + b0, d_rej + b0, d_ok + b0}, nb);
         }
-        if (int rc = beside(nb <= 64,
+        if (int rc = side.beside(nb <= 64,
                             [&]() { return cpg_g1_msm_fixed_batched(table, d_fs + b0 * sh.NF * 32, nb, 0, d_fix + b0); },
                             [&]() { return cpg_g1_msm_batched(d_bases + b0 * sh.NV, sh.NV, d_vs + b0 * sh.NV * 32, nb, sh.NV, var_window, d_var + b0); })) return rc;
         return launch(AddFixedAndTest{d_var + b0, d_fix + b0, d_rej + b0, d_ok + b0}, nb);
-    }
-    // fixed() and variable(): the two independent MSMs of a check.  A handful of proofs (one shuffle per block) makes both
-    // latency chains - the 255 doublings of the variable-base Horner pass (1.3 ms) and the CRS table look-ups with their
-    // partial-sum tree (0.75 ms) - so with `small` the fixed-base one runs BESIDE the other on a side stream; big
-    // sub-batches fill the GPU either way and keep the single stream.
-    template <class FX, class VA>
-    int beside(bool small, FX fixed, VA variable) {
-#ifndef CPG_HOST_EMU
-        if (small) {
-            if (!side_stream) {
-                if (cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&side_fork, cudaEventDisableTiming) != cudaSuccess ||
-                    cudaEventCreateWithFlags(&side_join, cudaEventDisableTiming) != cudaSuccess)
-                    return fail("cpg_verify_batch: stream creation failed");
-            }
-            if (cudaEventRecord(side_fork, cur()) != cudaSuccess || cudaStreamWaitEvent(side_stream, side_fork, 0) != cudaSuccess)
-                return fail("cpg_verify_batch: stream fork failed");
-            int rc = 0;
-            {
-                StreamScope scope(side_stream);
-                rc = fixed();
-            }
-            if (!rc) rc = variable();
-            if (cudaEventRecord(side_join, side_stream) != cudaSuccess || cudaStreamWaitEvent(cur(), side_join, 0) != cudaSuccess)
-                if (!rc) rc = fail("cpg_verify_batch: stream join failed");
-            return rc;
-        }
-#else
-        (void)small;
-#endif
-        if (int rc = variable()) return rc;
-        return fixed();
     }
     // proofs [b0, b0 + nb), b0 a multiple of `group`: whole groups through one aggregated check each
     // (provisional verdicts; recheck_failed_groups settles the failing ones), the tail proof by proof
@@ -666,7 +681,7 @@ struct Verifier {
         const size_t G = cur_group;
         const size_t ng = G > 1 ? nb / G : 0, g0 = G > 1 ? b0 / G : 0;
         if (ng) {
-            if (int rc = beside(ng <= 64,
+            if (int rc = side.beside(ng <= 64,
                                 [&]() {
                                     if (int r = launch(GroupSumFixed{(uint32_t)G, sh.NF, d_fs + b0 * sh.NF * 32, d_gfs + g0 * sh.NF * 32}, ng * sh.NF)) return r;
                                     return cpg_g1_msm_fixed_batched(table, d_gfs + g0 * sh.NF * 32, ng, 0, d_fix + g0);
@@ -928,9 +943,8 @@ int cpg_verifier_free(void* handle) {
         for (cudaStream_t st : {v->streams[i], v->tstreams[i], v->mstreams[i]}) if (st) cudaStreamDestroy(st);
         for (cudaEvent_t e : {v->stream_done[i], v->ev_up[i], v->ev_p1[i], v->ev_p2[i]}) if (e) cudaEventDestroy(e);
     }
-    if (v->side_stream) cudaStreamDestroy(v->side_stream);
-    for (cudaEvent_t e : {v->side_fork, v->side_join}) if (e) cudaEventDestroy(e);
 #endif
+    v->side.destroy();
     cpg_host_free(v->h_wire); cpg_host_free(v->h_psc);
     v->cache_free();
     cpg_fixed_table_free(v->table);
