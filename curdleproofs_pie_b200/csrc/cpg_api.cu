@@ -240,6 +240,20 @@ int launch_horner_jac(const HornerJac& f, uint64_t n) {
     g_launches++;
     return ck(cudaGetLastError(), "kernel launch");
 }
+void* scratch_alloc(size_t bytes);
+void scratch_free(void* p);
+// Horner pass over XYZZ window sums (the table-lookup MSMs of the prover).  Thousands of MSMs: one thread each.  A few
+// MSMs (one proof per call): the 258 dependent doublings of a thread are 2.8 ms per round - the window sums are turned
+// into Jacobian points and the warp-cooperative pass above takes over (1.2 ms).  Same group element either way.
+int launch_horner_xyzz(const MsmShape& hs, const Xyzz* partial, Jac* out, uint64_t M) {
+    if (M > 1024) return launch_occ(Horner{hs, partial, out}, M);
+    Jac* tmp = (Jac*)scratch_alloc(M * hs.W * sizeof(Jac));
+    if (!tmp) return fail("Horner: scratch allocation failed");
+    int rc = launch(XyzzToJac{partial, tmp}, M * hs.W);
+    if (!rc) rc = launch_horner_jac(HornerJac{hs.W, hs.c, tmp, out}, M);
+    scratch_free(tmp);
+    return rc;
+}
 void* scratch_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocAsync(&p, bytes ? bytes : 1, cur()) != cudaSuccess) { cudaGetLastError(); return nullptr; }
@@ -262,6 +276,7 @@ int launch_decomp(const F& f, uint64_t n) { return launch(f, n); }
 int launch_sort_digits(const SortDigits& f, uint64_t n) { return launch(f, n); }
 int launch_bucket_affine(const BucketAccumulateAffine& f, uint64_t n) { return launch(f, n); }
 int launch_horner_jac(const HornerJac& f, uint64_t n) { return launch(f, n); }
+int launch_horner_xyzz(const MsmShape& hs, const Xyzz* partial, Jac* out, uint64_t M) { return launch(Horner{hs, partial, out}, M); }
 void* scratch_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void scratch_free(void* p) { free(p); }
 #endif
@@ -992,7 +1007,8 @@ static int msm_fixed_impl(const void* table, const uint8_t* d_scalars, size_t B,
     // few MSMs over many bases (a single large proof): <= 64 bases per thread, then a tree over the partial sums
     // (fan-in 8) - every stage is a short chain instead of one thread walking hundreds of bases / partials
     uint32_t nchunk = 1;
-    if ((uint64_t)B * t->s.W < 8192 && t->s.nb >= 128) nchunk = (t->s.nb + 63) / 64;
+    // (Whisk-size tables, ~131 bases: chunks of 16 - a chunk of 44 was a 0.43 ms chain in each of the 21 prover rounds)
+    if ((uint64_t)B * t->s.W < 8192 && t->s.nb >= 128) nchunk = t->s.nb >= 1024 ? (t->s.nb + 63) / 64 : (t->s.nb + 15) / 16;
     Xyzz* partial = sc.get<Xyzz>((uint64_t)B * t->s.W * nchunk);
     if (!partial) return fail("cpg_g1_msm_fixed_batched: scratch allocation failed");
 #ifndef CPG_HOST_EMU

@@ -780,16 +780,24 @@ struct VarTableMsmWindow {         // sum_i +-tab[base i of msm m][|d_w| - 1] fo
     uint32_t nb, TS, W; Recode rc; uint32_t B;
     const Aff* table; const uint32_t* tab_off;   // tab_off[m]: first base (in bases, not entries) of msm m's nb consecutive tables
     const uint32_t* scalars;       // [B][nb][8]
-    Xyzz* partial;                 // [B*W]
+    Xyzz* partial;                 // [B*W*nchunk]
+    uint32_t nchunk = 1;           // > 1 (a few MSMs: one proof per call): thread = (msm, window, chunk of the bases), as FixedMsmWindow
     CPG_HD void operator()(uint64_t t) const {
-        uint32_t lane = (uint32_t)(t % 32), w = (uint32_t)((t / 32) % W);
-        uint64_t m = (t / (32ull * W)) * 32 + lane;
+        uint32_t w, ch = 0; uint64_t m;
+        if (nchunk > 1) {
+            ch = (uint32_t)(t % nchunk); w = (uint32_t)((t / nchunk) % W); m = t / ((uint64_t)nchunk * W);
+        } else {
+            const uint32_t lane = (uint32_t)(t % 32);
+            w = (uint32_t)((t / 32) % W); m = (t / (32ull * W)) * 32 + lane;
+        }
         if (m >= B) return;
         const uint32_t* ks = scalars + m * nb * 8;
         const Aff* tab = table + (uint64_t)tab_off[m] * TS;
         Xyzz acc = xyzz_inf();
         uint32_t kp[8];
-        for (uint32_t i = 0; i < nb; i++) {
+        const uint32_t per = (nb + nchunk - 1) / nchunk;
+        const uint32_t i0 = ch * per, i1 = i0 + per < nb ? i0 + per : nb;
+        for (uint32_t i = i0; i < i1; i++) {
             const uint32_t* k = ks + 8 * (uint64_t)i;
             if ((k[0] | k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) == 0) continue;
             recode_add(rc, k, kp);
@@ -798,7 +806,7 @@ struct VarTableMsmWindow {         // sum_i +-tab[base i of msm m][|d_w| - 1] fo
             uint32_t a = (uint32_t)(d < 0 ? -d : d);
             acc = xyzz_add_mixed(acc, cneg(tab[(uint64_t)i * TS + (a - 1)], d < 0));
         }
-        partial[m * W + w] = acc;
+        partial[(m * W + w) * nchunk + ch] = acc;
     }
 };
 

@@ -847,14 +847,24 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
                 Recode rc_ = make_recode(c);
                 const uint64_t M = B * pl.nvar;
                 Scratch sc;
-                Xyzz* partial = sc.get<Xyzz>(M * rc_.W);
+                // a few MSMs (one proof per call): 124 sequential additions per (msm, window) thread are 1.3 ms per round -
+                // the bases are cut into chunks of <= 16 and the chunk sums added by one more short launch
+                const uint32_t nchunk = M * rc_.W < 8192 && ell >= 32 ? (ell + 15) / 16 : 1;
+                Xyzz* partial = sc.get<Xyzz>(M * rc_.W * nchunk);
                 if (!partial) return fail("cpg_prove_batch: scratch allocation failed");
 #ifndef CPG_HOST_EMU
                 if (g_prof_on && g_d_counters) if (int rc = launch(CountNonZero{(const uint32_t*)p.d_vs, g_d_counters + 1, ell, ell, 0}, M * ell)) return rc;
 #endif
-                if (int rc = launch<128, 3>(VarTableMsmWindow{ell, p.tab_ts, rc_.W, rc_, (uint32_t)M, p.d_tab, p.d_off, (const uint32_t*)p.d_vs, partial}, ((M + 31) / 32) * 32 * rc_.W)) return rc;
+                if (int rc = launch<128, 3>(VarTableMsmWindow{ell, p.tab_ts, rc_.W, rc_, (uint32_t)M, p.d_tab, p.d_off, (const uint32_t*)p.d_vs, partial, nchunk},
+                                            nchunk > 1 ? M * rc_.W * nchunk : ((M + 31) / 32) * 32 * rc_.W)) return rc;
+                if (nchunk > 1) {
+                    Xyzz* sums = sc.get<Xyzz>(M * rc_.W);
+                    if (!sums) return fail("cpg_prove_batch: scratch allocation failed");
+                    if (int rc = launch_occ(SumPartialsRagged{rc_.W * nchunk, nchunk, rc_.W, partial, sums}, M * rc_.W)) return rc;
+                    partial = sums;
+                }
                 MsmShape hs; memset(&hs, 0, sizeof hs); hs.W = rc_.W; hs.c = c;
-                if (int rc = launch_occ(Horner{hs, partial, p.d_var}, M)) return rc;
+                if (int rc = launch_horner_xyzz(hs, partial, p.d_var, M)) return rc;
             } else if (int rc = cpg_g1_msm_batched_off(p.d_bases, p.d_off, p.d_vs, B * pl.nvar, ell, pr.var_window, p.d_var)) return rc;
         }
         return 0;
