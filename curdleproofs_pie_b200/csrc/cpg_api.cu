@@ -1008,7 +1008,8 @@ static int msm_fixed_impl(const void* table, const uint8_t* d_scalars, size_t B,
     // (fan-in 8) - every stage is a short chain instead of one thread walking hundreds of bases / partials
     uint32_t nchunk = 1;
     // (Whisk-size tables, ~131 bases: chunks of 16 - a chunk of 44 was a 0.43 ms chain in each of the 21 prover rounds)
-    if ((uint64_t)B * t->s.W < 8192 && t->s.nb >= 128) nchunk = t->s.nb >= 1024 ? (t->s.nb + 63) / 64 : (t->s.nb + 15) / 16;
+    static const uint32_t big_chunk = getenv("CPG_FIXED_CHUNK") ? (uint32_t)atoi(getenv("CPG_FIXED_CHUNK")) : 64;   // bases per thread for tables of >= 1024 bases
+    if ((uint64_t)B * t->s.W < 8192 && t->s.nb >= 128) nchunk = t->s.nb >= 1024 ? (t->s.nb + big_chunk - 1) / big_chunk : (t->s.nb + 15) / 16;
     Xyzz* partial = sc.get<Xyzz>((uint64_t)B * t->s.W * nchunk);
     if (!partial) return fail("cpg_g1_msm_fixed_batched: scratch allocation failed");
 #ifndef CPG_HOST_EMU
