@@ -750,10 +750,20 @@ struct VarTableBuild {             // thread = one base: d * P for d = 1..TS, af
     uint32_t TS; const Aff* bases; uint64_t row_stride, first, count;   // base t = bases[(t / count) * row_stride + first + t % count]
     uint64_t t0;                   // this launch handles bases t0 + u, u < launch size
     Jac* scratch; Fq* pz;          // [launch size][TS] multiples before normalisation / prefix products of their Z
-    Aff* table;                    // [nbases][TS] (out)
+    Aff* table;                    // [nbases][S][TS] (out)
+    // S > 1 (a few proofs per call): S SHIFT GROUPS per base, thread = (base, group s): the multiples of 2^(shift_bits s) P.
+    // The MSM over such a table folds S windows into one (window s Wp + w' looks up group s), so its Horner pass is
+    // Wp = ceil(W / S) windows long instead of W - the dependent doublings that dominate a one-proof call.
+    uint32_t S = 1, shift_bits = 0;
     CPG_HD void operator()(uint64_t u) const {
-        const uint64_t t = t0 + u;
-        const Aff P = bases[(t / count) * row_stride + first + t % count];
+        const uint64_t t = t0 + u, tb = t / S;
+        const uint32_t sg = (uint32_t)(t % S);
+        Aff P = bases[(tb / count) * row_stride + first + tb % count];
+        if (sg) {
+            Jac q = to_jac(P);
+            for (uint32_t k = 0; k < sg * shift_bits; k++) q = jac_dbl(q);
+            P = jac_to_aff(q);
+        }
         Jac* m = scratch + u * TS; Fq* z = pz + u * TS; Aff* out = table + t * TS;
         Jac acc = to_jac(P);
         Fq prod = fq_one();
@@ -782,17 +792,19 @@ struct VarTableMsmWindow {         // sum_i +-tab[base i of msm m][|d_w| - 1] fo
     const uint32_t* scalars;       // [B][nb][8]
     Xyzz* partial;                 // [B*W*nchunk]
     uint32_t nchunk = 1;           // > 1 (a few MSMs: one proof per call): thread = (msm, window, chunk of the bases), as FixedMsmWindow
+    uint32_t S = 1, Wp = 0;        // shift groups of the table (VarTableBuild) and windows per group; Wp = 0 means W (no groups)
     CPG_HD void operator()(uint64_t t) const {
+        const uint32_t WP = Wp ? Wp : W;
         uint32_t w, ch = 0; uint64_t m;
         if (nchunk > 1) {
-            ch = (uint32_t)(t % nchunk); w = (uint32_t)((t / nchunk) % W); m = t / ((uint64_t)nchunk * W);
+            ch = (uint32_t)(t % nchunk); w = (uint32_t)((t / nchunk) % WP); m = t / ((uint64_t)nchunk * WP);
         } else {
             const uint32_t lane = (uint32_t)(t % 32);
-            w = (uint32_t)((t / 32) % W); m = (t / (32ull * W)) * 32 + lane;
+            w = (uint32_t)((t / 32) % WP); m = (t / (32ull * WP)) * 32 + lane;
         }
         if (m >= B) return;
         const uint32_t* ks = scalars + m * nb * 8;
-        const Aff* tab = table + (uint64_t)tab_off[m] * TS;
+        const Aff* tab = table + (uint64_t)tab_off[m] * S * TS;
         Xyzz acc = xyzz_inf();
         uint32_t kp[8];
         const uint32_t per = (nb + nchunk - 1) / nchunk;
@@ -801,12 +813,16 @@ struct VarTableMsmWindow {         // sum_i +-tab[base i of msm m][|d_w| - 1] fo
             const uint32_t* k = ks + 8 * (uint64_t)i;
             if ((k[0] | k[1] | k[2] | k[3] | k[4] | k[5] | k[6] | k[7]) == 0) continue;
             recode_add(rc, k, kp);
-            int d = recode_digit(rc, kp, w);
-            if (!d) continue;
-            uint32_t a = (uint32_t)(d < 0 ? -d : d);
-            acc = xyzz_add_mixed(acc, cneg(tab[(uint64_t)i * TS + (a - 1)], d < 0));
+            for (uint32_t sg = 0; sg < S; sg++) {
+                const uint32_t wf = sg * WP + w;                 // the full-width window this group's entry stands for
+                if (wf >= W) break;
+                int d = recode_digit(rc, kp, wf);
+                if (!d) continue;
+                uint32_t a = (uint32_t)(d < 0 ? -d : d);
+                acc = xyzz_add_mixed(acc, cneg(tab[((uint64_t)i * S + sg) * TS + (a - 1)], d < 0));
+            }
         }
-        partial[(m * W + w) * nchunk + ch] = acc;
+        partial[(m * WP + w) * nchunk + ch] = acc;
     }
 };
 

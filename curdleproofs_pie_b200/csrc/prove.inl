@@ -594,7 +594,8 @@ struct ProverLane {
     uint8_t *h_tu = nullptr, *h_outs = nullptr, *h_proof = nullptr, *h_err = nullptr;   // pinned: results leave per lane
     uint8_t *h_in = nullptr, *h_rand = nullptr;   // pinned staging of the two large inputs (pageable caller memory copies at a third of the rate)
     uint32_t* d_k12 = nullptr;    // [B][8] GLV halves of k
-    Aff* d_tab = nullptr; uint32_t tab_ts = 0;   // multiples 1..tab_ts of every T_i, U_i: [B][2 ell][tab_ts]
+    Aff* d_tab = nullptr; uint32_t tab_ts = 0;   // multiples 1..tab_ts of every T_i, U_i: [B][2 ell][tab_s][tab_ts]
+    uint32_t tab_s = 1;           // shift groups per base (VarTableBuild): 4 for a call of <= 16 proofs, whose rounds are latency chains
     Jac* d_tab_jac = nullptr; Fq* d_tab_pz = nullptr;   // build scratch for TAB_CHUNK bases at a time
 #ifndef CPG_HOST_EMU
     cudaStream_t stream = nullptr; cudaEvent_t done = nullptr;
@@ -616,7 +617,7 @@ struct ProverLane {
         tab_ts = ts;
         d_gather = (Jac*)cpg_malloc(sizeof(Jac) * (world > 1 ? (size_t)world * Bn * (P_MAX_OUT + P_MAX_VAR) : 1));
         d_k12 = (uint32_t*)cpg_malloc(Bn * 32);
-        d_tab = (Aff*)cpg_malloc(sizeof(Aff) * (Bn * 2 * sh.ell * (size_t)ts + 1));
+        d_tab = (Aff*)cpg_malloc(sizeof(Aff) * (std::max<size_t>(Bn, 64) * 2 * sh.ell * (size_t)ts + 1));   // (>= 16 proofs x 4 shift groups)
         d_tab_jac = (Jac*)cpg_malloc(sizeof(Jac) * (TAB_CHUNK * (size_t)ts + 1));
         d_tab_pz = (Fq*)cpg_malloc(sizeof(Fq) * (TAB_CHUNK * (size_t)ts + 1));
         const size_t ell = sh.ell, n = sh.n;
@@ -699,10 +700,14 @@ int prove_lane_prologue(Prover& pr, ProverLane& p) {
     }
     if (int rc = launch(ProveShuffle{ell, p.d_bases, p.d_perm, p.d_k12, p.d_tu48}, B * 2 * (size_t)ell)) return rc;
     if (p.tab_ts) {                                     // multiples of every T_i, U_i (they enter 8 small MSMs each)
-        const size_t nbases = B * 2 * (size_t)ell;
-        for (size_t t0 = 0; t0 < nbases; t0 += TAB_CHUNK) {
-            size_t cnt = nbases - t0 < TAB_CHUNK ? nbases - t0 : TAB_CHUNK;
-            if (int rc = launch_occ(VarTableBuild{p.tab_ts, p.d_bases, 4 * (uint64_t)ell, 2 * (uint64_t)ell, 2 * (uint64_t)ell, t0, p.d_tab_jac, p.d_tab_pz, p.d_tab}, cnt)) return rc;
+        // a call of a few proofs: 4 shift groups per base, so that the Horner pass of the 8 table-MSM rounds is 11 windows
+        // (60 doublings, 0.4 ms) instead of 43 (258 doublings, 1.5 ms) - for the price of a 4x table and 198 doublings here
+        p.tab_s = B <= 16 ? 4 : 1;
+        const uint32_t c = (uint32_t)pr.table_window, Wt = windows_for(c), Wp = (Wt + p.tab_s - 1) / p.tab_s;
+        const size_t nthreads = B * 2 * (size_t)ell * p.tab_s;
+        for (size_t t0 = 0; t0 < nthreads; t0 += TAB_CHUNK) {
+            size_t cnt = nthreads - t0 < TAB_CHUNK ? nthreads - t0 : TAB_CHUNK;
+            if (int rc = launch_occ(VarTableBuild{p.tab_ts, p.d_bases, 4 * (uint64_t)ell, 2 * (uint64_t)ell, 2 * (uint64_t)ell, t0, p.d_tab_jac, p.d_tab_pz, p.d_tab, p.tab_s, c * Wp}, cnt)) return rc;
         }
     }
     return 0;
@@ -848,22 +853,25 @@ int prove_lane_round(Prover& pr, ProverLane& p, uint32_t r) {
                 const uint64_t M = B * pl.nvar;
                 Scratch sc;
                 // a few MSMs (one proof per call): 124 sequential additions per (msm, window) thread are 1.3 ms per round -
-                // the bases are cut into chunks of <= 16 and the chunk sums added by one more short launch
-                const uint32_t nchunk = M * rc_.W < 8192 && ell >= 32 ? (ell + 15) / 16 : 1;
-                Xyzz* partial = sc.get<Xyzz>(M * rc_.W * nchunk);
+                // the bases are cut into chunks and the chunk sums added by one or two more short launches
+                const uint32_t Wp = (rc_.W + p.tab_s - 1) / p.tab_s;          // windows after folding the table's shift groups
+                uint32_t nchunk = 1;                                            // a power of two: ~16 additions per thread
+                if (M * Wp < 8192 && ell >= 32) { const uint32_t want = (ell * p.tab_s + 15) / 16; while (nchunk < want && nchunk < 64) nchunk *= 2; }
+                Xyzz* partial = sc.get<Xyzz>(M * Wp * nchunk);
                 if (!partial) return fail("cpg_prove_batch: scratch allocation failed");
 #ifndef CPG_HOST_EMU
                 if (g_prof_on && g_d_counters) if (int rc = launch(CountNonZero{(const uint32_t*)p.d_vs, g_d_counters + 1, ell, ell, 0}, M * ell)) return rc;
 #endif
-                if (int rc = launch<128, 3>(VarTableMsmWindow{ell, p.tab_ts, rc_.W, rc_, (uint32_t)M, p.d_tab, p.d_off, (const uint32_t*)p.d_vs, partial, nchunk},
-                                            nchunk > 1 ? M * rc_.W * nchunk : ((M + 31) / 32) * 32 * rc_.W)) return rc;
-                if (nchunk > 1) {
-                    Xyzz* sums = sc.get<Xyzz>(M * rc_.W);
+                if (int rc = launch<128, 3>(VarTableMsmWindow{ell, p.tab_ts, rc_.W, rc_, (uint32_t)M, p.d_tab, p.d_off, (const uint32_t*)p.d_vs, partial, nchunk, p.tab_s, Wp},
+                                            nchunk > 1 ? M * Wp * nchunk : ((M + 31) / 32) * 32 * Wp)) return rc;
+                for (uint32_t nc = nchunk; nc > 1;) {                           // chunk sums: a tree of fan-in <= 8 (groups never straddle a window)
+                    const uint32_t per = nc >= 8 ? 8 : nc, nout = nc / per;
+                    Xyzz* sums = sc.get<Xyzz>(M * Wp * nout);
                     if (!sums) return fail("cpg_prove_batch: scratch allocation failed");
-                    if (int rc = launch_occ(SumPartialsRagged{rc_.W * nchunk, nchunk, rc_.W, partial, sums}, M * rc_.W)) return rc;
-                    partial = sums;
+                    if (int rc = launch_occ(SumPartialsRagged{Wp * nc, per, Wp * nout, partial, sums}, M * Wp * nout)) return rc;
+                    partial = sums; nc = nout;
                 }
-                MsmShape hs; memset(&hs, 0, sizeof hs); hs.W = rc_.W; hs.c = c;
+                MsmShape hs; memset(&hs, 0, sizeof hs); hs.W = Wp; hs.c = c;
                 if (int rc = launch_horner_xyzz(hs, partial, p.d_var, M)) return rc;
             } else if (int rc = cpg_g1_msm_batched_off(p.d_bases, p.d_off, p.d_vs, B * pl.nvar, ell, pr.var_window, p.d_var)) return rc;
         }
