@@ -1018,8 +1018,9 @@ static int msm_fixed_impl(const void* table, const uint8_t* d_scalars, size_t B,
     const uint64_t nthreads = nchunk > 1 ? (uint64_t)B * t->s.W * nchunk : (((uint64_t)B + 31) / 32) * 32 * t->s.W;
     if (int r = launch<128, 3>(FixedMsmWindow{t->s, rc, (uint32_t)B, nchunk, t->table, (const uint32_t*)d_scalars, row_stride, row_off, partial}, nthreads)) return r;
     uint32_t np = t->s.W * nchunk;
-    while (np > (nchunk > 1 ? 8u : 64u)) {
-        const uint32_t per = nchunk > 1 ? 8 : 16, np_out = (np + per - 1) / per;
+    const bool few = (uint64_t)B * t->s.W < 8192;           // a few MSMs: every stage a short chain (fan-in 8), also for small tables
+    while (np > (few ? 8u : 64u)) {
+        const uint32_t per = few ? 8 : 16, np_out = (np + per - 1) / per;
         Xyzz* stage = sc.get<Xyzz>((uint64_t)B * np_out);
         if (!stage) return fail("cpg_g1_msm_fixed_batched: scratch allocation failed");
         if (int r = launch_occ(SumPartialsRagged{np, per, np_out, partial, stage}, (uint64_t)B * np_out)) return r;
