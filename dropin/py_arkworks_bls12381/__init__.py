@@ -95,6 +95,7 @@ def _value(p):
     """Affine bytes of a concrete (possibly not yet decoded) point."""
     if p._aff is None:
         if p._dec in (0, 1):
+            _undecoded[id(p)] = p                        # (still pending if an earlier flush was interrupted by an error)
             _flush_decodes()
         if p._dec == _BAD:
             raise ValueError(_INVALID)
