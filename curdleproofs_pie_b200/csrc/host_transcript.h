@@ -153,7 +153,25 @@ struct Strobe128 {
     CPG_HD void absorb(const uint8_t* d, size_t n) {
         while (n) {
             size_t room = RATE - pos, take = n < room ? n : room;
-            for (size_t i = 0; i < take; i++) st.b[pos + i] ^= d[i];
+            size_t i = 0;
+            // 8 source bytes at a time when the source is 8-byte aligned (wire points and scalars are): the word is
+            // XORed into the one or two state words it straddles.  Byte by byte this loop was 17 % of the instructions
+            // of a verifier transcript (28 KB absorbed per proof, ~10 instructions per byte in device code).
+            if ((((uintptr_t)d) & 7) == 0) {
+                for (; i + 8 <= take; i += 8) {
+                    uint64_t v;
+#if defined(__CUDA_ARCH__)
+                    v = *(const uint64_t*)(d + i);
+#else
+                    memcpy(&v, d + i, 8);
+#endif
+                    const size_t p = pos + i;
+                    const unsigned sh = (unsigned)(p & 7) * 8;
+                    st.w[p >> 3] ^= v << sh;
+                    if (sh) st.w[(p >> 3) + 1] ^= v >> (64 - sh);
+                }
+            }
+            for (; i < take; i++) st.b[pos + i] ^= d[i];
             pos += (uint8_t)take; d += take; n -= take;
             if (pos == RATE) run_f();
         }
